@@ -1,0 +1,1162 @@
+// b200gbm engine implementation: network bootstrap, dataset ingestion/binning, GBDT driver and the
+// device-resident leaf-wise tree learner.  See engine.h / kernels.cuh / hist_kernel.cuh.
+#include "engine.h"
+
+#include <arpa/inet.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/select.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <functional>
+#include <cstring>
+#include <numeric>
+#include <thread>
+
+namespace b200gbm {
+
+// =============================================================================== device / network
+static thread_local int t_device = -1;
+static thread_local Network t_net;
+Network& Net() { return t_net; }
+
+static int DeviceCountOrDie() {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt <= 0)
+    Fatal(std::string("b200gbm: no CUDA device available (") + cudaGetErrorString(e) +
+          "). This engine is CUDA-only (sm_100a); there is no CPU fallback.");
+  return cnt;
+}
+int CurrentDevice() {
+  if (t_device < 0) {
+    int cnt = DeviceCountOrDie();
+    const char* lr = std::getenv("LOCAL_RANK");
+    t_device = (lr ? std::atoi(lr) : 0) % cnt;
+  }
+  return t_device;
+}
+void SetThreadDevice(int ordinal) {
+  int cnt = DeviceCountOrDie();
+  if (ordinal < 0 || ordinal >= cnt) Fatal("b200gbm: device ordinal out of range");
+  t_device = ordinal;
+}
+void EnsureDevice() { B200_CUDA(cudaSetDevice(CurrentDevice())); }
+
+static void SendAll(int fd, const void* buf, size_t n) {
+  const char* p = static_cast<const char*>(buf);
+  while (n) { ssize_t k = ::send(fd, p, n, 0); if (k <= 0) Fatal("network bootstrap: send failed"); p += k; n -= k; }
+}
+static void RecvAll(int fd, void* buf, size_t n) {
+  char* p = static_cast<char*>(buf);
+  while (n) { ssize_t k = ::recv(fd, p, n, 0); if (k <= 0) Fatal("network bootstrap: recv failed"); p += k; n -= k; }
+}
+
+// Replaces LGBM_NetworkInit's TCP mesh (reference call site TrainUtils.scala:279-295): the machine list
+// is only used to agree on ranks and to hand rank 0's ncclUniqueId to the others over one TCP
+// connection each; all training traffic then goes over NCCL (NVLink / NVSwitch).
+void NetworkInit(const char* machines, int local_listen_port, int listen_time_out_sec, int num_machines) {
+  NetworkFree();
+  if (num_machines <= 1) return;
+  std::vector<std::pair<std::string, int>> nodes;
+  {
+    std::string s(machines ? machines : "");
+    for (auto& c : s) if (c == ' ' || c == ';') c = ',';
+    std::stringstream ss(s);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+      if (tok.empty()) continue;
+      size_t p = tok.rfind(':');
+      if (p == std::string::npos) Fatal("machines should be a list of ip:port, got '" + tok + "'");
+      nodes.emplace_back(tok.substr(0, p), std::atoi(tok.c_str() + p + 1));
+    }
+  }
+  if (static_cast<int>(nodes.size()) < num_machines) Fatal("machine list shorter than num_machines");
+  nodes.resize(num_machines);
+  int rank = -1;
+  for (int i = 0; i < num_machines; ++i) if (nodes[i].second == local_listen_port) { rank = i; break; }
+  if (rank < 0) Fatal("local_listen_port " + std::to_string(local_listen_port) + " is not in the machine list");
+  if (t_device < 0) {
+    int cnt = DeviceCountOrDie();
+    const char* lr = std::getenv("LOCAL_RANK");
+    t_device = (lr ? std::atoi(lr) : rank) % cnt;
+  }
+  EnsureDevice();
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(std::max(listen_time_out_sec, 1));
+  ncclUniqueId id;
+  if (rank == 0) {
+    B200_NCCL(ncclGetUniqueId(&id));
+    for (int r = 1; r < num_machines; ++r) {
+      int fd = -1;
+      while (true) {
+        addrinfo hints{}, *res = nullptr;
+        hints.ai_family = AF_INET; hints.ai_socktype = SOCK_STREAM;
+        std::string port = std::to_string(nodes[r].second);
+        if (getaddrinfo(nodes[r].first.c_str(), port.c_str(), &hints, &res) == 0 && res) {
+          fd = ::socket(res->ai_family, res->ai_socktype, res->ai_protocol);
+          if (fd >= 0 && ::connect(fd, res->ai_addr, res->ai_addrlen) == 0) { freeaddrinfo(res); break; }
+          if (fd >= 0) ::close(fd);
+          fd = -1;
+          freeaddrinfo(res);
+        }
+        if (std::chrono::steady_clock::now() > deadline) Fatal("network bootstrap: cannot reach " + nodes[r].first + ":" + std::to_string(nodes[r].second));
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+      }
+      SendAll(fd, &id, sizeof(id));
+      char ack = 0;
+      RecvAll(fd, &ack, 1);
+      ::close(fd);
+    }
+  } else {
+    int ls = ::socket(AF_INET, SOCK_STREAM, 0);
+    if (ls < 0) Fatal("network bootstrap: socket() failed");
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    sockaddr_in addr{};
+    addr.sin_family = AF_INET; addr.sin_addr.s_addr = htonl(INADDR_ANY); addr.sin_port = htons(static_cast<uint16_t>(local_listen_port));
+    if (::bind(ls, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) { ::close(ls); Fatal("network bootstrap: cannot bind port " + std::to_string(local_listen_port)); }
+    ::listen(ls, 4);
+    fd_set fds;
+    FD_ZERO(&fds); FD_SET(ls, &fds);
+    timeval tv{std::max(listen_time_out_sec, 1), 0};
+    if (::select(ls + 1, &fds, nullptr, nullptr, &tv) <= 0) { ::close(ls); Fatal("network bootstrap: timed out waiting for rank 0"); }
+    int fd = ::accept(ls, nullptr, nullptr);
+    if (fd < 0) { ::close(ls); Fatal("network bootstrap: accept failed"); }
+    RecvAll(fd, &id, sizeof(id));
+    char ack = 1;
+    SendAll(fd, &ack, 1);
+    ::close(fd);
+    ::close(ls);
+  }
+  ncclComm_t comm;
+  B200_NCCL(ncclCommInitRank(&comm, num_machines, id, rank));
+  t_net.active = true; t_net.rank = rank; t_net.world = num_machines; t_net.comm = comm;
+}
+void NetworkFree() {
+  if (t_net.active && t_net.comm) { ncclCommDestroy(t_net.comm); }
+  t_net = Network();
+}
+
+// small host-value collectives (init scores, label statistics, bin mappers): stage through device memory
+static void AllReduceHost(double* v, int n, ncclRedOp_t op, cudaStream_t s) {
+  if (!Net().active) return;
+  DevBuf<double> d; d.Alloc(n);
+  d.Upload(v, n, s);
+  B200_NCCL(ncclAllReduce(d.p, d.p, n, ncclDouble, op, Net().comm, s));
+  d.Download(v, n, s);
+  B200_CUDA(cudaStreamSynchronize(s));
+}
+
+// =============================================================================== dataset
+Dataset::~Dataset() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+template <typename T>
+__global__ void k_gather_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, const int* __restrict__ rows, int nsample,
+                              double* __restrict__ out) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < static_cast<long long>(nsample) * ncol;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int s = static_cast<int>(e / ncol), f = static_cast<int>(e % ncol);
+    long long r = rows[s];
+    out[e] = row_major ? static_cast<double>(X[r * ncol + f]) : static_cast<double>(X[static_cast<long long>(f) * nrow + r]);
+  }
+}
+
+static bool IsDevicePointer(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr int kMapperRecord = 8 + 256;
+static void PackMapper(const FeatureBins& fb, double* r) {
+  r[0] = fb.num_bin; r[1] = fb.missing_type; r[2] = fb.trivial; r[3] = fb.default_bin; r[4] = fb.most_freq_bin;
+  r[5] = fb.sparse_rate; r[6] = fb.min_val; r[7] = fb.max_val;
+  for (int i = 0; i < 256; ++i) r[8 + i] = i < static_cast<int>(fb.upper.size()) ? fb.upper[i] : 0.0;
+}
+static FeatureBins UnpackMapper(const double* r) {
+  FeatureBins fb;
+  fb.num_bin = static_cast<int>(r[0]); fb.missing_type = static_cast<int>(r[1]); fb.trivial = r[2] != 0;
+  fb.default_bin = static_cast<uint32_t>(r[3]); fb.most_freq_bin = static_cast<uint32_t>(r[4]);
+  fb.sparse_rate = r[5]; fb.min_val = r[6]; fb.max_val = r[7];
+  fb.upper.assign(r + 8, r + 8 + fb.num_bin);
+  return fb;
+}
+
+void Dataset::FindBins(const void* data, bool on_device, int data_type, int is_row_major) {
+  const int n = num_data, F = num_total_features;
+  if (cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+  if (cfg.max_bin < 2) Fatal("max_bin should be >= 2");
+  if (!cfg.categorical_feature.empty()) Fatal("categorical_feature is not supported by this build yet (numerical features only)");
+  if (cfg.zero_as_missing) Fatal("zero_as_missing=true is not supported by this build");
+  LcgRandom rnd(cfg.data_random_seed);
+  int sample_cnt = n < cfg.bin_construct_sample_cnt ? n : cfg.bin_construct_sample_cnt;
+  std::vector<int> rows = rnd.Sample(n, sample_cnt);
+  sample_cnt = static_cast<int>(rows.size());
+  std::vector<double> S(static_cast<size_t>(sample_cnt) * F);
+  if (on_device) {
+    DevBuf<int> d_rows; d_rows.Alloc(sample_cnt);
+    DevBuf<double> d_S; d_S.Alloc(S.size());
+    d_rows.Upload(rows.data(), sample_cnt, stream);
+    int grid = static_cast<int>(std::min<size_t>((S.size() + 255) / 256, 148 * 32));
+    if (data_type == 0) k_gather_rows<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(data), n, F, is_row_major, d_rows.p, sample_cnt, d_S.p);
+    else k_gather_rows<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(data), n, F, is_row_major, d_rows.p, sample_cnt, d_S.p);
+    B200_CUDA(cudaGetLastError());
+    d_S.Download(S.data(), S.size(), stream);
+    B200_CUDA(cudaStreamSynchronize(stream));
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < sample_cnt; ++s) {
+      const long long r = rows[s];
+      for (int f = 0; f < F; ++f) {
+        double v;
+        if (data_type == 0) v = is_row_major ? static_cast<const float*>(data)[r * F + f] : static_cast<const float*>(data)[static_cast<long long>(f) * n + r];
+        else v = is_row_major ? static_cast<const double*>(data)[r * F + f] : static_cast<const double*>(data)[static_cast<long long>(f) * n + r];
+        S[static_cast<size_t>(s) * F + f] = v;
+      }
+    }
+  }
+  std::vector<std::vector<double>> nz(F);
+  {
+    const int world = Net().active ? Net().world : 1, rank = Net().active ? Net().rank : 0;
+    int step = std::max(1, (F + world - 1) / world);
+    const int f0 = world == 1 ? 0 : std::min(F, rank * step), f1 = world == 1 ? F : std::min(F, f0 + step);
+#pragma omp parallel for schedule(dynamic)
+    for (int f = f0; f < f1; ++f) {
+      nz[f].reserve(sample_cnt);
+      for (int s = 0; s < sample_cnt; ++s) {
+        double v = S[static_cast<size_t>(s) * F + f];
+        if (std::fabs(v) > kZeroThr || std::isnan(v)) nz[f].push_back(v);
+      }
+    }
+  }
+  FindBinsFromColumns(&nz, sample_cnt);
+}
+
+// nz[f] = sampled values of feature f with |v| > 1e-35 or NaN (only this rank's slice needs filling)
+void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sample_cnt) {
+  std::vector<std::vector<double>>& nz = *nzp;
+  const int n = num_data, F = num_total_features;
+  const int filter_cnt = static_cast<int>(static_cast<double>(cfg.min_data_in_leaf) * sample_cnt / n);
+  // feature ownership for distributed bin finding: contiguous slices of ceil(F/R)
+  const int world = Net().active ? Net().world : 1, rank = Net().active ? Net().rank : 0;
+  int step = (F + world - 1) / world;
+  if (step < 1) step = 1;
+  const int f0 = world == 1 ? 0 : std::min(F, rank * step), f1 = world == 1 ? F : std::min(F, f0 + step);
+  mappers.assign(F, FeatureBins());
+#pragma omp parallel for schedule(dynamic)
+  for (int f = f0; f < f1; ++f) {
+    mappers[f] = FindFeatureBins(&nz[f], sample_cnt, cfg.max_bin, cfg.min_data_in_bin, filter_cnt, cfg.feature_pre_filter, cfg.use_missing,
+                                 cfg.zero_as_missing);
+  }
+  if (world > 1) {   // C5: all-gather the serialized mappers
+    std::vector<double> send(static_cast<size_t>(step) * kMapperRecord, 0.0), recv(static_cast<size_t>(world) * step * kMapperRecord);
+    for (int f = f0; f < f1; ++f) PackMapper(mappers[f], &send[static_cast<size_t>(f - f0) * kMapperRecord]);
+    DevBuf<double> ds, dr; ds.Alloc(send.size()); dr.Alloc(recv.size());
+    ds.Upload(send.data(), send.size(), stream);
+    B200_NCCL(ncclAllGather(ds.p, dr.p, send.size(), ncclDouble, Net().comm, stream));
+    dr.Download(recv.data(), recv.size(), stream);
+    B200_CUDA(cudaStreamSynchronize(stream));
+    for (int f = 0; f < F; ++f) {
+      int owner = f / step, off = f - owner * step;
+      mappers[f] = UnpackMapper(&recv[(static_cast<size_t>(owner) * step + off) * kMapperRecord]);
+    }
+  }
+}
+
+void Dataset::UploadMeta() {
+  used.clear();
+  inner_of.assign(num_total_features, -1);
+  for (int f = 0; f < num_total_features; ++f)
+    if (!mappers[f].trivial) { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
+  nf = static_cast<int>(used.size());
+  num_tiles = std::max(1, (nf + 31) / 32);
+  nf_pad = num_tiles * 32;
+  meta_host.assign(nf_pad, FeatMeta{1, 0, 0, 0, 0, 0, 0, 0});
+  std::vector<double> ubh(static_cast<size_t>(nf_pad) * 256, 0.0);
+  for (int u = 0; u < nf; ++u) {
+    const FeatureBins& fb = mappers[used[u]];
+    meta_host[u] = FeatMeta{fb.num_bin, fb.missing_type, static_cast<int>(fb.default_bin), fb.most_freq_bin == 0 ? 1 : 0, used[u], 0, 0, 0};
+    for (int b = 0; b < fb.num_bin; ++b) ubh[static_cast<size_t>(u) * 256 + b] = fb.upper[b];
+  }
+  meta.Alloc(nf_pad); ub.Alloc(ubh.size());
+  meta.Upload(meta_host.data(), nf_pad, stream);
+  ub.Upload(ubh.data(), ubh.size(), stream);
+  B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+template <typename T>
+static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long long ld, const Dataset& d, long long row_offset, cudaStream_t s) {
+  static bool attr_set[2] = {false, false};
+  const int which = sizeof(T) == 4 ? 0 : 1;
+  if (!attr_set[which]) { B200_CUDA(cudaFuncSetAttribute(k_bin_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); attr_set[which] = true; }
+  dim3 grid(static_cast<unsigned>(std::min<long long>((nrow + 7) / 8, 148 * 8)), d.num_tiles);
+  if (grid.x == 0) grid.x = 1;
+  k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.nf, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
+  B200_CUDA(cudaGetLastError());
+}
+
+void Dataset::BinBlock(const void* data, bool on_device, int data_type, int is_row_major, long long n, long long start_row) {
+  const int F = num_total_features;
+  const size_t esz = data_type == 0 ? 4 : 8;
+  if (start_row < 0 || start_row + n > num_data) Fatal("row block out of range");
+  if (on_device) {
+    const long long ld = is_row_major ? F : n;
+    if (data_type == 0) LaunchBin<float>(static_cast<const float*>(data), n, F, is_row_major, ld, *this, start_row, stream);
+    else LaunchBin<double>(static_cast<const double*>(data), n, F, is_row_major, ld, *this, start_row, stream);
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return;
+  }
+  // host source: stream row chunks through two device buffers, copy of chunk i+1 overlaps binning of chunk i
+  long long chunk = std::max<long long>(1, std::min<long long>(n, (256LL << 20) / (static_cast<long long>(F) * esz)));
+  DevBuf<unsigned char> buf[2];
+  buf[0].Alloc(static_cast<size_t>(chunk) * F * esz);
+  buf[1].Alloc(static_cast<size_t>(chunk) * F * esz);
+  cudaStream_t copy_stream;
+  B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  cudaEvent_t copied[2], binned[2];
+  for (int i = 0; i < 2; ++i) { B200_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&binned[i], cudaEventDisableTiming)); }
+  int it = 0;
+  for (long long r0 = 0; r0 < n; r0 += chunk, ++it) {
+    const int b = it & 1;
+    const long long rows = std::min(chunk, n - r0);
+    if (it >= 2) B200_CUDA(cudaStreamWaitEvent(copy_stream, binned[b], 0));
+    if (is_row_major) {
+      B200_CUDA(cudaMemcpyAsync(buf[b].p, static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * F * esz, static_cast<size_t>(rows) * F * esz,
+                                cudaMemcpyHostToDevice, copy_stream));
+    } else {   // column-major: F column segments of `rows` elements, device chunk keeps ld = rows
+      B200_CUDA(cudaMemcpy2DAsync(buf[b].p, static_cast<size_t>(rows) * esz, static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * esz,
+                                  static_cast<size_t>(n) * esz, static_cast<size_t>(rows) * esz, F, cudaMemcpyHostToDevice, copy_stream));
+    }
+    B200_CUDA(cudaEventRecord(copied[b], copy_stream));
+    B200_CUDA(cudaStreamWaitEvent(stream, copied[b], 0));
+    const long long ld = is_row_major ? F : rows;
+    if (data_type == 0) LaunchBin<float>(reinterpret_cast<const float*>(buf[b].p), rows, F, is_row_major, ld, *this, start_row + r0, stream);
+    else LaunchBin<double>(reinterpret_cast<const double*>(buf[b].p), rows, F, is_row_major, ld, *this, start_row + r0, stream);
+    B200_CUDA(cudaEventRecord(binned[b], stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(stream));
+  B200_CUDA(cudaStreamSynchronize(copy_stream));
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(binned[i]); }
+  cudaStreamDestroy(copy_stream);
+}
+
+Dataset* Dataset::CreateFromSampledColumn(double** sample_data, int** sample_indices, int ncol, const int* num_per_col, int num_sample_row,
+                                          int num_total_row, const char* params) {
+  (void)sample_indices;
+  EnsureDevice();
+  if (num_total_row <= 0 || ncol <= 0) Fatal("Dataset should have at least one row and one column");
+  std::unique_ptr<Dataset> d(new Dataset());
+  d->device = CurrentDevice();
+  B200_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  d->num_data = num_total_row; d->num_total_features = ncol;
+  d->cfg.Parse(params);
+  if (d->cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+  if (!d->cfg.categorical_feature.empty()) Fatal("categorical_feature is not supported by this build yet (numerical features only)");
+  std::vector<std::vector<double>> nz(ncol);
+  for (int f = 0; f < ncol; ++f) nz[f].assign(sample_data[f], sample_data[f] + num_per_col[f]);
+  d->FindBinsFromColumns(&nz, num_sample_row);
+  d->feature_names.resize(ncol);
+  for (int f = 0; f < ncol; ++f) d->feature_names[f] = "Column_" + std::to_string(f);
+  d->UploadMeta();
+  d->rows_stride = static_cast<size_t>(num_total_row);
+  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  return d.release();
+}
+
+void Dataset::PushRows(const void* data, int data_type, int nrow, int ncol, int start_row) {
+  EnsureDevice();
+  if (ncol != num_total_features) Fatal("PushRows: wrong number of columns");
+  if (data_type != 0 && data_type != 1) Fatal("PushRows: unknown data type");
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, stream));
+  BinBlock(data, IsDevicePointer(data), data_type, 1, nrow, start_row);
+  B200_CUDA(cudaEventRecord(e1, stream));
+  B200_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  ingest_ms += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+void Dataset::GetBinsRowMajor(uint8_t* out) const {
+  std::vector<uint8_t> h(bins.n);
+  B200_CUDA(cudaMemcpy(h.data(), bins.p, bins.n, cudaMemcpyDeviceToHost));
+  std::memset(out, 0, static_cast<size_t>(num_data) * num_total_features);
+  for (int u = 0; u < nf; ++u) {
+    const int f = used[u];
+    const uint8_t* src = h.data() + (static_cast<size_t>(u >> 5) * rows_stride) * 32 + (u & 31);
+    for (int i = 0; i < num_data; ++i) out[static_cast<size_t>(i) * num_total_features + f] = src[static_cast<size_t>(i) * 32];
+  }
+}
+
+void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const {
+  EnsureDevice();
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+  const int n = num_data;
+  DevBuf<float> g, h; g.Alloc(n); h.Alloc(n);
+  g.Upload(grad, n, stream); h.Upload(hess, n, stream);
+  DevBuf<int4> q; q.Alloc(n);
+  DevBuf<TreeCtrl> ctrl; ctrl.Alloc(1); ctrl.Zero(stream);
+  DevBuf<int> didx; didx.Alloc(std::max(cnt, 1));
+  if (idx) didx.Upload(idx, cnt, stream);
+  const size_t elems = static_cast<size_t>(nf_pad) * 512;
+  DevBuf<long long> H; H.Alloc(elems); H.Zero(stream);
+  DevBuf<double> D; D.Alloc(elems);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  k_absmax<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, ctrl.p);
+  k_set_scale<<<1, 1, 0, stream>>>(ctrl.p, 0, 1.0);
+  k_quantize<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, q.p, ctrl.p, 0);
+  HistWork w{0, cnt, idx ? 1 : 0, 0};
+  B200_CUDA(cudaMemcpyAsync(&ctrl.p->hist_work, &w, sizeof(w), cudaMemcpyHostToDevice, stream));
+  k4_hist_build<4><<<sms, kHistThreads, kHistSmemBytes, stream>>>(bins.p, rows_stride, num_tiles, q.p, didx.p, didx.p, &ctrl.p->hist_work,
+                                                                  reinterpret_cast<unsigned long long*>(H.p));
+  k_hist_to_double<<<sms * 4, 256, 0, stream>>>(H.p, D.p, elems, ctrl.p);
+  B200_CUDA(cudaGetLastError());
+  std::vector<double> hd(elems);
+  D.Download(hd.data(), elems, stream);
+  B200_CUDA(cudaStreamSynchronize(stream));
+  std::memset(out, 0, sizeof(double) * static_cast<size_t>(num_total_features) * 512);
+  for (int u = 0; u < nf; ++u) std::memcpy(out + static_cast<size_t>(used[u]) * 512, hd.data() + static_cast<size_t>(u) * 512, sizeof(double) * 512);
+}
+
+Dataset* Dataset::CreateFromMat(const void* data, int data_type, int nrow, int ncol, int is_row_major, const char* params,
+                                const Dataset* reference) {
+  EnsureDevice();
+  if (data_type != 0 && data_type != 1) Fatal("Unknown data type in CreateFromMat (expect C_API_DTYPE_FLOAT32 or FLOAT64)");
+  if (nrow <= 0 || ncol <= 0) Fatal("Dataset should have at least one row and one column");
+  std::unique_ptr<Dataset> d(new Dataset());
+  d->device = CurrentDevice();
+  B200_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  d->num_data = nrow; d->num_total_features = ncol;
+  d->cfg.Parse(params);
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, d->stream));
+  const bool on_device = IsDevicePointer(data);
+  if (reference) {
+    if (reference->num_total_features != ncol) Fatal("Validation data has a different number of features than the reference dataset");
+    d->mappers = reference->mappers;
+    d->feature_names = reference->feature_names;
+  } else {
+    d->FindBins(data, on_device, data_type, is_row_major);
+    d->feature_names.resize(ncol);
+    for (int f = 0; f < ncol; ++f) d->feature_names[f] = "Column_" + std::to_string(f);
+  }
+  d->UploadMeta();
+  d->rows_stride = static_cast<size_t>(nrow);
+  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  d->BinBlock(data, on_device, data_type, is_row_major, nrow, 0);
+  B200_CUDA(cudaEventRecord(e1, d->stream));
+  B200_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  d->ingest_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return d.release();
+}
+
+Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type,
+                                int64_t nindptr, int64_t nelem, int64_t num_col, const char* params, const Dataset* reference) {
+  (void)nelem;
+  if (num_col <= 0) Fatal("CreateFromCSR: num_col must be given");
+  const int64_t nrow = nindptr - 1;
+  std::vector<double> dense(static_cast<size_t>(nrow) * num_col, 0.0);
+  for (int64_t r = 0; r < nrow; ++r) {
+    int64_t a = indptr_type == 2 ? static_cast<const int32_t*>(indptr)[r] : static_cast<const int64_t*>(indptr)[r];
+    int64_t b = indptr_type == 2 ? static_cast<const int32_t*>(indptr)[r + 1] : static_cast<const int64_t*>(indptr)[r + 1];
+    for (int64_t k = a; k < b; ++k) {
+      double v = data_type == 0 ? static_cast<const float*>(data)[k] : static_cast<const double*>(data)[k];
+      if (indices[k] < num_col) dense[static_cast<size_t>(r) * num_col + indices[k]] = v;
+    }
+  }
+  return CreateFromMat(dense.data(), 1, static_cast<int>(nrow), static_cast<int>(num_col), 1, params, reference);
+}
+
+void Dataset::SetField(const char* name, const void* data, int n, int type) {
+  EnsureDevice();
+  std::string s(name);
+  auto to_f32 = [&](std::vector<float>* out) {
+    out->resize(n);
+    if (type == 0) std::memcpy(out->data(), data, sizeof(float) * n);
+    else if (type == 1) for (int i = 0; i < n; ++i) (*out)[i] = static_cast<float>(static_cast<const double*>(data)[i]);
+    else Fatal("Input type error for field " + s + " (expect float32)");
+  };
+  if (s == "label" || s == "target") {
+    if (n != num_data) Fatal("Length of label is not same with #data");
+    to_f32(&label);
+    d_label.Alloc(n); d_label.Upload(label.data(), n, stream);
+  } else if (s == "weight" || s == "weights") {
+    if (n == 0 || data == nullptr) { weight.clear(); d_weight.Free(); return; }
+    if (n != num_data) Fatal("Length of weights is not same with #data");
+    to_f32(&weight);
+    d_weight.Alloc(n); d_weight.Upload(weight.data(), n, stream);
+  } else if (s == "init_score") {
+    if (n == 0 || data == nullptr) { init_score.clear(); return; }
+    if (n % num_data != 0) Fatal("Initial score size doesn't match data size");
+    init_score.resize(n);
+    if (type == 1) std::memcpy(init_score.data(), data, sizeof(double) * n);
+    else if (type == 0) for (int i = 0; i < n; ++i) init_score[i] = static_cast<const float*>(data)[i];
+    else Fatal("Input type error for init_score (expect float64)");
+  } else if (s == "group" || s == "query") {
+    if (type != 2) Fatal("Input type error for group (expect int32)");
+    const int32_t* g = static_cast<const int32_t*>(data);
+    group_sizes.assign(g, g + n);
+    query_boundaries.assign(1, 0);
+    for (int i = 0; i < n; ++i) query_boundaries.push_back(query_boundaries.back() + g[i]);
+    if (query_boundaries.back() != num_data) Fatal("Sum of query counts is not same with #data");
+    d_qb.Alloc(query_boundaries.size()); d_qb.Upload(query_boundaries.data(), query_boundaries.size(), stream);
+  } else {
+    Fatal("Unknown field name: " + s);
+  }
+  B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Dataset::GetField(const char* name, int* out_len, const void** out_ptr, int* out_type) const {
+  std::string s(name);
+  if (s == "label" || s == "target") { *out_len = static_cast<int>(label.size()); *out_ptr = label.data(); *out_type = 0; }
+  else if (s == "weight" || s == "weights") { *out_len = static_cast<int>(weight.size()); *out_ptr = weight.empty() ? nullptr : weight.data(); *out_type = 0; }
+  else if (s == "init_score") { *out_len = static_cast<int>(init_score.size()); *out_ptr = init_score.empty() ? nullptr : init_score.data(); *out_type = 1; }
+  else if (s == "group" || s == "query") { *out_len = static_cast<int>(query_boundaries.size()); *out_ptr = query_boundaries.empty() ? nullptr : query_boundaries.data(); *out_type = 2; }
+  else Fatal("Unknown field name: " + s);
+}
+
+void Dataset::SetFeatureNames(const char** names, int n) {
+  if (n != num_total_features) Fatal("Size of feature_names error, should equal with total number of features");
+  feature_names.assign(n, "");
+  for (int i = 0; i < n; ++i) {
+    feature_names[i] = names[i];
+    for (auto& c : feature_names[i]) if (c == ' ') c = '_';
+  }
+}
+
+// =============================================================================== booster
+static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
+
+Booster::Booster(const std::string& model_text) {
+  std::unique_ptr<HostModel> m = HostModel::FromString(model_text);
+  model = std::move(*m);
+  K = model.num_tree_per_iteration;
+  num_init_iteration = model.NumIterations();
+}
+
+Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
+  EnsureDevice();
+  device_ = CurrentDevice();
+  cfg.Parse(params);
+  if (cfg.boosting != "gbdt") Fatal("boosting_type=" + cfg.boosting + " is not implemented by this build yet (gbdt only)");
+  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank")
+    Fatal("Unknown/unsupported objective type name: " + cfg.objective);
+  if (cfg.bagging_freq > 0 && (cfg.bagging_fraction < 1.0 || cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
+    Fatal("bagging is not implemented by this build yet");
+  if (cfg.feature_fraction < 1.0) Fatal("feature_fraction < 1 is not implemented by this build yet");
+  if (cfg.num_leaves < 2) Fatal("num_leaves should be >= 2");
+  if (train->label.empty()) Fatal("label should not be empty for training");
+  if (cfg.objective == "multiclass" && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
+  if (cfg.objective == "lambdarank" && train->query_boundaries.empty()) Fatal("Ranking tasks require query information");
+  K = cfg.objective == "multiclass" ? cfg.num_class : 1;
+  parallel_ = Net().active && Net().world > 1;
+  cfg.num_machines = parallel_ ? Net().world : 1;
+  shrinkage_ = cfg.learning_rate;
+  model.num_class = cfg.objective == "multiclass" ? cfg.num_class : 1;
+  model.num_tree_per_iteration = K;
+  model.label_index = 0;
+  model.max_feature_idx = train->num_total_features - 1;
+  model.feature_names = train->feature_names;
+  for (int f = 0; f < train->num_total_features; ++f) model.feature_infos.push_back(train->mappers[f].InfoString());
+  InitTraining();
+  model.objective_str = ObjectiveString();
+}
+
+Booster::~Booster() {
+  for (auto* v : valids_) delete v;
+  if (tree_host_) cudaFreeHost(tree_host_);
+  if (ctrl_host_) cudaFreeHost(ctrl_host_);
+  if (leaves_host_) cudaFreeHost(leaves_host_);
+  if (ev_a_) cudaEventDestroy(ev_a_);
+  if (ev_b_) cudaEventDestroy(ev_b_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+std::string Booster::ObjectiveString() const {
+  if (cfg.objective == "binary") return "binary sigmoid:" + Config::Num(cfg.sigmoid);
+  if (cfg.objective == "multiclass") return "multiclass num_class:" + std::to_string(cfg.num_class);
+  return cfg.objective;
+}
+
+void Booster::InitTraining() {
+  const int n = train->num_data;
+  const int L = cfg.num_leaves;
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device_));
+  num_sms_ = prop.multiProcessorCount;
+  B200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreate(&ev_a_)); B200_CUDA(cudaEventCreate(&ev_b_));
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+
+  sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step;
+  sp_.min_gain_to_split = cfg.min_gain_to_split; sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf;
+  sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth; sp_.num_leaves = L; sp_.parallel = parallel_ ? 1 : 0;
+  sp_.nf = train->nf; sp_.nf_pad = train->nf_pad; sp_.num_tiles = train->num_tiles; sp_.pad = 0;
+
+  score_.Alloc(static_cast<size_t>(K) * n); score_.Zero(stream_);
+  grad_.Alloc(static_cast<size_t>(K) * n); hess_.Alloc(static_cast<size_t>(K) * n);
+  qgh_.Alloc(n); idx0_.Alloc(n); idx1_.Alloc(n);
+  slot_elems_ = static_cast<size_t>(train->nf_pad) * 512;
+  H_.Alloc(slot_elems_); pool_.Alloc(slot_elems_ * L);
+  flags_.Alloc(static_cast<size_t>(L) * train->nf_pad);
+  cands_.Alloc(2 * static_cast<size_t>(train->nf_pad));
+  leaves_.Alloc(L); ctrl_.Alloc(1); ctrl_.Zero(stream_);
+  const int chunks = n / kPartChunk + 2;
+  part_bits_.Alloc(static_cast<size_t>(chunks) * (kPartChunk / 32)); part_chunks_.Alloc(chunks);
+  // SoA tree blob
+  {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += Align16(bytes); return o; };
+    size_t o_lc = take(4 * (L - 1)), o_rc = take(4 * (L - 1)), o_sf = take(4 * (L - 1)), o_tb = take(4 * (L - 1)), o_dt = take(4 * (L - 1));
+    size_t o_sg = take(4 * (L - 1)), o_lv = take(8 * L), o_lw = take(8 * L), o_lcn = take(4 * L), o_iv = take(8 * (L - 1)), o_iw = take(8 * (L - 1));
+    size_t o_ic = take(4 * (L - 1)), o_lp = take(4 * L), o_ld = take(4 * L), o_nl = take(16);
+    tree_blob_bytes_ = off;
+    tree_blob_.Alloc(off);
+    unsigned char* b = tree_blob_.p;
+    tree_dev_.left_child = reinterpret_cast<int*>(b + o_lc); tree_dev_.right_child = reinterpret_cast<int*>(b + o_rc);
+    tree_dev_.split_feature_inner = reinterpret_cast<int*>(b + o_sf); tree_dev_.threshold_bin = reinterpret_cast<int*>(b + o_tb);
+    tree_dev_.decision_type = reinterpret_cast<int*>(b + o_dt); tree_dev_.split_gain = reinterpret_cast<float*>(b + o_sg);
+    tree_dev_.leaf_value = reinterpret_cast<double*>(b + o_lv); tree_dev_.leaf_weight = reinterpret_cast<double*>(b + o_lw);
+    tree_dev_.leaf_count = reinterpret_cast<int*>(b + o_lcn); tree_dev_.internal_value = reinterpret_cast<double*>(b + o_iv);
+    tree_dev_.internal_weight = reinterpret_cast<double*>(b + o_iw); tree_dev_.internal_count = reinterpret_cast<int*>(b + o_ic);
+    tree_dev_.leaf_parent = reinterpret_cast<int*>(b + o_lp); tree_dev_.leaf_depth = reinterpret_cast<int*>(b + o_ld);
+    tree_dev_.num_leaves = reinterpret_cast<int*>(b + o_nl);
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&tree_host_), off));
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctrl_host_), sizeof(TreeCtrl)));
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&leaves_host_), sizeof(LeafState) * L));
+  }
+  // init score from the dataset
+  if (!train->init_score.empty()) {
+    if (train->init_score.size() != static_cast<size_t>(K) * n) Fatal("Initial score size doesn't match data size");
+    has_init_score_ = true;
+    score_.Upload(train->init_score.data(), train->init_score.size(), stream_);
+  }
+  // ---- objective set-up
+  class_need_train_.assign(K, true);
+  const_hessian_ = false;
+  if (cfg.objective == "regression") {
+    const_hessian_ = train->weight.empty();
+  } else if (cfg.objective == "binary") {
+    double cnt[2] = {0, 0};
+    for (int i = 0; i < n; ++i) cnt[train->label[i] > 0 ? 1 : 0] += 1;
+    AllReduceHost(cnt, 2, ncclSum, stream_);          // global class counts (R14)
+    binary_need_train_ = !(cnt[0] == 0 || cnt[1] == 0);
+    binary_w_[0] = binary_w_[1] = 1.0;
+    if (cfg.is_unbalance && cnt[0] > 0 && cnt[1] > 0) {
+      if (cnt[1] > cnt[0]) { binary_w_[1] = 1.0; binary_w_[0] = cnt[1] / cnt[0]; }
+      else { binary_w_[1] = cnt[0] / cnt[1]; binary_w_[0] = 1.0; }
+    }
+    binary_w_[1] *= cfg.scale_pos_weight;
+    class_need_train_[0] = binary_need_train_;
+  } else if (cfg.objective == "multiclass") {
+    class_init_probs_.assign(K + 1, 0.0);
+    for (int i = 0; i < n; ++i) {
+      int l = static_cast<int>(train->label[i]);
+      if (l < 0 || l >= K) Fatal("Label must be in [0, " + std::to_string(K) + "), but found " + std::to_string(l) + " in label");
+      double w = train->weight.empty() ? 1.0 : train->weight[i];
+      class_init_probs_[l] += w; class_init_probs_[K] += w;
+    }
+    AllReduceHost(class_init_probs_.data(), K + 1, ncclSum, stream_);
+    for (int k = 0; k < K; ++k) {
+      class_init_probs_[k] /= class_init_probs_[K];
+      class_need_train_[k] = !(std::fabs(class_init_probs_[k]) <= kEps || std::fabs(class_init_probs_[k]) >= 1.0 - kEps);
+    }
+  } else if (cfg.objective == "lambdarank") {
+    std::vector<double> lg = cfg.label_gain;
+    if (lg.empty()) { lg.push_back(0.0); for (int i = 1; i < 31; ++i) lg.push_back(static_cast<double>((1 << i) - 1)); }
+    const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
+    std::vector<double> imd(nq);
+    lr_max_q_ = 0;
+    for (int q = 0; q < nq; ++q) {
+      const int s = train->query_boundaries[q], cnt = train->query_boundaries[q + 1] - s;
+      lr_max_q_ = std::max(lr_max_q_, cnt);
+      std::vector<int> label_cnt(lg.size(), 0);
+      for (int i = 0; i < cnt; ++i) {
+        int l = static_cast<int>(train->label[s + i]);
+        if (l < 0 || l >= static_cast<int>(lg.size())) Fatal("Label excel the max range " + std::to_string(lg.size()) + " for lambdarank");
+        ++label_cnt[l];
+      }
+      int top = static_cast<int>(lg.size()) - 1, k = std::min(cfg.lambdarank_truncation_level, cnt);
+      double m = 0;
+      for (int j = 0; j < k; ++j) {
+        while (top > 0 && label_cnt[top] <= 0) --top;
+        m += lg[top] / std::log2(2.0 + j);
+        --label_cnt[top];
+      }
+      imd[q] = m > 0.0 ? 1.0 / m : m;
+    }
+    lr_inv_max_dcg_.Alloc(nq); lr_inv_max_dcg_.Upload(imd.data(), nq, stream_);
+    lr_label_gain_.Alloc(lg.size()); lr_label_gain_.Upload(lg.data(), lg.size(), stream_);
+    const size_t bins_n = 1024 * 1024;
+    lr_min_in_ = -50.0 / cfg.sigmoid / 2; lr_max_in_ = 50.0 / cfg.sigmoid / 2;
+    lr_idx_factor_ = bins_n / (lr_max_in_ - lr_min_in_);
+    std::vector<float> tab(bins_n);
+    for (size_t i = 0; i < bins_n; ++i) tab[i] = static_cast<float>(1.0 / (1.0 + std::exp((i / lr_idx_factor_ + lr_min_in_) * cfg.sigmoid)));
+    lr_sig_table_.Alloc(bins_n); lr_sig_table_.Upload(tab.data(), bins_n, stream_);
+    B200_CUDA(cudaStreamSynchronize(stream_));
+    size_t smem = static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4);
+    if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
+    B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
+  }
+  B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+double Booster::ObjectiveInitScore(int k) {
+  const int n = train->num_data;
+  if (cfg.objective == "regression") {
+    double suml = 0, sumw = 0;
+    if (!train->weight.empty()) for (int i = 0; i < n; ++i) { suml += static_cast<double>(train->label[i]) * train->weight[i]; sumw += train->weight[i]; }
+    else { sumw = n; for (int i = 0; i < n; ++i) suml += train->label[i]; }
+    double v = suml / sumw;
+    if (parallel_) { AllReduceHost(&v, 1, ncclSum, stream_); v /= Net().world; }   // GlobalSyncUpByMean (R11)
+    return v;
+  }
+  if (cfg.objective == "binary") {
+    double s[2] = {0, 0};
+    if (!train->weight.empty()) for (int i = 0; i < n; ++i) { s[0] += (train->label[i] > 0) * static_cast<double>(train->weight[i]); s[1] += train->weight[i]; }
+    else { s[1] = n; for (int i = 0; i < n; ++i) s[0] += (train->label[i] > 0); }
+    AllReduceHost(s, 2, ncclSum, stream_);
+    double pavg = s[0] / s[1];
+    pavg = std::min(pavg, 1.0 - kEps);
+    pavg = std::max(pavg, kEps);
+    return std::log(pavg / (1.0 - pavg)) / cfg.sigmoid;
+  }
+  if (cfg.objective == "multiclass") return std::log(std::max(kEps, class_init_probs_[k]));
+  return 0.0;
+}
+
+double Booster::BoostFromAverage(int k) {
+  if (model.trees.empty() && !has_init_score_ && cfg.boost_from_average) {
+    double init = ObjectiveInitScore(k);
+    if (std::fabs(init) > kEps) {
+      const int n = train->num_data;
+      k_add_const<<<num_sms_ * 4, 256, 0, stream_>>>(score_.p + static_cast<size_t>(k) * n, n, init);
+      for (auto* v : valids_) k_add_const<<<num_sms_ * 4, 256, 0, stream_>>>(v->score.p + static_cast<size_t>(k) * v->ds->num_data, v->ds->num_data, init);
+      B200_CUDA(cudaGetLastError());
+      return init;
+    }
+  }
+  return 0.0;
+}
+
+void Booster::ComputeGradients() {
+  const int n = train->num_data;
+  const int grid = num_sms_ * 8;
+  const float* w = train->weight.empty() ? nullptr : train->d_weight.p;
+  if (cfg.objective == "regression") {
+    k_grad_l2<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n);
+  } else if (cfg.objective == "binary") {
+    if (binary_need_train_)
+      k_grad_binary<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, cfg.sigmoid, binary_w_[0], binary_w_[1]);
+  } else if (cfg.objective == "multiclass") {
+    k_grad_softmax<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, K, static_cast<double>(K) / (K - 1.0));
+  } else if (cfg.objective == "lambdarank") {
+    const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
+    size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4), 1024);
+    k_grad_lambdarank<<<std::min(nq, num_sms_ * 8), 256, smem, stream_>>>(
+        score_.p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
+        lr_max_in_, lr_idx_factor_, cfg.sigmoid, cfg.lambdarank_truncation_level, cfg.lambdarank_norm ? 1 : 0, grad_.p, hess_.p, lr_max_q_);
+  }
+  B200_CUDA(cudaGetLastError());
+  timing.launches += 1;
+}
+
+// One tree: the whole leaf-wise growth is enqueued without a host sync; leaf choice, smaller/larger
+// selection, partition sizes all live in TreeCtrl / LeafState on the device.
+void Booster::TrainOneTree(int k, HostTree* out) {
+  const Dataset& d = *train;
+  const int n = d.num_data;
+  const int L = cfg.num_leaves;
+  const float* g = grad_.p + static_cast<size_t>(k) * n;
+  const float* h = hess_.p + static_cast<size_t>(k) * n;
+  TreeCtrl* ctrl = ctrl_.p;
+  cudaStream_t s = stream_;
+  const int egrid = num_sms_ * 8;
+  B200_CUDA(cudaMemsetAsync(&ctrl->absmax_bits[0], 0, 8, s));
+  k_absmax<<<egrid, 256, 0, s>>>(g, h, n, ctrl);
+  if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->absmax_bits[0], &ctrl->absmax_bits[0], 2, ncclUint32, ncclMax, Net().comm, s));
+  k_set_scale<<<1, 1, 0, s>>>(ctrl, const_hessian_ ? 1 : 0, 1.0);
+  k_quantize<<<egrid, 256, 0, s>>>(g, h, n, qgh_.p, ctrl, const_hessian_ ? 1 : 0);
+  if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->root_q[0], &ctrl->root_q[0], 3, ncclInt64, ncclSum, Net().comm, s));
+  k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, n, nullptr);
+  timing.launches += 4;
+  const int pgrid = std::max(1, std::min(n / kPartChunk + 1, num_sms_ * 8));
+  const dim3 sgrid((d.nf + 7) / 8, 2);
+  std::vector<cudaEvent_t> evs;
+  for (int split = 0; split < L - 1; ++split) {
+    k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 0);
+    B200_CUDA(cudaMemsetAsync(H_.p, 0, slot_elems_ * sizeof(long long), s));
+    if (profile_hist) { cudaEvent_t a, b; B200_CUDA(cudaEventCreate(&a)); B200_CUDA(cudaEventCreate(&b)); evs.push_back(a); evs.push_back(b); B200_CUDA(cudaEventRecord(a, s)); }
+    if (const_hessian_)
+      k4_hist_build<3><<<num_sms_, kHistThreads, kHistSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                      reinterpret_cast<unsigned long long*>(H_.p));
+    else
+      k4_hist_build<4><<<num_sms_, kHistThreads, kHistSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                      reinterpret_cast<unsigned long long*>(H_.p));
+    if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
+    if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
+    k_scan<<<sgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+    k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
+    k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
+    k_part_scan<<<1, 1024, 0, s>>>(ctrl, part_chunks_.p);
+    k_part_scatter<<<pgrid, 256, 0, s>>>(ctrl, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
+    timing.launches += 7; timing.hist_launches += 1;
+  }
+  k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 1);
+  k_add_score<<<egrid, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, idx0_.p, idx1_.p, score_.p + static_cast<size_t>(k) * n, shrinkage_);
+  for (auto* v : valids_)
+    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, v->ds->meta.p, v->ds->bins.p, v->ds->rows_stride, v->ds->num_data,
+                                            v->score.p + static_cast<size_t>(k) * v->ds->num_data, shrinkage_);
+  timing.launches += 2 + static_cast<long long>(valids_.size());
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(tree_host_, tree_blob_.p, tree_blob_bytes_, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl, sizeof(TreeCtrl), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  if (profile_hist) {
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); timing.hist_ms += ms; }
+    for (auto e : evs) cudaEventDestroy(e);
+  }
+  timing.hist_rows += ctrl_host_->trace_rows;
+  // ---- host copy of the tree
+  const unsigned char* hb = tree_host_;
+  auto at = [&](const void* devp) { return hb + (static_cast<const unsigned char*>(devp) - tree_blob_.p); };
+  const int nl = *reinterpret_cast<const int*>(at(tree_dev_.num_leaves));
+  out->Resize(nl);
+  if (nl > 1) {
+    const int* lc = reinterpret_cast<const int*>(at(tree_dev_.left_child));
+    const int* rc = reinterpret_cast<const int*>(at(tree_dev_.right_child));
+    const int* sf = reinterpret_cast<const int*>(at(tree_dev_.split_feature_inner));
+    const int* tb = reinterpret_cast<const int*>(at(tree_dev_.threshold_bin));
+    const int* dt = reinterpret_cast<const int*>(at(tree_dev_.decision_type));
+    const float* sg = reinterpret_cast<const float*>(at(tree_dev_.split_gain));
+    const double* lv = reinterpret_cast<const double*>(at(tree_dev_.leaf_value));
+    const double* lw = reinterpret_cast<const double*>(at(tree_dev_.leaf_weight));
+    const int* lcn = reinterpret_cast<const int*>(at(tree_dev_.leaf_count));
+    const double* iv = reinterpret_cast<const double*>(at(tree_dev_.internal_value));
+    const double* iw = reinterpret_cast<const double*>(at(tree_dev_.internal_weight));
+    const int* ic = reinterpret_cast<const int*>(at(tree_dev_.internal_count));
+    const int* ld = reinterpret_cast<const int*>(at(tree_dev_.leaf_depth));
+    for (int i = 0; i < nl - 1; ++i) {
+      out->left_child[i] = lc[i]; out->right_child[i] = rc[i]; out->split_feature_inner[i] = sf[i];
+      out->split_feature[i] = d.used[sf[i]]; out->threshold_in_bin[i] = static_cast<uint32_t>(tb[i]);
+      double thr = d.mappers[d.used[sf[i]]].upper[tb[i]];
+      if (std::isnan(thr)) thr = 0.0; else if (thr >= 1e300) thr = 1e300; else if (thr <= -1e300) thr = -1e300;
+      out->threshold[i] = thr;
+      out->decision_type[i] = static_cast<int8_t>(dt[i]); out->split_gain[i] = sg[i];
+      out->internal_value[i] = iv[i]; out->internal_weight[i] = iw[i]; out->internal_count[i] = ic[i];
+    }
+    for (int i = 0; i < nl; ++i) { out->leaf_value[i] = lv[i]; out->leaf_weight[i] = lw[i]; out->leaf_count[i] = lcn[i]; out->leaf_depth[i] = ld[i]; }
+  } else {
+    out->leaf_value[0] = 0.0;
+  }
+}
+
+bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
+  if (!train) Fatal("this booster was loaded from a model string and cannot be trained");
+  EnsureDevice();
+  cudaStream_t s = stream_;
+  const int n = train->num_data;
+  B200_CUDA(cudaEventRecord(ev_a_, s));
+  std::vector<double> init_scores(K, 0.0);
+  bool saved_const = const_hessian_;
+  if (!custom_g) {
+    for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
+    ComputeGradients();
+  } else {
+    grad_.Upload(custom_g, static_cast<size_t>(K) * n, s);
+    hess_.Upload(custom_h, static_cast<size_t>(K) * n, s);
+    const_hessian_ = false;
+  }
+  bool should_continue = false;
+  for (int k = 0; k < K; ++k) {
+    std::unique_ptr<HostTree> t(new HostTree());
+    t->Resize(1);
+    t->leaf_value[0] = 0;
+    if (class_need_train_[k] && train->nf > 0) TrainOneTree(k, t.get());
+    if (t->num_leaves > 1) {
+      should_continue = true;
+      t->Shrink(shrinkage_);
+      if (std::fabs(init_scores[k]) > kEps) t->AddBias(init_scores[k]);
+    } else if (static_cast<int>(model.trees.size()) < K) {
+      double output = class_need_train_[k] ? init_scores[k] : ObjectiveInitScore(k);
+      t->MakeConstant(output);
+      k_add_const<<<num_sms_ * 4, 256, 0, s>>>(score_.p + static_cast<size_t>(k) * n, n, output);
+      for (auto* v : valids_) k_add_const<<<num_sms_ * 4, 256, 0, s>>>(v->score.p + static_cast<size_t>(k) * v->ds->num_data, v->ds->num_data, output);
+    } else {
+      t->MakeConstant(0.0);
+    }
+    model.trees.push_back(std::move(t));
+  }
+  const_hessian_ = saved_const;
+  B200_CUDA(cudaEventRecord(ev_b_, s));
+  B200_CUDA(cudaEventSynchronize(ev_b_));
+  float ms = 0;
+  B200_CUDA(cudaEventElapsedTime(&ms, ev_a_, ev_b_));
+  timing.total_ms += ms;
+  if (!should_continue) {
+    if (static_cast<int>(model.trees.size()) > K) for (int k = 0; k < K; ++k) model.trees.pop_back();
+    return true;
+  }
+  ++iter;
+  return false;
+}
+
+bool Booster::UpdateOneIter() { return TrainTrees(nullptr, nullptr); }
+bool Booster::UpdateOneIterCustom(const float* grad, const float* hess) { return TrainTrees(grad, hess); }
+
+void Booster::ResetParameter(const char* params) {
+  Config nc;
+  nc.Parse(params);
+  for (auto& kv : nc.raw) cfg.raw[kv.first] = kv.second;
+  int keep_machines = cfg.num_machines;
+  cfg.Refresh();
+  cfg.num_machines = keep_machines;
+  shrinkage_ = cfg.learning_rate;
+  sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step; sp_.min_gain_to_split = cfg.min_gain_to_split;
+  sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf; sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth;
+}
+
+void Booster::AddValidData(const Dataset* valid) {
+  EnsureDevice();
+  if (!train) Fatal("cannot add validation data to a prediction-only booster");
+  if (valid->nf != train->nf) Fatal("validation data must be created with reference=train");
+  ValidSet* v = new ValidSet();
+  v->ds = valid;
+  v->score.Alloc(static_cast<size_t>(K) * valid->num_data);
+  v->score.Zero(stream_);
+  if (!valid->init_score.empty() && valid->init_score.size() == static_cast<size_t>(K) * valid->num_data)
+    v->score.Upload(valid->init_score.data(), valid->init_score.size(), stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  valids_.push_back(v);
+}
+
+void Booster::MergeFrom(const Booster* other) {
+  // [UPSTREAM GBDT::MergeFrom] other's trees first, then ours; scores are NOT replayed
+  std::vector<std::unique_ptr<HostTree>> mine = std::move(model.trees);
+  model.trees.clear();
+  for (auto& t : other->model.trees) model.trees.emplace_back(new HostTree(*t));
+  num_init_iteration = static_cast<int>(model.trees.size()) / std::max(K, 1);
+  for (auto& t : mine) model.trees.push_back(std::move(t));
+}
+
+std::string Booster::SaveModelToString(int start_iteration, int num_iteration, int importance_type) const {
+  std::string pb = train ? cfg.ToString() : std::string();
+  return model.ToString(start_iteration, num_iteration, importance_type, pb);
+}
+
+std::string Booster::DumpModelJson(int start_iteration, int num_iteration) const {
+  std::ostringstream s;
+  int t0, t1;
+  model.IterRange(start_iteration, num_iteration, &t0, &t1);
+  s << "{\"name\":\"tree\",\"version\":\"v3\",\"num_class\":" << model.num_class << ",\"num_tree_per_iteration\":" << model.num_tree_per_iteration
+    << ",\"label_index\":" << model.label_index << ",\"max_feature_idx\":" << model.max_feature_idx << ",\"objective\":\"" << model.objective_str
+    << "\",\"average_output\":" << (model.average_output ? "true" : "false") << ",\"feature_names\":[";
+  for (size_t i = 0; i < model.feature_names.size(); ++i) s << (i ? "," : "") << '"' << model.feature_names[i] << '"';
+  s << "],\"tree_info\":[";
+  char buf[64];
+  auto num = [&](double v) { snprintf(buf, sizeof(buf), "%.17g", v); return std::string(buf); };
+  for (int t = t0; t < t1; ++t) {
+    const HostTree& tr = *model.trees[t];
+    s << (t > t0 ? "," : "") << "{\"tree_index\":" << (t - t0) << ",\"num_leaves\":" << tr.num_leaves << ",\"num_cat\":0,\"shrinkage\":" << num(tr.shrinkage)
+      << ",\"tree_structure\":";
+    struct Rec { static void node(std::ostringstream& o, const HostTree& tr, int idx, const std::function<std::string(double)>& num) {
+      if (idx >= 0) {
+        int mt = (tr.decision_type[idx] >> 2) & 3;
+        o << "{\"split_index\":" << idx << ",\"split_feature\":" << tr.split_feature[idx] << ",\"split_gain\":" << num(tr.split_gain[idx])
+          << ",\"threshold\":" << num(tr.threshold[idx]) << ",\"decision_type\":\"<=\",\"default_left\":" << ((tr.decision_type[idx] & 2) ? "true" : "false")
+          << ",\"missing_type\":\"" << (mt == 0 ? "None" : mt == 1 ? "Zero" : "NaN") << "\",\"internal_value\":" << num(tr.internal_value[idx])
+          << ",\"internal_weight\":" << num(tr.internal_weight[idx]) << ",\"internal_count\":" << tr.internal_count[idx] << ",\"left_child\":";
+        node(o, tr, tr.left_child[idx], num);
+        o << ",\"right_child\":";
+        node(o, tr, tr.right_child[idx], num);
+        o << "}";
+      } else {
+        int l = ~idx;
+        o << "{\"leaf_index\":" << l << ",\"leaf_value\":" << num(tr.leaf_value[l]) << ",\"leaf_weight\":" << num(tr.leaf_weight[l]) << ",\"leaf_count\":" << tr.leaf_count[l] << "}";
+      }
+    } };
+    if (tr.num_leaves <= 1) s << "{\"leaf_value\":" << num(tr.leaf_value[0]) << "}";
+    else Rec::node(s, tr, 0, num);
+    s << "}";
+  }
+  s << "],\"feature_importances\":{";
+  std::vector<double> imp = model.FeatureImportance(num_iteration, 0);
+  bool first = true;
+  for (size_t i = 0; i < imp.size() && i < model.feature_names.size(); ++i)
+    if (imp[i] > 0) { s << (first ? "" : ",") << '"' << model.feature_names[i] << "\":" << static_cast<long long>(imp[i]); first = false; }
+  s << "}}";
+  return s.str();
+}
+
+// ---- evaluation (host side: metrics are not on the hot path; scores are read back) -------------
+std::vector<std::string> Booster::EvalNames() const {
+  std::vector<std::string> names;
+  for (auto& m : cfg.metric) {
+    if (m == "ndcg" || m == "map") for (int k : cfg.eval_at) names.push_back(m + "@" + std::to_string(k));
+    else names.push_back(m);
+  }
+  return names;
+}
+int64_t Booster::NumPredict(int data_idx) const {
+  if (data_idx == 0) return static_cast<int64_t>(K) * train->num_data;
+  if (data_idx - 1 >= static_cast<int>(valids_.size())) Fatal("data_idx out of range");
+  return static_cast<int64_t>(K) * valids_[data_idx - 1]->ds->num_data;
+}
+void Booster::GetPredict(int data_idx, int64_t* out_len, double* out) {
+  EnsureDevice();
+  const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
+  const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
+  const int n = ds->num_data;
+  std::vector<double> raw(static_cast<size_t>(K) * n);
+  sc.Download(raw.data(), raw.size(), stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  std::vector<double> r(K), o(K);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < K; ++k) r[k] = raw[static_cast<size_t>(k) * n + i];
+    model.Convert(r.data(), o.data());
+    for (int k = 0; k < K; ++k) out[static_cast<size_t>(k) * n + i] = o[k];
+  }
+  *out_len = static_cast<int64_t>(K) * n;
+}
+
+static double AucOf(const std::vector<double>& score, const std::vector<float>& label, const std::vector<float>& weight) {
+  const size_t n = score.size();
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return score[a] > score[b]; });
+  double sum_pos = 0, accum = 0, cur_pos = 0, cur_neg = 0, threshold = score[order[0]], sum_neg_total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const int j = order[i];
+    const double w = weight.empty() ? 1.0 : weight[j];
+    if (score[j] != threshold) {
+      threshold = score[j];
+      accum += cur_neg * (cur_pos * 0.5 + sum_pos);
+      sum_pos += cur_pos;
+      cur_neg = cur_pos = 0;
+    }
+    if (label[j] > 0) cur_pos += w; else { cur_neg += w; sum_neg_total += w; }
+  }
+  accum += cur_neg * (cur_pos * 0.5 + sum_pos);
+  sum_pos += cur_pos;
+  if (sum_pos > 0 && sum_neg_total > 0) return accum / (sum_pos * sum_neg_total);
+  return 1.0;
+}
+
+std::vector<double> Booster::GetEval(int data_idx) {
+  EnsureDevice();
+  const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
+  const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
+  const int n = ds->num_data;
+  std::vector<double> raw(static_cast<size_t>(K) * n);
+  sc.Download(raw.data(), raw.size(), stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  const std::vector<float>& y = ds->label;
+  const std::vector<float>& w = ds->weight;
+  std::vector<double> out;
+  auto avg = [&](double loss, double sw) {
+    double v[2] = {loss, sw};
+    AllReduceHost(v, 2, ncclSum, stream_);     // averaged metrics are global in distributed mode (B.5)
+    return v[0] / v[1];
+  };
+  for (auto& m : cfg.metric) {
+    if (m == "l2" || m == "rmse" || m == "l1") {
+      double loss = 0, sw = 0;
+      for (int i = 0; i < n; ++i) {
+        double wi = w.empty() ? 1.0 : w[i], d = raw[i] - y[i];
+        loss += (m == "l1" ? std::fabs(d) : d * d) * wi; sw += wi;
+      }
+      double v = avg(loss, sw);
+      out.push_back(m == "rmse" ? std::sqrt(v) : v);
+    } else if (m == "binary_logloss" || m == "binary_error") {
+      double loss = 0, sw = 0;
+      for (int i = 0; i < n; ++i) {
+        double wi = w.empty() ? 1.0 : w[i];
+        double p = 1.0 / (1.0 + std::exp(-cfg.sigmoid * raw[i]));
+        if (m == "binary_error") loss += ((p <= 0.5) == (y[i] > 0) ? 1.0 : 0.0) * wi;
+        else {
+          double pl = y[i] > 0 ? p : 1.0 - p;
+          loss += (pl > kEps ? -std::log(pl) : -std::log(kEps)) * wi;
+        }
+        sw += wi;
+      }
+      out.push_back(avg(loss, sw));
+    } else if (m == "auc") {
+      std::vector<double> s1(raw.begin(), raw.begin() + n);
+      out.push_back(AucOf(s1, y, w));
+    } else if (m == "multi_logloss" || m == "multi_error") {
+      double loss = 0, sw = 0;
+      std::vector<double> r(K), p(K);
+      for (int i = 0; i < n; ++i) {
+        double wi = w.empty() ? 1.0 : w[i];
+        for (int k = 0; k < K; ++k) r[k] = raw[static_cast<size_t>(k) * n + i];
+        model.Convert(r.data(), p.data());
+        int l = static_cast<int>(y[i]);
+        if (m == "multi_error") { int larger = 0; for (int k = 0; k < K; ++k) if (p[k] >= p[l]) ++larger; loss += (larger > 1 ? 1.0 : 0.0) * wi; }
+        else loss += (p[l] > kEps ? -std::log(p[l]) : -std::log(kEps)) * wi;
+        sw += wi;
+      }
+      out.push_back(avg(loss, sw));
+    } else if (m == "ndcg") {
+      std::vector<double> lg = cfg.label_gain;
+      if (lg.empty()) { lg.push_back(0.0); for (int i = 1; i < 31; ++i) lg.push_back(static_cast<double>((1 << i) - 1)); }
+      const int nq = static_cast<int>(ds->query_boundaries.size()) - 1;
+      if (nq <= 0) Fatal("The NDCG metric requires query information");
+      std::vector<double> acc(cfg.eval_at.size(), 0.0);
+      double sumq = 0;
+      for (int q = 0; q < nq; ++q) {
+        const int s0 = ds->query_boundaries[q], cnt = ds->query_boundaries[q + 1] - s0;
+        std::vector<int> ord(cnt);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return raw[s0 + a] > raw[s0 + b]; });
+        std::vector<int> lab(cnt);
+        for (int i = 0; i < cnt; ++i) lab[i] = static_cast<int>(y[s0 + i]);
+        std::vector<int> sorted_lab = lab;
+        std::sort(sorted_lab.begin(), sorted_lab.end(), std::greater<int>());
+        sumq += 1;
+        for (size_t e = 0; e < cfg.eval_at.size(); ++e) {
+          int k = std::min(cfg.eval_at[e], cnt);
+          double maxdcg = 0, dcg = 0;
+          for (int j = 0; j < k; ++j) { maxdcg += lg[sorted_lab[j]] / std::log2(2.0 + j); dcg += lg[lab[ord[j]]] / std::log2(2.0 + j); }
+          acc[e] += maxdcg > 0 ? dcg / maxdcg : 1.0;
+        }
+      }
+      for (size_t e = 0; e < acc.size(); ++e) out.push_back(avg(acc[e], sumq));
+    } else {
+      Fatal("Unknown metric type name: " + m);
+    }
+  }
+  return out;
+}
+
+void Booster::GetRawScores(int data_idx, double* out) {
+  EnsureDevice();
+  const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
+  const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
+  sc.Download(out, static_cast<size_t>(K) * ds->num_data, stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Booster::ExportLastHistogram(double* out) {
+  EnsureDevice();
+  DevBuf<double> d; d.Alloc(slot_elems_);
+  k_hist_to_double<<<num_sms_ * 4, 256, 0, stream_>>>(H_.p, d.p, slot_elems_, ctrl_.p);
+  d.Download(out, slot_elems_, stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace b200gbm

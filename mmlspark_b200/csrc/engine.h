@@ -1,0 +1,206 @@
+// b200gbm engine: device dataset, data-parallel network state, booster (GBDT driver + tree learner).
+// Everything below the C ABI (include/b200gbm_c_api.h).  One host thread drives one
+// (network, dataset, booster) triple, exactly like one Spark task thread in the reference
+// (SURVEY.md fact 8): network / device / last-error state are thread_local.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bin_mapper.h"
+#include "config.h"
+#include "kernels.cuh"
+#include "model.h"
+
+namespace b200gbm {
+
+#define B200_CUDA(x)                                                                                      \
+  do {                                                                                                    \
+    cudaError_t e__ = (x);                                                                                \
+    if (e__ != cudaSuccess)                                                                               \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+#define B200_NCCL(x)                                                                                      \
+  do {                                                                                                    \
+    ncclResult_t r__ = (x);                                                                               \
+    if (r__ != ncclSuccess)                                                                               \
+      throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(r__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+[[noreturn]] inline void Fatal(const std::string& m) { throw std::runtime_error(m); }
+
+// ---- per-thread device + network state -------------------------------------------------------
+struct Network {
+  bool active = false;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+};
+Network& Net();                 // thread-local
+int CurrentDevice();            // thread-local CUDA ordinal (selects on first use)
+void SetThreadDevice(int ordinal);
+void EnsureDevice();            // cudaSetDevice(CurrentDevice()) + fail loudly when no GPU
+void NetworkInit(const char* machines, int local_listen_port, int listen_time_out_sec, int num_machines);
+void NetworkFree();
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { Free(); }
+  void Alloc(size_t count) {
+    Free();
+    n = count;
+    if (count) B200_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+  }
+  void Free() { if (p) { cudaFree(p); p = nullptr; } n = 0; }
+  void Zero(cudaStream_t s) { if (p) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void Upload(const T* h, size_t count, cudaStream_t s) { B200_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
+  void Download(T* h, size_t count, cudaStream_t s) const { B200_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+};
+
+// ---- dataset -----------------------------------------------------------------------------------
+class Dataset {
+ public:
+  ~Dataset();
+  // data: host or device pointer (detected); data_type 0=f32 1=f64; reference != null => reuse its bins
+  static Dataset* CreateFromMat(const void* data, int data_type, int nrow, int ncol, int is_row_major, const char* params,
+                                const Dataset* reference);
+  static Dataset* CreateFromCSR(const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type,
+                                int64_t nindptr, int64_t nelem, int64_t num_col, const char* params, const Dataset* reference);
+  // LightGBM streaming ingestion: bins from a column-wise sample, then row blocks pushed in place
+  static Dataset* CreateFromSampledColumn(double** sample_data, int** sample_indices, int ncol, const int* num_per_col,
+                                          int num_sample_row, int num_total_row, const char* params);
+  void PushRows(const void* data, int data_type, int nrow, int ncol, int start_row);
+  void GetBinsRowMajor(uint8_t* out) const;
+  // K4 on this dataset's bins for the given rows (kernel-level parity entry), fp64 [F][256][2]
+  void Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const;
+  void SetField(const char* name, const void* data, int n, int type);
+  void GetField(const char* name, int* out_len, const void** out_ptr, int* out_type) const;
+  void SetFeatureNames(const char** names, int n);
+
+  int device = 0;
+  int num_data = 0, num_total_features = 0;
+  Config cfg;
+  std::vector<FeatureBins> mappers;          // [num_total_features]
+  std::vector<int> used;                     // inner -> real
+  std::vector<int> inner_of;                 // real -> inner or -1
+  std::vector<FeatMeta> meta_host;
+  int nf = 0, nf_pad = 0, num_tiles = 0;
+  size_t rows_stride = 0;
+  DevBuf<uint8_t> bins;                      // [num_tiles][rows_stride][32]
+  DevBuf<FeatMeta> meta;
+  DevBuf<double> ub;                         // [nf][256]
+  std::vector<float> label, weight;
+  std::vector<double> init_score;
+  std::vector<int32_t> query_boundaries, group_sizes;
+  DevBuf<float> d_label, d_weight;
+  DevBuf<int> d_qb;
+  std::vector<std::string> feature_names;
+  cudaStream_t stream = nullptr;
+  double ingest_ms = 0.0;                    // H2D + binning time of the last create (CUDA events)
+
+ private:
+  void FindBins(const void* data, bool on_device, int data_type, int is_row_major);
+  void FindBinsFromColumns(std::vector<std::vector<double>>* nz, int sample_cnt);
+  void BinBlock(const void* data, bool on_device, int data_type, int is_row_major, long long nrow, long long start_row);
+  void UploadMeta();
+};
+
+// ---- booster -----------------------------------------------------------------------------------
+struct ValidSet {
+  const Dataset* ds = nullptr;
+  DevBuf<double> score;   // [K][n]
+};
+
+class Booster {
+ public:
+  Booster(const Dataset* train, const char* params);      // training booster
+  explicit Booster(const std::string& model_text);        // prediction-only booster
+  ~Booster();
+
+  bool UpdateOneIter();                                   // returns is_finished
+  bool UpdateOneIterCustom(const float* grad, const float* hess);
+  void ResetParameter(const char* params);
+  void AddValidData(const Dataset* valid);
+  void MergeFrom(const Booster* other);
+  std::vector<std::string> EvalNames() const;
+  std::vector<double> GetEval(int data_idx);
+  void GetPredict(int data_idx, int64_t* out_len, double* out);
+  int64_t NumPredict(int data_idx) const;
+  void GetRawScores(int data_idx, double* out);
+  std::string SaveModelToString(int start_iteration, int num_iteration, int importance_type) const;
+  std::string DumpModelJson(int start_iteration, int num_iteration) const;
+
+  // instrumentation for bench.py / parity tests (B200GBM_* extensions of the C ABI)
+  struct Timing { double hist_ms = 0, total_ms = 0; long long hist_rows = 0; long long hist_launches = 0, launches = 0; };
+  Timing timing;
+  bool profile_hist = false;                              // time K4 with events on the engine stream
+  void ExportLastHistogram(double* out);                  // fp64 view of the scratch histogram of the last round
+  std::vector<double> trace;                              // per split records (see B200GBM_BoosterGetTrace)
+
+  Config cfg;
+  HostModel model;
+  const Dataset* train = nullptr;
+  int K = 1;
+  int iter = 0;
+  int num_init_iteration = 0;
+
+ private:
+  void InitTraining();
+  void ComputeGradients();
+  bool TrainTrees(const float* custom_g, const float* custom_h);
+  void TrainOneTree(int class_id, HostTree* out);
+  double BoostFromAverage(int class_id);
+  double ObjectiveInitScore(int class_id);
+  std::string ObjectiveString() const;
+
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  bool parallel_ = false;
+  bool const_hessian_ = false;
+  bool has_init_score_ = false;
+  double shrinkage_ = 0.1;
+  std::vector<bool> class_need_train_;
+  double binary_w_[2] = {1.0, 1.0};
+  bool binary_need_train_ = true;
+  std::vector<double> class_init_probs_;
+  SplitParams sp_{};
+  // device state
+  DevBuf<double> score_;        // [K][n]
+  DevBuf<float> grad_, hess_;   // [K][n]
+  DevBuf<int4> qgh_;
+  DevBuf<int> idx0_, idx1_;
+  DevBuf<long long> H_;         // scratch histogram of the current smaller leaf
+  DevBuf<long long> pool_;      // [num_leaves] leaf histograms
+  size_t slot_elems_ = 0;
+  DevBuf<uint8_t> flags_;       // [num_leaves][nf_pad]
+  DevBuf<SplitCand> cands_;     // [2][nf_pad]
+  DevBuf<LeafState> leaves_;
+  DevBuf<TreeCtrl> ctrl_;
+  DevBuf<unsigned char> tree_blob_;
+  TreeDev tree_dev_{};
+  size_t tree_blob_bytes_ = 0;
+  unsigned char* tree_host_ = nullptr;   // pinned mirror of tree_blob_
+  TreeCtrl* ctrl_host_ = nullptr;        // pinned
+  LeafState* leaves_host_ = nullptr;     // pinned
+  DevBuf<unsigned> part_bits_;
+  DevBuf<int> part_chunks_;
+  // lambdarank
+  DevBuf<double> lr_inv_max_dcg_, lr_label_gain_;
+  DevBuf<float> lr_sig_table_;
+  double lr_min_in_ = -50, lr_max_in_ = 50, lr_idx_factor_ = 0;
+  int lr_max_q_ = 0;
+  std::vector<ValidSet*> valids_;
+  int num_sms_ = 148;
+  cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;
+};
+
+}  // namespace b200gbm

@@ -51,7 +51,7 @@ struct HistWork {
   int begin;      // first position in idx (or first row when use_idx == 0)
   int count;      // rows of the leaf on this rank
   int use_idx;    // 0: rows are begin..begin+count-1 directly (root of a full pass)
-  int slot;       // destination slot in the histogram pool
+  int buf;        // which of the two index buffers holds the leaf's row list
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -70,9 +70,8 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int NATOM>
 __global__ void __launch_bounds__(kHistThreads, 1)
 k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tiles,
-              const int4* __restrict__ qgh, const int* __restrict__ idx,
-              const HistWork* __restrict__ work, unsigned long long* __restrict__ hist_pool,
-              size_t slot_elems) {
+              const int4* __restrict__ qgh, const int* __restrict__ idx0, const int* __restrict__ idx1,
+              const HistWork* __restrict__ work, unsigned long long* __restrict__ hist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* plane = reinterpret_cast<unsigned*>(smem_raw);              // [4][kPlaneWords]
   unsigned char* stage_bins = smem_raw + 4 * kPlaneWords * 4;           // [kStages][256][32]
@@ -82,7 +81,7 @@ k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tile
   const int n = w.count;
   if (n <= 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long* hist = hist_pool + static_cast<size_t>(w.slot) * slot_elems;
+  const int* __restrict__ idx = w.buf ? idx1 : idx0;
 
   // rows per work item: large enough to amortise the flush, small enough to fill the grid
   long long cells_rows = static_cast<long long>(n) * num_tiles;

@@ -1,0 +1,800 @@
+// sm_100a kernels of the b200gbm training engine other than K4 (hist_kernel.cuh).
+// Kernel numbering follows SURVEY.md §2.5.  Everything a tree needs lives in device memory
+// (leaf table, control block, tree arrays) so the host enqueues a whole tree without a sync.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "hist_kernel.cuh"
+
+namespace b200gbm {
+
+constexpr double kEpsD = 1e-15;
+#define kNegInf (-__longlong_as_double(0x7ff0000000000000LL))   /* -inf, usable in device code */
+
+struct FeatMeta {          // per inner (used) feature
+  int num_bin;
+  int missing_type;        // 0 none, 2 NaN
+  int default_bin;
+  int offset;              // 1 iff most_freq_bin == 0  ([UPSTREAM] storage convention, affects NaN forward scan)
+  int real_index;
+  int pad0, pad1, pad2;
+};
+
+struct SplitParams {
+  double l1, l2, max_delta_step, min_gain_to_split, min_sum_hessian;
+  int min_data_in_leaf, max_depth, num_leaves, parallel;
+  int nf, nf_pad, num_tiles, pad;
+};
+
+struct SplitCand {         // best threshold of one (leaf, feature)
+  double gain;             // best_gain - min_gain_shift, or -inf
+  double left_g, left_h;   // best_sum_left_gradient / _hessian (hessian still carries +kEpsilon)
+  int threshold, left_count, default_left, feature;   // feature = inner index
+};
+
+struct LeafBest {
+  double gain;
+  double left_g, left_h, right_g, right_h;   // sums as stored in SplitInfo (epsilon removed)
+  double left_out, right_out;
+  int feature, threshold, default_left, left_count, right_count, pad;
+};
+
+struct LeafState {
+  int begin, count, buf, depth;
+  int global_count, identity, hist_slot, parent_node;
+  double sum_g, sum_h;
+  LeafBest best;
+};
+
+struct TreeCtrl {
+  int num_leaves, left_leaf, right_leaf, smaller, larger, go, finished, split_leaf;
+  int split_feature, split_threshold, split_default_left, split_missing_type, split_num_bin, new_leaf, pending, pad;
+  int part_begin, part_count, part_buf, part_identity, part_left_total, smaller_rows, round, pad2;
+  HistWork hist_work;
+  unsigned absmax_bits[2];     // max|g|, max|h| as float bits (non-negative floats order like uints)
+  int exp_g, exp_h;            // fixed-point exponents: q = rint(x * 2^exp)
+  double inv_g, inv_h;         // hist value -> real value
+  long long root_q[4];         // sum q_g, sum q_h, local rows, unused  (allreduced)
+  long long trace_rows;        // sum of rows scanned by K4 this tree (for the roofline byte model)
+};
+
+struct TreeDev {               // SoA tree under construction (sizes: num_leaves / num_leaves-1)
+  int* left_child; int* right_child; int* split_feature_inner; int* threshold_bin; int* decision_type;
+  float* split_gain; double* leaf_value; double* leaf_weight; int* leaf_count; double* internal_value;
+  double* internal_weight; int* internal_count; int* leaf_parent; int* leaf_depth; int* num_leaves;
+};
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ double d_sign(double x) { return (x > 0.0) - (x < 0.0); }
+__device__ __forceinline__ double d_threshold_l1(double s, double l1) {
+  double r = fmax(0.0, fabs(s) - l1);
+  return d_sign(s) * r;
+}
+__device__ __forceinline__ double d_calc_output(double g, double h, const SplitParams& p) {
+  double ret = (p.l1 > 0) ? -d_threshold_l1(g, p.l1) / (h + p.l2) : -g / (h + p.l2);
+  if (p.max_delta_step > 0 && fabs(ret) > p.max_delta_step) ret = d_sign(ret) * p.max_delta_step;
+  return ret;
+}
+__device__ __forceinline__ double d_leaf_gain(double g, double h, const SplitParams& p) {
+  if (!(p.max_delta_step > 0)) {
+    if (p.l1 > 0) { double sg = d_threshold_l1(g, p.l1); return (sg * sg) / (h + p.l2); }
+    return (g * g) / (h + p.l2);
+  }
+  double out = d_calc_output(g, h, p);
+  double sg = (p.l1 > 0) ? d_threshold_l1(g, p.l1) : g;
+  return -(2.0 * sg * out + (h + p.l2) * out * out);
+}
+
+// ---------------------------------------------------------------- binning (dataset creation)
+// One warp per row-of-a-tile: lane = feature of the tile.  Upper bounds of the tile's 32 features sit
+// in shared memory ([32][256] doubles = 64 KB).  ValueToBin: lower-bound search `value <= ub[m]`.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, long long ld, const FeatMeta* __restrict__ meta,
+           const double* __restrict__ ub, int nf, uint8_t* __restrict__ bins, long long rows_stride, long long row_offset) {
+  extern __shared__ double s_ub[];   // [32][256]
+  const int tile = blockIdx.y;
+  for (int e = threadIdx.x; e < 32 * 256; e += blockDim.x) {
+    int f = tile * 32 + (e >> 8);
+    s_ub[e] = f < nf ? ub[static_cast<size_t>(f) * 256 + (e & 255)] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = tile * 32 + lane;
+  FeatMeta m;
+  m.num_bin = 1; m.missing_type = 0; m.real_index = 0;
+  if (u < nf) m = meta[u];
+  const double* myub = s_ub + lane * 256;
+  for (long long r = blockIdx.x * 8LL + warp; r < nrow; r += gridDim.x * 8LL) {
+    unsigned bin = 0;
+    if (u < nf) {
+      double v = row_major ? static_cast<double>(X[r * ld + m.real_index]) : static_cast<double>(X[static_cast<long long>(m.real_index) * ld + r]);
+      if (isnan(v)) {
+        if (m.missing_type == 2) bin = m.num_bin - 1; else v = 0.0;
+      }
+      if (!isnan(v)) {
+        int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
+        while (lo < hi) {
+          int mid = (hi + lo - 1) / 2;
+          if (v <= myub[mid]) hi = mid; else lo = mid + 1;
+        }
+        bin = lo;
+      }
+    }
+    bins[(static_cast<size_t>(tile) * rows_stride + row_offset + r) * 32 + lane] = static_cast<uint8_t>(bin);
+  }
+}
+
+// ---------------------------------------------------------------- K1 gradients
+// [UPSTREAM RegressionL2loss::GetGradients]
+__global__ void k_grad_l2(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                          float* __restrict__ g, float* __restrict__ h, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (weight) { g[i] = static_cast<float>((score[i] - label[i]) * weight[i]); h[i] = weight[i]; }
+    else { g[i] = static_cast<float>(score[i] - label[i]); h[i] = 1.0f; }
+  }
+}
+// [UPSTREAM BinaryLogloss::GetGradients]
+__global__ void k_grad_binary(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                              float* __restrict__ g, float* __restrict__ h, int n, double sigmoid, double w_neg, double w_pos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int is_pos = label[i] > 0;
+    const double lab = is_pos ? 1.0 : -1.0;
+    const double lw = is_pos ? w_pos : w_neg;
+    const double response = -lab * sigmoid / (1.0 + exp(lab * sigmoid * score[i]));
+    const double abs_response = fabs(response);
+    double gg = response * lw, hh = abs_response * (sigmoid - abs_response) * lw;
+    if (weight) { gg *= weight[i]; hh *= weight[i]; }
+    g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
+  }
+}
+// [UPSTREAM MulticlassSoftmax::GetGradients]; score/g/h are class-major [K][n]
+__global__ void k_grad_softmax(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                               float* __restrict__ g, float* __restrict__ h, int n, int K, double factor) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double wmax = score[i];
+    for (int k = 1; k < K; ++k) wmax = fmax(wmax, score[static_cast<size_t>(n) * k + i]);
+    double wsum = 0;
+    for (int k = 0; k < K; ++k) wsum += exp(score[static_cast<size_t>(n) * k + i] - wmax);
+    const int lab = static_cast<int>(label[i]);
+    const double w = weight ? weight[i] : 1.0;
+    for (int k = 0; k < K; ++k) {
+      double p = exp(score[static_cast<size_t>(n) * k + i] - wmax) / wsum;
+      double gg = (lab == k) ? p - 1.0 : p, hh = factor * p * (1.0 - p);
+      if (weight) { gg *= w; hh *= w; }
+      g[static_cast<size_t>(n) * k + i] = static_cast<float>(gg);
+      h[static_cast<size_t>(n) * k + i] = static_cast<float>(hh);
+    }
+  }
+}
+
+// [UPSTREAM LambdarankNDCG::GetGradientsForOneQuery] — one block per query (K2).
+// Sorting: stable rank by score descending (O(cnt^2) rank counting; queries are ~100 docs).
+__global__ void __launch_bounds__(256)
+k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                  const int* __restrict__ qb, int nq, const double* __restrict__ inv_max_dcg, const double* __restrict__ label_gain,
+                  const float* __restrict__ sig_table, int sig_bins, double min_in, double max_in, double idx_factor, double sigmoid,
+                  int truncation, int norm, float* __restrict__ g, float* __restrict__ h, int max_q) {
+  extern __shared__ unsigned char lr_smem[];
+  double* s_score = reinterpret_cast<double*>(lr_smem);                 // [max_q] sorted scores
+  float* s_lam = reinterpret_cast<float*>(s_score + max_q);              // [max_q] by sorted pos
+  float* s_hes = s_lam + max_q;
+  int* s_lab = reinterpret_cast<int*>(s_hes + max_q);                    // label by sorted pos
+  int* s_orig = s_lab + max_q;                                           // original index by sorted pos
+  __shared__ double s_sum_lambda;
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    const int start = qb[q], cnt = qb[q + 1] - start;
+    __syncthreads();
+    if (threadIdx.x == 0) s_sum_lambda = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      double si = score[start + i];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) {
+        double sj = score[start + j];
+        rank += (sj > si) || (sj == si && j < i);
+      }
+      s_score[rank] = si; s_lab[rank] = static_cast<int>(label[start + i]); s_orig[rank] = i;
+      s_lam[rank] = 0.f; s_hes[rank] = 0.f;
+    }
+    __syncthreads();
+    const double imd = inv_max_dcg[q];
+    const double best_score = s_score[0];
+    int worst_idx = cnt - 1;
+    if (worst_idx > 0 && s_score[worst_idx] == kNegInf) worst_idx -= 1;
+    const double worst_score = s_score[worst_idx];
+    // pairs (i<j), i below the truncation level.  Accumulation order differs from the sequential
+    // reference only in fp32 addition order of per-document lambdas (documented tolerance).
+    const int ilim = min(cnt - 1, truncation);
+    double local_sum = 0.0;
+    for (int p = threadIdx.x; p < ilim * cnt; p += blockDim.x) {
+      const int i = p / cnt, j = p % cnt;
+      if (j <= i) continue;
+      if (s_score[i] == kNegInf || s_score[j] == kNegInf) continue;
+      if (s_lab[i] == s_lab[j]) continue;
+      int hr, lr;
+      if (s_lab[i] > s_lab[j]) { hr = i; lr = j; } else { hr = j; lr = i; }
+      const double delta_score = s_score[hr] - s_score[lr];
+      const double dcg_gap = label_gain[s_lab[hr]] - label_gain[s_lab[lr]];
+      const double paired_discount = fabs(1.0 / log2(2.0 + hr) - 1.0 / log2(2.0 + lr));
+      double delta = dcg_gap * paired_discount * imd;
+      if (norm && best_score != worst_score) delta /= (0.01f + fabs(delta_score));
+      double p_lambda;
+      if (delta_score <= min_in) p_lambda = sig_table[0];
+      else if (delta_score >= max_in) p_lambda = sig_table[sig_bins - 1];
+      else p_lambda = sig_table[static_cast<size_t>((delta_score - min_in) * idx_factor)];
+      double p_hessian = p_lambda * (1.0f - p_lambda);
+      p_lambda *= -sigmoid * delta;
+      p_hessian *= sigmoid * sigmoid * delta;
+      atomicAdd(&s_lam[lr], -static_cast<float>(p_lambda));
+      atomicAdd(&s_hes[lr], static_cast<float>(p_hessian));
+      atomicAdd(&s_lam[hr], static_cast<float>(p_lambda));
+      atomicAdd(&s_hes[hr], static_cast<float>(p_hessian));
+      local_sum -= 2 * p_lambda;
+    }
+    atomicAdd(&s_sum_lambda, local_sum);
+    __syncthreads();
+    double nf = 1.0;
+    const double sum_lambdas = s_sum_lambda;
+    const bool do_norm = norm && sum_lambdas > 0;
+    if (do_norm) nf = log2(1 + sum_lambdas) / sum_lambdas;
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+      float lam = s_lam[r], hes = s_hes[r];
+      if (do_norm) { lam = static_cast<float>(lam * nf); hes = static_cast<float>(hes * nf); }
+      int o = start + s_orig[r];
+      if (weight) { lam = static_cast<float>(lam * weight[o]); hes = static_cast<float>(hes * weight[o]); }
+      g[o] = lam; h[o] = hes;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- quantisation + root sums (K3)
+__global__ void k_absmax(const float* __restrict__ g, const float* __restrict__ h, int n, TreeCtrl* ctrl) {
+  float mg = 0.f, mh = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    mg = fmaxf(mg, fabsf(g[i])); mh = fmaxf(mh, fabsf(h[i]));
+  }
+  for (int o = 16; o; o >>= 1) { mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&ctrl->absmax_bits[0], __float_as_uint(mg));
+    atomicMax(&ctrl->absmax_bits[1], __float_as_uint(mh));
+  }
+}
+// exponents so that |q| < 2^35:  e = 34 - ilogb(max)
+__global__ void k_set_scale(TreeCtrl* ctrl, int const_hessian, double hess_const) {
+  float mg = __uint_as_float(ctrl->absmax_bits[0]), mh = __uint_as_float(ctrl->absmax_bits[1]);
+  int eg = (mg > 0.f && isfinite(mg)) ? 34 - ilogbf(mg) : 0;
+  int eh = (mh > 0.f && isfinite(mh)) ? 34 - ilogbf(mh) : 0;
+  eg = max(min(eg, 1000), -1000); eh = max(min(eh, 1000), -1000);
+  ctrl->exp_g = eg; ctrl->exp_h = eh;
+  ctrl->inv_g = ldexp(1.0, -eg);
+  ctrl->inv_h = const_hessian ? hess_const : ldexp(1.0, -eh);
+  ctrl->root_q[0] = 0; ctrl->root_q[1] = 0; ctrl->root_q[2] = 0; ctrl->root_q[3] = 0;
+}
+__global__ void __launch_bounds__(256)
+k_quantize(const float* __restrict__ g, const float* __restrict__ h, int n, int4* __restrict__ qgh, TreeCtrl* ctrl, int const_hessian) {
+  const int eg = ctrl->exp_g, eh = ctrl->exp_h;
+  long long sg = 0, sh = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long qg = __double2ll_rn(ldexp(static_cast<double>(g[i]), eg));
+    int4 q;
+    q.x = static_cast<int>(qg >> kLoBits); q.y = static_cast<int>(qg & ((1LL << kLoBits) - 1));
+    long long qh;
+    if (const_hessian) { qh = 1; q.z = 1; q.w = 0; }
+    else { qh = __double2ll_rn(ldexp(static_cast<double>(h[i]), eh)); q.z = static_cast<int>(qh >> kLoBits); q.w = static_cast<int>(qh & ((1LL << kLoBits) - 1)); }
+    qgh[i] = q;
+    sg += qg; sh += qh;
+  }
+  for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sh += __shfl_xor_sync(0xffffffffu, sh, o); }
+  __shared__ long long s_g[8], s_h[8];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_g[warp] = sg; s_h[warp] = sh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += s_g[w]; b += s_h[w]; }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[0]), static_cast<unsigned long long>(a));
+    atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[1]), static_cast<unsigned long long>(b));
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[2]), static_cast<unsigned long long>(n));
+  }
+}
+
+// ---------------------------------------------------------------- tree init / round controller
+__global__ void __launch_bounds__(256)
+k_tree_init(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, SplitParams p, int n_local, const uint8_t* feature_used) {
+  for (int u = threadIdx.x; u < p.nf_pad; u += blockDim.x) flags[u] = (u < p.nf && (!feature_used || feature_used[u])) ? 1 : 0;
+  for (int l = threadIdx.x; l < p.num_leaves; l += blockDim.x) {
+    leaves[l].best.gain = kNegInf; leaves[l].best.feature = -1;
+    tree.leaf_parent[l] = -1; tree.leaf_depth[l] = 0; tree.leaf_value[l] = 0; tree.leaf_weight[l] = 0; tree.leaf_count[l] = 0;
+  }
+  if (threadIdx.x == 0) {
+    LeafState& r = leaves[0];
+    r.begin = 0; r.count = n_local; r.buf = 0; r.depth = 0; r.identity = 1; r.hist_slot = 0; r.parent_node = -1;
+    r.global_count = static_cast<int>(ctrl->root_q[2]);
+    r.sum_g = static_cast<double>(ctrl->root_q[0]) * ctrl->inv_g;
+    r.sum_h = static_cast<double>(ctrl->root_q[1]) * ctrl->inv_h;
+    ctrl->num_leaves = 1; ctrl->left_leaf = 0; ctrl->right_leaf = -1; ctrl->smaller = 0; ctrl->larger = -1;
+    ctrl->go = 0; ctrl->finished = 0; ctrl->split_leaf = -1; ctrl->pending = 0; ctrl->round = 0; ctrl->trace_rows = 0;
+    *tree.num_leaves = 1;
+  }
+}
+
+// Applies the split chosen in the previous round (Tree::Split + leaf bookkeeping, using the TRUE row
+// counts in the serial learner and the hessian-reconstructed global counts in the data-parallel one),
+// then runs SerialTreeLearner::BeforeFindBestSplit for the coming round.
+__global__ void __launch_bounds__(256)
+k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p,
+            int last) {
+  __shared__ int s_copy_from, s_copy_to;
+  if (threadIdx.x == 0) {
+    s_copy_from = -1; s_copy_to = -1;
+    if (ctrl->pending) {
+      ctrl->pending = 0;
+      const int leaf = ctrl->split_leaf, nl = ctrl->new_leaf;
+      LeafState& L = leaves[leaf];
+      LeafState& R = leaves[nl];
+      LeafBest b = L.best;
+      const int true_left = ctrl->part_left_total, true_right = ctrl->part_count - true_left;
+      if (!p.parallel) { b.left_count = true_left; b.right_count = true_right; }
+      // Tree::Split
+      const int node = ctrl->num_leaves - 1;
+      const int parent = tree.leaf_parent[leaf];
+      if (parent >= 0) {
+        if (tree.left_child[parent] == ~leaf) tree.left_child[parent] = node; else tree.right_child[parent] = node;
+      }
+      tree.split_feature_inner[node] = b.feature;
+      tree.split_gain[node] = static_cast<float>(b.gain + p.min_gain_to_split);
+      tree.left_child[node] = ~leaf; tree.right_child[node] = ~nl;
+      tree.leaf_parent[leaf] = node; tree.leaf_parent[nl] = node;
+      tree.internal_weight[node] = tree.leaf_weight[leaf];
+      tree.internal_value[node] = tree.leaf_value[leaf];
+      tree.internal_count[node] = b.left_count + b.right_count;
+      tree.leaf_value[leaf] = isnan(b.left_out) ? 0.0 : b.left_out;
+      tree.leaf_weight[leaf] = b.left_h; tree.leaf_count[leaf] = b.left_count;
+      tree.leaf_value[nl] = isnan(b.right_out) ? 0.0 : b.right_out;
+      tree.leaf_weight[nl] = b.right_h; tree.leaf_count[nl] = b.right_count;
+      tree.leaf_depth[nl] = tree.leaf_depth[leaf] + 1; tree.leaf_depth[leaf] += 1;
+      const FeatMeta fm = meta[b.feature];
+      tree.decision_type[node] = (b.default_left ? 2 : 0) | (fm.missing_type << 2);
+      tree.threshold_bin[node] = b.threshold;
+      ctrl->num_leaves += 1; *tree.num_leaves = ctrl->num_leaves;
+      // data partition bookkeeping: children live in the other index buffer
+      const int dst_buf = L.identity ? 0 : (L.buf ^ 1);
+      R.begin = L.begin + true_left; R.count = true_right; R.buf = dst_buf; R.identity = 0; R.depth = L.depth + 1;
+      L.count = true_left; L.buf = dst_buf; L.identity = 0; L.depth += 1;
+      L.global_count = b.left_count; R.global_count = b.right_count;
+      L.sum_g = b.left_g; L.sum_h = b.left_h; R.sum_g = b.right_g; R.sum_h = b.right_h;
+      R.hist_slot = nl;
+      L.best.gain = kNegInf; L.best.feature = -1; R.best.gain = kNegInf; R.best.feature = -1;
+      ctrl->left_leaf = leaf; ctrl->right_leaf = nl;
+    }
+    ctrl->go = 0; ctrl->smaller = -1; ctrl->larger = -1; ctrl->split_leaf = -1;
+    ctrl->hist_work.count = 0; ctrl->part_count = 0;
+    if (!ctrl->finished && !last && ctrl->num_leaves < p.num_leaves) {
+      const int ll = ctrl->left_leaf, rl = ctrl->right_leaf;
+      bool go = true;
+      if (p.max_depth > 0 && tree.leaf_depth[ll] >= p.max_depth) go = false;
+      const int nl_cnt = leaves[ll].global_count, nr_cnt = rl >= 0 ? leaves[rl].global_count : 0;
+      if (go && nr_cnt < p.min_data_in_leaf * 2 && nl_cnt < p.min_data_in_leaf * 2) go = false;
+      if (!go) {
+        leaves[ll].best.gain = kNegInf;
+        if (rl >= 0) leaves[rl].best.gain = kNegInf;
+      } else {
+        int smaller = ll, larger = -1;
+        if (rl >= 0) {
+          if (nl_cnt < nr_cnt) { smaller = ll; larger = rl; } else { smaller = rl; larger = ll; }
+          // parent's histogram sits in the slot of `ll`; the larger child inherits it
+          if (larger == rl) { int t = leaves[ll].hist_slot; leaves[ll].hist_slot = leaves[rl].hist_slot; leaves[rl].hist_slot = t; }
+          s_copy_from = ll; s_copy_to = rl;
+        }
+        ctrl->smaller = smaller; ctrl->larger = larger; ctrl->go = 1;
+        const LeafState& S = leaves[smaller];
+        ctrl->hist_work.begin = S.begin; ctrl->hist_work.count = S.count; ctrl->hist_work.use_idx = S.identity ? 0 : 1;
+        ctrl->hist_work.buf = S.buf;       // K4 reads the row list from index buffer `buf`
+        ctrl->smaller_rows = S.count;
+        ctrl->trace_rows += S.count;
+      }
+    }
+    ctrl->round += 1;
+  }
+  __syncthreads();
+  if (s_copy_from >= 0)   // children inherit the parent's per-feature is_splittable flags
+    for (int u = threadIdx.x; u < p.nf_pad; u += blockDim.x) flags[static_cast<size_t>(s_copy_to) * p.nf_pad + u] = flags[static_cast<size_t>(s_copy_from) * p.nf_pad + u];
+}
+
+// ---------------------------------------------------------------- K5/K6 split scan
+// One warp per (which in {smaller, larger}, feature).  Lane l owns bins 8l..8l+7.  All prefix sums are
+// exact int64; gains are fp64.  Replaces FeatureHistogram::FindBestThresholdSequentially (+Subtract).
+__device__ __forceinline__ long long warp_suffix_excl(long long v, int lane) {   // sum over lanes > lane
+  long long inc = v;
+  for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_down_sync(0xffffffffu, inc, o); if (lane + o < 32) inc += t; }
+  return inc - v;
+}
+__device__ __forceinline__ long long warp_prefix_excl(long long v, int lane) {   // sum over lanes < lane
+  long long inc = v;
+  for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  return inc - v;
+}
+
+__global__ void __launch_bounds__(256)
+k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta,
+       const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
+       SplitCand* __restrict__ cands, SplitParams p) {
+  if (!ctrl->go) return;
+  const int which = blockIdx.y;
+  const int leaf = which ? ctrl->larger : ctrl->smaller;
+  if (leaf < 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = blockIdx.x * 8 + warp;
+  if (u >= p.nf) return;
+  SplitCand out;
+  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
+  if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
+
+  const LeafState& L = leaves[leaf];
+  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
+  const long long* src = H + static_cast<size_t>(u) * 512;
+  long long qg[8], qh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = lane * 8 + j;
+    longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
+    if (which) {
+      longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2);
+      s.x = pr.x - s.x; s.y = pr.y - s.y;
+    }
+    *reinterpret_cast<longlong2*>(dst + b * 2) = s;
+    qg[j] = s.x; qh[j] = s.y;
+  }
+  const FeatMeta m = meta[u];
+  const double inv_g = ctrl->inv_g, inv_h = ctrl->inv_h;
+  const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
+  const int num_data = L.global_count;
+  const double cnt_factor = num_data / sum_h;
+  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, p) + p.min_gain_to_split;
+  const bool two_way = (m.num_bin > 2 && m.missing_type == 2);
+  const int na = two_way ? 1 : 0;
+
+  int cnt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cnt[j] = static_cast<int>(static_cast<double>(qh[j]) * inv_h * cnt_factor + 0.5);
+
+  // ---- reverse pass: bins num_bin-1-na .. 1, candidate threshold = b-1
+  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
+  int best_thr = -1, best_lc = 0, best_dl = 1;
+  bool any_valid = false;
+  {
+    const int hi = m.num_bin - 1 - na;
+    long long lg = 0, lh = 0, lc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int b = lane * 8 + j; if (b >= 1 && b <= hi) { lg += qg[j]; lh += qh[j]; lc += cnt[j]; } }
+    long long rg = warp_suffix_excl(lg, lane), rh = warp_suffix_excl(lh, lane), rc = warp_suffix_excl(lc, lane);
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const int b = lane * 8 + j;
+      if (b < 1 || b > hi) continue;
+      rg += qg[j]; rh += qh[j]; rc += cnt[j];
+      const double srg = static_cast<double>(rg) * inv_g;
+      const double srh = kEpsD + static_cast<double>(rh) * inv_h;
+      const int right_count = static_cast<int>(rc);
+      if (right_count < p.min_data_in_leaf || srh < p.min_sum_hessian) continue;
+      const int left_count = num_data - right_count;
+      if (left_count < p.min_data_in_leaf) continue;
+      const double slh = sum_h - srh;
+      if (slh < p.min_sum_hessian) continue;
+      const double slg = sum_g - srg;
+      const double gain = d_leaf_gain(slg, slh, p) + d_leaf_gain(srg, srh, p);
+      if (gain <= min_gain_shift) continue;
+      any_valid = true;
+      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_thr = b - 1; best_lc = left_count; }
+    }
+    // warp argmax: higher gain, ties -> higher threshold (first seen in the right-to-left scan)
+    for (int o = 16; o; o >>= 1) {
+      double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+      int ot = __shfl_xor_sync(0xffffffffu, best_thr, o);
+      double olg = __shfl_xor_sync(0xffffffffu, best_lg, o), olh = __shfl_xor_sync(0xffffffffu, best_lh, o);
+      int olc = __shfl_xor_sync(0xffffffffu, best_lc, o);
+      if (og > best_gain || (og == best_gain && ot > best_thr)) { best_gain = og; best_thr = ot; best_lg = olg; best_lh = olh; best_lc = olc; }
+    }
+  }
+  // ---- forward pass (NaN-as-missing features only): bins 0 .. num_bin-2, threshold = b, NaN goes right
+  if (two_way) {
+    const int hi = m.num_bin - 2;
+    long long ag = 0, ah = 0, ac = 0;     // everything stored except bin 0 (incl. the NaN bin)
+    long long lg = 0, lh = 0, lc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = lane * 8 + j;
+      if (b >= 1 && b < m.num_bin) { ag += qg[j]; ah += qh[j]; ac += cnt[j]; }
+      if (b >= m.offset && b <= hi) { lg += qg[j]; lh += qh[j]; lc += cnt[j]; }
+    }
+    for (int o = 16; o; o >>= 1) { ag += __shfl_xor_sync(0xffffffffu, ag, o); ah += __shfl_xor_sync(0xffffffffu, ah, o); ac += __shfl_xor_sync(0xffffffffu, ac, o); }
+    long long pg = warp_prefix_excl(lg, lane), ph = warp_prefix_excl(lh, lane), pc = warp_prefix_excl(lc, lane);
+    double base_g = 0.0, base_h = kEpsD; int base_c = 0;
+    if (m.offset == 1) {   // implicit bin 0 = leaf total - everything stored  [UPSTREAM NA_AS_MISSING && offset==1]
+      base_g = sum_g - static_cast<double>(ag) * inv_g;
+      base_h = (sum_h - kEpsD) - static_cast<double>(ah) * inv_h;
+      base_c = num_data - static_cast<int>(ac);
+    }
+    double f_gain = kNegInf, f_lg = 0, f_lh = 0; int f_thr = 1 << 30, f_lc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = lane * 8 + j;
+      if (b > hi) continue;
+      if (b >= m.offset) { pg += qg[j]; ph += qh[j]; pc += cnt[j]; }
+      const double slg = base_g + static_cast<double>(pg) * inv_g;
+      const double slh = base_h + static_cast<double>(ph) * inv_h;
+      const int left_count = base_c + static_cast<int>(pc);
+      if (left_count < p.min_data_in_leaf || slh < p.min_sum_hessian) continue;
+      const int right_count = num_data - left_count;
+      if (right_count < p.min_data_in_leaf) continue;
+      const double srh = sum_h - slh;
+      if (srh < p.min_sum_hessian) continue;
+      const double srg = sum_g - slg;
+      const double gain = d_leaf_gain(slg, slh, p) + d_leaf_gain(srg, srh, p);
+      if (gain <= min_gain_shift) continue;
+      any_valid = true;
+      if (gain > f_gain) { f_gain = gain; f_lg = slg; f_lh = slh; f_thr = b; f_lc = left_count; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      double og = __shfl_xor_sync(0xffffffffu, f_gain, o);
+      int ot = __shfl_xor_sync(0xffffffffu, f_thr, o);
+      double olg = __shfl_xor_sync(0xffffffffu, f_lg, o), olh = __shfl_xor_sync(0xffffffffu, f_lh, o);
+      int olc = __shfl_xor_sync(0xffffffffu, f_lc, o);
+      if (og > f_gain || (og == f_gain && ot < f_thr)) { f_gain = og; f_thr = ot; f_lg = olg; f_lh = olh; f_lc = olc; }
+    }
+    if (f_gain > best_gain) { best_gain = f_gain; best_thr = f_thr; best_lg = f_lg; best_lh = f_lh; best_lc = f_lc; best_dl = 0; }
+  } else if (m.missing_type == 2) {
+    best_dl = 0;
+  }
+  any_valid = __any_sync(0xffffffffu, any_valid);
+  if (lane == 0) {
+    *flag = any_valid ? 1 : 0;
+    if (any_valid && best_gain > min_gain_shift) {
+      out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = best_thr;
+      out.left_count = best_lc; out.default_left = best_dl;
+    }
+    cands[which * p.nf_pad + u] = out;
+  }
+}
+
+// argmax over features per leaf (gain desc, real feature index asc), then over leaves
+// (SplitInfo::operator> : gain desc, feature asc; ArrayArgs::ArgMax keeps the first on full ties).
+__global__ void __launch_bounds__(256)
+k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* __restrict__ cands, SplitParams p) {
+  __shared__ double s_gain[256];
+  __shared__ int s_feat[256], s_idx[256];
+  if (ctrl->go) {
+    for (int which = 0; which < 2; ++which) {
+      const int leaf = which ? ctrl->larger : ctrl->smaller;
+      if (leaf < 0) continue;
+      double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
+      for (int u = threadIdx.x; u < p.nf; u += blockDim.x) {
+        const SplitCand& c = cands[which * p.nf_pad + u];
+        const int rf = meta[u].real_index;
+        if (c.gain > bg || (c.gain == bg && rf < bf)) { bg = c.gain; bf = rf; bi = u; }
+      }
+      s_gain[threadIdx.x] = bg; s_feat[threadIdx.x] = bf; s_idx[threadIdx.x] = bi;
+      __syncthreads();
+      for (int s = 128; s; s >>= 1) {
+        if (threadIdx.x < s) {
+          double og = s_gain[threadIdx.x + s]; int of = s_feat[threadIdx.x + s];
+          if (og > s_gain[threadIdx.x] || (og == s_gain[threadIdx.x] && of < s_feat[threadIdx.x])) {
+            s_gain[threadIdx.x] = og; s_feat[threadIdx.x] = of; s_idx[threadIdx.x] = s_idx[threadIdx.x + s];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        LeafState& L = leaves[leaf];
+        LeafBest b;
+        b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
+        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.pad = 0;
+        if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
+          const SplitCand& c = cands[which * p.nf_pad + s_idx[0]];
+          const double sum_h = L.sum_h + 2 * kEpsD;
+          b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
+          b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
+          b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
+          b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
+          b.left_out = d_calc_output(c.left_g, c.left_h, p);
+          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, p);
+        }
+        L.best = b;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0 && !ctrl->finished) {
+    int best_leaf = 0;
+    for (int l = 1; l < ctrl->num_leaves; ++l) {
+      const LeafBest& a = leaves[l].best;
+      const LeafBest& b = leaves[best_leaf].best;
+      const int fa = a.feature < 0 ? 0x7fffffff : meta[a.feature].real_index;
+      const int fb = b.feature < 0 ? 0x7fffffff : meta[b.feature].real_index;
+      if (a.gain > b.gain || (a.gain == b.gain && fa < fb)) best_leaf = l;
+    }
+    const LeafBest& b = leaves[best_leaf].best;
+    if (!(b.gain > 0.0) || ctrl->num_leaves >= p.num_leaves) {
+      ctrl->finished = 1; ctrl->split_leaf = -1; ctrl->part_count = 0;
+    } else {
+      const LeafState& L = leaves[best_leaf];
+      const FeatMeta fm = meta[b.feature];
+      ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
+      ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
+      ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
+      ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
+      ctrl->part_left_total = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K7 row partition (stable)
+constexpr int kPartChunk = 2048;     // rows per chunk = 256 threads x 8
+__device__ __forceinline__ bool d_goes_left(unsigned bin, const TreeCtrl* c) {
+  if (c->split_missing_type == 2 && bin == static_cast<unsigned>(c->split_num_bin - 1)) return c->split_default_left != 0;
+  return bin <= static_cast<unsigned>(c->split_threshold);
+}
+// pass 1: decision bit per row (ballot words) + left count per chunk
+__global__ void __launch_bounds__(256)
+k_part_count(const TreeCtrl* __restrict__ ctrl, const uint8_t* __restrict__ bins, size_t rows_stride, const int* __restrict__ idx0,
+             const int* __restrict__ idx1, unsigned* __restrict__ bits, int* __restrict__ chunk_left) {
+  const int n = ctrl->part_count;
+  if (n <= 0) return;
+  const int* src = ctrl->part_buf ? idx1 : idx0;
+  const int f = ctrl->split_feature;
+  const uint8_t* col = bins + (static_cast<size_t>(f >> 5) * rows_stride) * 32 + (f & 31);
+  const int chunks = (n + kPartChunk - 1) / kPartChunk;
+  __shared__ int s_cnt[8];
+  for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = c * kPartChunk + k * 256 + threadIdx.x;
+      bool left = false;
+      if (i < n) {
+        const int r = ctrl->part_identity ? (ctrl->part_begin + i) : src[ctrl->part_begin + i];
+        left = d_goes_left(col[static_cast<size_t>(r) * 32], ctrl);
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, left);
+      if ((threadIdx.x & 31) == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
+    }
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_cnt[w]; chunk_left[c] = t; }
+    __syncthreads();
+  }
+}
+// pass 2: exclusive scan of the chunk counts (single block)
+__global__ void __launch_bounds__(1024)
+k_part_scan(TreeCtrl* ctrl, int* __restrict__ chunk_left) {
+  const int n = ctrl->part_count;
+  if (n <= 0) return;
+  const int chunks = (n + kPartChunk - 1) / kPartChunk;
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < chunks; base += 1024) {
+    const int i = base + threadIdx.x;
+    int v = i < chunks ? chunk_left[i] : 0;
+    int inc = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane], winc = w;
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + inc - v;
+    if (i < chunks) chunk_left[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ctrl->part_left_total = s_carry;
+}
+// pass 3: stable scatter into the other index buffer (lefts first, then rights, original order kept)
+__global__ void __launch_bounds__(256)
+k_part_scatter(const TreeCtrl* __restrict__ ctrl, int* __restrict__ idx0, int* __restrict__ idx1, const unsigned* __restrict__ bits,
+               const int* __restrict__ chunk_left) {
+  const int n = ctrl->part_count;
+  if (n <= 0) return;
+  const int* src = ctrl->part_buf ? idx1 : idx0;
+  int* dst = ctrl->part_identity ? idx0 : (ctrl->part_buf ? idx0 : idx1);
+  const int begin = ctrl->part_begin, total_left = ctrl->part_left_total;
+  const int chunks = (n + kPartChunk - 1) / kPartChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int s_wl[64];
+  for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+    // 64 ballot words per chunk; word w covers rows c*2048 + w*32 ..
+    const int wbase = c * (kPartChunk / 32);
+    if (threadIdx.x < 64) {
+      const int i0 = c * kPartChunk + threadIdx.x * 32;
+      s_wl[threadIdx.x] = i0 < n ? __popc(bits[wbase + threadIdx.x]) : 0;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 64 word counts (two per lane)
+      int a = s_wl[lane * 2], b = s_wl[lane * 2 + 1];
+      int sum = a + b, inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      int ex = inc - sum;
+      s_wl[lane * 2] = ex; s_wl[lane * 2 + 1] = ex + a;
+    }
+    __syncthreads();
+    const int left_base = chunk_left[c];
+    const int right_base = c * kPartChunk - left_base;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int w = k * 8 + warp;                 // word index inside the chunk
+      const int i = c * kPartChunk + w * 32 + lane;
+      if (i < n) {
+        const unsigned word = bits[wbase + w];
+        const bool left = (word >> lane) & 1u;
+        const int lefts_before = s_wl[w] + __popc(word & ((1u << lane) - 1u));
+        const int r = ctrl->part_identity ? (begin + i) : src[begin + i];
+        int pos;
+        if (left) pos = begin + left_base + lefts_before;
+        else pos = begin + total_left + right_base + (w * 32 + lane - lefts_before);
+        dst[pos] = r;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- K8/K9 leaf values -> scores
+// score[row] += shrinkage * leaf_value[leaf(row)], via the final data partition
+__global__ void __launch_bounds__(256)
+k_add_score(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, TreeDev tree, const int* __restrict__ idx0,
+            const int* __restrict__ idx1, double* __restrict__ score, double shrinkage) {
+  const int nl = ctrl->num_leaves;
+  if (nl <= 1) return;
+  for (int l = 0; l < nl; ++l) {
+    const LeafState& L = leaves[l];
+    double v = tree.leaf_value[l] * shrinkage;
+    if (!(fabs(v) > 1e-35)) v = 0.0;
+    const int* src = L.buf ? idx1 : idx0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.count; i += gridDim.x * blockDim.x) {
+      const int r = L.identity ? (L.begin + i) : src[L.begin + i];
+      score[r] += v;
+    }
+  }
+}
+__global__ void k_add_const(double* __restrict__ score, int n, double v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) score[i] += v;
+}
+// score of a (validation) dataset += shrinkage * tree(row), traversing by bin thresholds
+__global__ void __launch_bounds__(256)
+k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t* __restrict__ bins, size_t rows_stride, int n,
+                  double* __restrict__ score, double shrinkage) {
+  const int nl = *tree.num_leaves;
+  if (nl <= 1) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int node = 0;
+    while (node >= 0) {
+      const int f = tree.split_feature_inner[node];
+      const unsigned bin = bins[(static_cast<size_t>(f >> 5) * rows_stride + i) * 32 + (f & 31)];
+      const int dt = tree.decision_type[node];
+      bool left;
+      if (((dt >> 2) & 3) == 2 && bin == static_cast<unsigned>(meta[f].num_bin - 1)) left = dt & 2;
+      else left = bin <= static_cast<unsigned>(tree.threshold_bin[node]);
+      node = left ? tree.left_child[node] : tree.right_child[node];
+    }
+    double v = tree.leaf_value[~node] * shrinkage;
+    if (!(fabs(v) > 1e-35)) v = 0.0;
+    score[i] += v;
+  }
+}
+
+// histogram int64 -> fp64 (debug / parity export)
+__global__ void k_hist_to_double(const long long* __restrict__ H, double* __restrict__ out, size_t elems, const TreeCtrl* ctrl) {
+  const double ig = ctrl->inv_g, ih = ctrl->inv_h;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < elems; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<double>(H[i]) * ((i & 1) ? ih : ig);
+}
+
+}  // namespace b200gbm

@@ -155,12 +155,12 @@ int main(int argc, char** argv) {
   // correctness on the first 1M rows (contiguous) and on a strided index list
   {
     int n_chk = (int)std::min<size_t>(N, 1000000);
-    HistWork hw[2] = {{0, n_chk, 0, 0}, {0, n_chk / 3, 1, 1}};
+    HistWork hw[2] = {{0, n_chk, 0, 0}, {0, n_chk / 3, 1, 0}};
     CK(cudaMemcpy(d_work, hw, sizeof(hw), cudaMemcpyHostToDevice));
     gen_idx<<<nsm, 256>>>(d_idx, n_chk / 3, 3);
     CK(cudaMemset(d_hist, 0, slot_elems * 8 * 2));
-    k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_work, d_hist, slot_elems);
-    k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_work + 1, d_hist, slot_elems);
+    k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+    k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
     CK(cudaDeviceSynchronize());
     std::vector<long long> got(slot_elems * 2), want(slot_elems * 2, 0);
     CK(cudaMemcpy(got.data(), d_hist, slot_elems * 16, cudaMemcpyDeviceToHost));
@@ -193,8 +193,8 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 2; ++r) {
       CK(cudaMemsetAsync(d_hist, 0, slot_elems * 8));
       CK(cudaEventRecord(e0));
-      if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_work, d_hist, slot_elems);
-      else k4_hist_build<3><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_work, d_hist, slot_elems);
+      if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+      else k4_hist_build<3><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
       if (r >= 2) { best = std::min(best, ms); tot += ms; }
