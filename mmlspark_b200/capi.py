@@ -114,12 +114,16 @@ class PinnedBuffer:
             self.ptr = C.c_void_p()
 
 
+def _vp(p):
+    return p if isinstance(p, C.c_void_p) else C.c_void_p(int(p))
+
+
 def memcpy(dst_ptr, src_ptr, nbytes):
-    check(load().B200GBM_Memcpy(dst_ptr, src_ptr, C.c_size_t(nbytes)))
+    check(load().B200GBM_Memcpy(_vp(dst_ptr), _vp(src_ptr), C.c_size_t(nbytes)))
 
 
 def synthetic_fill(dev_x, dev_label, row_start, nrow, ncol, seed, kind):
-    check(load().B200GBM_SyntheticFill(dev_x, dev_label, C.c_int64(row_start), C.c_int32(nrow), C.c_int32(ncol), C.c_uint64(seed), C.c_int(kind)))
+    check(load().B200GBM_SyntheticFill(_vp(dev_x), _vp(dev_label) if dev_label is not None else None, C.c_int64(row_start), C.c_int32(nrow), C.c_int32(ncol), C.c_uint64(seed), C.c_int(kind)))
 
 
 def synthetic_rows(rows, ncol, seed, kind):
@@ -152,7 +156,7 @@ class Dataset:
     @classmethod
     def from_device_ptr(cls, ptr, dtype_code, n, F, params="", reference=None):
         h = C.c_void_p()
-        check(load().LGBM_DatasetCreateFromMat(ptr, C.c_int(dtype_code), C.c_int32(n), C.c_int32(F), C.c_int(1), params.encode(),
+        check(load().LGBM_DatasetCreateFromMat(_vp(ptr), C.c_int(dtype_code), C.c_int32(n), C.c_int32(F), C.c_int(1), params.encode(),
                                                reference.handle if reference is not None else None, C.byref(h)))
         return cls(h)
 
@@ -191,7 +195,7 @@ class Dataset:
             nrow, ncol = data.shape
             check(load().LGBM_DatasetPushRows(self.handle, _ptr(data), C.c_int(_np_dtype_code(data)), C.c_int32(nrow), C.c_int32(ncol), C.c_int32(start_row)))
         else:
-            check(load().LGBM_DatasetPushRows(self.handle, data, C.c_int(dtype_code), C.c_int32(nrow), C.c_int32(ncol), C.c_int32(start_row)))
+            check(load().LGBM_DatasetPushRows(self.handle, _vp(data), C.c_int(dtype_code), C.c_int32(nrow), C.c_int32(ncol), C.c_int32(start_row)))
 
     def set_field(self, name, arr):
         if name in ("label", "weight"):

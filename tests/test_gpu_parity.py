@@ -1,0 +1,290 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bar (BASELINE.json north_star): bin indices and tree structure bit-exact; leaf values
+and split gains within 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DS_PARAMS = "max_bin=255 is_pre_partition=True bin_construct_sample_cnt=200000 num_threads=0"
+
+
+def _classifier_params(objective="binary", extra="", iters=100, leaves=31, machines=1):
+    # byte-for-byte what TrainParams.toString emits (TrainParams.scala:47-63,83-88)
+    return ("metric= boost_from_average=true is_pre_partition=True boosting_type=gbdt tree_learner=data_parallel top_k=20 "
+            "num_iterations=%d learning_rate=0.1 num_leaves=%d max_bin=255 bagging_fraction=1.0 pos_bagging_fraction=1.0 "
+            "neg_bagging_fraction=1.0 bagging_freq=0 bagging_seed=3 early_stopping_round=0 feature_fraction=1.0 max_depth=-1 "
+            "min_sum_hessian_in_leaf=0.001 num_machines=%d verbosity=-1 lambda_l1=0.0 lambda_l2=0.0 metric= "
+            "min_gain_to_split=0.0 max_delta_step=0.0 min_data_in_leaf=20 objective=%s num_threads=0 %s" % (iters, leaves, machines, objective, extra))
+
+
+def _make(X, y, ds_params=DS_PARAMS, weight=None, group=None, init_score=None):
+    from mmlspark_b200 import capi
+    from oracle import oracle as O
+    ds = capi.Dataset.from_mat(X, ds_params)
+    ods = O.OracleDataset(X, ds_params)
+    for name, arr in (("label", y), ("weight", weight), ("group", group), ("init_score", init_score)):
+        if arr is not None:
+            ds.set_field(name, arr)
+            ods.set_field(name, arr)
+    return ds, ods
+
+
+def _train_both(ds, ods, params, iters):
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model
+    from oracle import oracle as O
+    b = capi.Booster(ds, params)
+    ob = O.OracleBooster(ods, params)
+    for it in range(iters):
+        f1 = b.update_one_iter()
+        f2 = ob.update()
+        assert f1 == f2, "is_finished differs at iteration %d" % it
+        if f1:
+            break
+    return b, ob, parse_model(b.save_model_to_string()), parse_model(ob.model_string())
+
+
+def _feature_matrix(rng, n):
+    """Columns that exercise the bin finder: gaussian, many zeros, few distinct values, negatives only,
+    constant (trivial), heavy ties, NaNs, tiny magnitudes, integers."""
+    cols = [
+        rng.standard_normal(n),
+        rng.standard_normal(n) * (rng.random(n) < 0.2),
+        rng.integers(0, 5, n).astype(np.float64),
+        -np.abs(rng.standard_normal(n)) - 0.5,
+        np.full(n, 3.25),
+        np.round(rng.standard_normal(n), 1),
+        np.where(rng.random(n) < 0.1, np.nan, rng.standard_normal(n)),
+        rng.standard_normal(n) * 1e-30,
+        rng.integers(-50, 50, n).astype(np.float64),
+        rng.exponential(2.0, n),
+        np.where(rng.random(n) < 0.85, 0.0, rng.random(n)),
+        np.where(rng.random(n) < 0.5, np.nan, rng.integers(0, 3, n).astype(np.float64)),
+    ]
+    return np.stack(cols, axis=1)
+
+
+@pytest.mark.parametrize("n,max_bin", [(3000, 255), (50000, 255), (20000, 63), (250000, 255)])
+def test_bins_bit_exact(built, n, max_bin):
+    from mmlspark_b200 import capi
+    from oracle import oracle as O
+    rng = np.random.default_rng(n + max_bin)
+    X = _feature_matrix(rng, n)
+    params = DS_PARAMS.replace("max_bin=255", "max_bin=%d" % max_bin)
+    ds = capi.Dataset.from_mat(X, params)
+    ods = O.OracleDataset(X, params)
+    for f in range(X.shape[1]):
+        assert ds.feature_info(f) == ods.feature_info(f), "feature %d meta differs" % f
+        ub, oub = ds.upper_bounds(f), ods.upper_bounds(f)
+        assert ub.tobytes() == oub.tobytes(), "feature %d bin upper bounds differ (bitwise)" % f   # NaN-safe bitwise compare
+    assert np.array_equal(ds.get_bins(), ods.bins())
+    # float32 column-major input goes through the same kernel
+    ds32 = capi.Dataset.from_mat(X.astype(np.float32), params, row_major=False)
+    ods32 = O.OracleDataset(X.astype(np.float32).astype(np.float64), params)
+    assert np.array_equal(ds32.get_bins(), ods32.bins())
+    for d in (ds, ds32):
+        d.free()
+
+
+def test_reference_dataset_uses_train_bins(built):
+    from mmlspark_b200 import capi
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    X = _feature_matrix(rng, 20000)
+    Xv = _feature_matrix(rng, 5000)
+    ds = capi.Dataset.from_mat(X, DS_PARAMS)
+    dv = capi.Dataset.from_mat(Xv, DS_PARAMS, reference=ds)
+    ods = O.OracleDataset(X, DS_PARAMS)
+    # bin the validation rows with the training mappers on the host
+    want = np.zeros(Xv.shape, dtype=np.uint8)
+    for f in range(X.shape[1]):
+        info = ods.feature_info(f)
+        if info["is_trivial"]:
+            continue
+        ub = ods.upper_bounds(f)
+        nb = info["num_bin"] - (1 if info["missing_type"] == 2 else 0)
+        v = Xv[:, f].copy()
+        nan = np.isnan(v)
+        v[nan] = 0.0
+        b = np.searchsorted(ub[:nb - 1], v, side="left")
+        if info["missing_type"] == 2:
+            b[nan] = info["num_bin"] - 1
+        want[:, f] = b
+    assert np.array_equal(dv.get_bins(), want)
+
+
+@pytest.mark.parametrize("n,F", [(1000, 7), (40000, 70), (300000, 33)])
+def test_histogram_kernel_vs_oracle(built, n, F):
+    """K4 (fixed-point shared-memory atomics) against the fp64 oracle histogram: root pass and gathered leaves."""
+    from mmlspark_b200 import capi
+    from oracle import oracle as O
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, F))
+    X[:, 1] = np.where(rng.random(n) < 0.3, np.nan, X[:, 1])
+    ds = capi.Dataset.from_mat(X, DS_PARAMS)
+    bins = ds.get_bins()
+    g = (rng.standard_normal(n) * np.exp(rng.standard_normal(n) * 3)).astype(np.float32)   # wide dynamic range
+    h = rng.random(n).astype(np.float32)
+    for idx in (None, np.sort(rng.choice(n, n // 3, replace=False)).astype(np.int32), np.arange(0, min(n, 37), dtype=np.int32), np.zeros(0, dtype=np.int32)):
+        got = ds.histogram(g, h, idx)
+        want = O.histogram(bins, g, h, idx)
+        cnt = n if idx is None else len(idx)
+        # fixed point: every element is rounded to 2^-35 of the maximum magnitude => |err| <= cnt * 2^-36 * max
+        tol_g = max(cnt, 1) * 2.0 ** -35 * float(np.abs(g).max())
+        tol_h = max(cnt, 1) * 2.0 ** -35 * float(np.abs(h).max())
+        assert np.abs(got[:, :, 0] - want[:, :, 0]).max() <= tol_g
+        assert np.abs(got[:, :, 1] - want[:, :, 1]).max() <= tol_h
+        np.testing.assert_allclose(got.sum(axis=1), want.sum(axis=1), rtol=1e-9, atol=tol_g)
+    ds.free()
+
+
+def test_regression_tree_sequence_identical(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(1)
+    n, F = 60000, 50
+    X = rng.standard_normal((n, F))
+    y = (2 * X[:, 0] + np.sin(3 * X[:, 1]) + X[:, 2] * X[:, 3] + 0.3 * rng.standard_normal(n)).astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params("regression", "alpha=0.9 tweedie_variance_power=1.5").replace("is_unbalance=false", "")
+    b, ob, m, om = _train_both(ds, ods, params, 30)
+    compare_models(m, om)
+    assert len(m["trees"]) == 30
+    np.testing.assert_allclose(b.get_scores(), ob.scores(), rtol=1e-7, atol=1e-7)
+
+
+def test_binary_config1_100_iters(built):
+    """BASELINE config 1: LightGBMClassifier binary, synthetic 50k x 28 dense, 100 iterations."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(42)
+    n, F = 50000, 28
+    X = rng.standard_normal((n, F))
+    w = np.random.default_rng(7).standard_normal(F)
+    y = (X @ w + 0.5 * rng.standard_normal(n) > 0).astype(np.float32)
+    ds, ods = _make(X, y)
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("binary", "is_unbalance=false"), 100)
+    compare_models(m, om)
+    assert len(m["trees"]) == 100
+    p = b.predict_for_mat(X[:2000], predict_type=1)[:, 0]
+    np.testing.assert_allclose(p, ob.predict_raw(X[:2000])[:, 0], rtol=1e-6, atol=1e-6)
+
+
+def test_binary_weighted_unbalanced_regularised(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(3)
+    n, F = 30000, 20
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] + X[:, 1] ** 2 + rng.standard_normal(n) > 1.5).astype(np.float32)
+    wt = rng.random(n).astype(np.float32) + 0.5
+    ds, ods = _make(X, y, weight=wt)
+    params = _classifier_params("binary", "is_unbalance=true", leaves=15).replace("lambda_l1=0.0", "lambda_l1=0.5").replace(
+        "lambda_l2=0.0", "lambda_l2=2.0").replace("min_gain_to_split=0.0", "min_gain_to_split=0.1").replace("max_delta_step=0.0", "max_delta_step=0.7")
+    b, ob, m, om = _train_both(ds, ods, params, 25)
+    compare_models(m, om)
+
+
+def test_missing_values_two_way_scan(built):
+    """NaN features exercise the left-to-right + right-to-left scan and default_left."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(9)
+    n, F = 40000, 12
+    X = rng.standard_normal((n, F))
+    for f in (0, 3, 5):
+        X[rng.random(n) < 0.25, f] = np.nan
+    X[:, 7] = np.where(rng.random(n) < 0.6, 0.0, X[:, 7])          # most_freq_bin == default bin (offset path)
+    y = (np.where(np.isnan(X[:, 0]), 1.5, X[:, 0]) + np.nan_to_num(X[:, 3]) * 0.5 + X[:, 7] + 0.2 * rng.standard_normal(n)).astype(np.float32)
+    ds, ods = _make(X, y)
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("regression", ""), 20)
+    compare_models(m, om)
+    dts = np.concatenate([t["decision_type"] for t in m["trees"] if t["num_leaves"] > 1])
+    assert (dts >= 8).any(), "expected at least one split on a NaN-missing feature"
+
+
+def test_max_depth_and_small_leaves(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(11)
+    n, F = 5000, 10
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] > 0).astype(np.float32) + 0.1 * rng.standard_normal(n).astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params("regression", "", leaves=63).replace("max_depth=-1", "max_depth=4").replace("min_data_in_leaf=20", "min_data_in_leaf=200")
+    b, ob, m, om = _train_both(ds, ods, params, 15)
+    compare_models(m, om)
+
+
+def test_multiclass_softmax(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(21)
+    n, F, K = 30000, 16, 4
+    X = rng.standard_normal((n, F))
+    W = rng.standard_normal((F, K))
+    y = np.argmax(X @ W + rng.standard_normal((n, K)), axis=1).astype(np.float32)
+    ds, ods = _make(X, y)
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("multiclass", "num_class=%d" % K, leaves=15), 10)
+    compare_models(m, om)
+    assert len(m["trees"]) == 10 * K
+    prob = b.predict_for_mat(X[:100])
+    np.testing.assert_allclose(prob.sum(axis=1), 1.0, atol=1e-9)          # VerifyLightGBMClassifier.scala:91-99
+
+
+def test_lambdarank(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(31)
+    sizes = rng.integers(5, 40, 600).astype(np.int32)
+    n, F = int(sizes.sum()), 12
+    X = rng.standard_normal((n, F))
+    rel = np.clip(np.round(X[:, 0] + 0.5 * X[:, 1] + rng.standard_normal(n) * 0.5 + 1.5), 0, 4).astype(np.float32)
+    ds, ods = _make(X, rel, group=sizes)
+    params = _classifier_params("lambdarank", "max_position=20 eval_at=1,2,3,4,5", leaves=15).replace("boost_from_average=true", "")
+    b, ob, m, om = _train_both(ds, ods, params, 10)
+    # per-document lambdas are fp32 sums whose order differs on the GPU => gains/values to 1e-4, structure identical
+    compare_models(m, om, value_tol=1e-4, gain_tol=1e-4)
+
+
+def test_custom_objective_and_init_score(built):
+    """LGBM_BoosterUpdateOneIterCustom (fobj path, LightGBMBooster.scala:368-388) equals the built-in L2 objective
+    when fed the same gradients; init_score shifts the starting point."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    rng = np.random.default_rng(41)
+    n, F = 20000, 8
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] - X[:, 1] + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    init = np.full(n, 0.25)
+    ds, ods = _make(X, y, init_score=init)
+    params = _classifier_params("regression", "")
+    b1, ob, m1, om = _train_both(ds, ods, params, 5)
+    compare_models(m1, om)
+    b2 = capi.Booster(ds, params)
+    for _ in range(5):
+        s = b2.get_scores()
+        b2.update_one_iter_custom((s - y).astype(np.float32), np.ones(n, dtype=np.float32))
+    compare_models(parse_model(b2.save_model_to_string()), m1)
+
+
+def test_finishes_when_no_split_possible(built):
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((30, 3))
+    y = rng.standard_normal(30).astype(np.float32)
+    ds, ods = _make(X, y)
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("regression", ""), 3)
+    assert len(m["trees"]) == len(om["trees"]) == 1 and m["trees"][0]["num_leaves"] == 1
+    np.testing.assert_allclose(m["trees"][0]["leaf_value"], om["trees"][0]["leaf_value"], rtol=1e-12)
+
+
+def test_determinism_run_to_run(built):
+    """Integer (fixed-point) accumulation makes the engine bit-reproducible despite atomics."""
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(77)
+    n, F = 100000, 40
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] * X[:, 1] + rng.standard_normal(n)).astype(np.float32)
+    ds, _ = _make(X, y)
+    strs = []
+    for _ in range(2):
+        b = capi.Booster(ds, _classifier_params("regression", ""))
+        for _ in range(5):
+            b.update_one_iter()
+        strs.append(b.save_model_to_string())
+        b.free()
+    assert strs[0] == strs[1]
