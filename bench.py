@@ -182,11 +182,15 @@ def main():
         print(json.dumps(line))
         return
 
-    from mmlspark_b200 import capi
-    capi.load()
     dist = None
     if world > 1:
+        # torch first: its bundled libnccl.so.2 (2.28) must be the one the process binds; the engine's NCCL calls
+        # (CommInitRank / AllReduce / AllGather) then resolve to the same library
+        import torch  # noqa: F401
         import torch.distributed as dist_mod
+    from mmlspark_b200 import capi
+    capi.load()
+    if world > 1:
         dist = dist_mod
         dist.init_process_group("gloo")          # host-side barrier / max-reduce only; training traffic is NCCL inside the library
     capi.set_device(local_rank)

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <chrono>
 #include <functional>
+#include <mutex>
+#include <omp.h>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -24,7 +26,29 @@ static thread_local int t_device = -1;
 static thread_local Network t_net;
 Network& Net() { return t_net; }
 
+// Host-side OpenMP loops (bin finding on the sample, batch predict) must respect the container's CPU
+// quota: the GPU box shows 128 logical CPUs behind a 16-core cgroup quota and oversubscribed OpenMP
+// teams there are ~100x slower.
+static void CapHostThreadsOnce() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int n = omp_get_max_threads();
+    FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+      char q[64] = {0};
+      long long period = 0;
+      if (std::fscanf(f, "%63s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0) {
+        long long quota = std::atoll(q);
+        n = static_cast<int>(std::max<long long>(1, std::min<long long>(n, quota / period)));
+      }
+      std::fclose(f);
+    }
+    omp_set_num_threads(n);
+  });
+}
+
 static int DeviceCountOrDie() {
+  CapHostThreadsOnce();
   int cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
   if (e != cudaSuccess || cnt <= 0)
@@ -293,9 +317,8 @@ void Dataset::UploadMeta() {
 
 template <typename T>
 static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long long ld, const Dataset& d, long long row_offset, cudaStream_t s) {
-  static bool attr_set[2] = {false, false};
-  const int which = sizeof(T) == 4 ? 0 : 1;
-  if (!attr_set[which]) { B200_CUDA(cudaFuncSetAttribute(k_bin_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); attr_set[which] = true; }
+  // function attributes are per device/context: set on every call (rank-threads drive different GPUs)
+  B200_CUDA(cudaFuncSetAttribute(k_bin_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   dim3 grid(static_cast<unsigned>(std::min<long long>((nrow + 7) / 8, 148 * 8)), d.num_tiles);
   if (grid.x == 0) grid.x = 1;
   k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.nf, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);

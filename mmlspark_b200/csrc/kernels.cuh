@@ -92,11 +92,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, long long ld, const FeatMeta* __restrict__ meta,
            const double* __restrict__ ub, int nf, uint8_t* __restrict__ bins, long long rows_stride, long long row_offset) {
-  extern __shared__ double s_ub[];   // [32][256]
+  extern __shared__ double s_ub[];   // [256 bins][32 lanes]: lane l always hits bank pair 2l -> no conflicts beyond the 64-bit 2-phase
   const int tile = blockIdx.y;
   for (int e = threadIdx.x; e < 32 * 256; e += blockDim.x) {
     int f = tile * 32 + (e >> 8);
-    s_ub[e] = f < nf ? ub[static_cast<size_t>(f) * 256 + (e & 255)] : 0.0;
+    s_ub[(e & 255) * 32 + (e >> 8)] = f < nf ? ub[static_cast<size_t>(f) * 256 + (e & 255)] : 0.0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +104,7 @@ k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, lon
   FeatMeta m;
   m.num_bin = 1; m.missing_type = 0; m.real_index = 0;
   if (u < nf) m = meta[u];
-  const double* myub = s_ub + lane * 256;
+  const double* myub = s_ub + lane;
   for (long long r = blockIdx.x * 8LL + warp; r < nrow; r += gridDim.x * 8LL) {
     unsigned bin = 0;
     if (u < nf) {
@@ -116,7 +116,7 @@ k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, lon
         int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
         while (lo < hi) {
           int mid = (hi + lo - 1) / 2;
-          if (v <= myub[mid]) hi = mid; else lo = mid + 1;
+          if (v <= myub[mid * 32]) hi = mid; else lo = mid + 1;
         }
         bin = lo;
       }

@@ -1375,6 +1375,13 @@ void orc_booster_hist_stats(void* h, double* seconds, long long* cells) {
   Booster* b = static_cast<Booster*>(h);
   *seconds = b->learner.hist_seconds; *cells = b->learner.hist_cells;
 }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -22,6 +22,23 @@ def build(force=False):
     return so
 
 
+def effective_cpus():
+    """Host threads this process may really use: min(affinity mask, cgroup CPU quota).  The GPU box reports
+    128 logical CPUs but its container quota is 16 cores — 128 OpenMP threads there run ~100x slower."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            if q != "max":
+                n = max(1, min(n, int(int(q) / int(p))))
+    except Exception:
+        pass
+    env = os.environ.get("OMP_NUM_THREADS")
+    if env:
+        n = max(1, min(n, int(env)))
+    return n
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -55,6 +72,7 @@ def lib():
         L.orc_best_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.orc_random_sample.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_count_cardinality.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_set_num_threads(C.c_int(effective_cpus()))
         _LIB = L
     return _LIB
 
