@@ -1,0 +1,225 @@
+"""Behavioural tests of the estimator layer on the GPU, ported from the reference's suites
+(lightgbm/src/test/scala/.../split1/VerifyLightGBMClassifier.scala, split2/VerifyLightGBMRegressor.scala,
+split2/VerifyLightGBMRanker.scala): each parameter moves the metric the right way, model strings carry the
+parameter block the reference greps, save/load round-trips, edge cases don't hang."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU ")
+    except Exception:
+        return 0
+
+
+def _auc(y, s):
+    from sklearn.metrics import roc_auc_score
+    return roc_auc_score(y, s)
+
+
+def _binary_frame(seed=0, n=20000, F=12, imbalance=None):
+    from mmlspark_b200.lightgbm import Frame
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, F))
+    s = X[:, 0] + 0.8 * X[:, 1] * X[:, 2] + 0.5 * np.sin(3 * X[:, 3]) + 0.7 * rng.standard_normal(n)
+    y = (s > (np.quantile(s, imbalance) if imbalance else 0)).astype(np.float64)
+    return Frame({"features": X, "label": y})
+
+
+def test_classifier_fit_transform_outputs(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame()
+    model = LightGBMClassifier(numIterations=30, numLeaves=15, numTasks=1).fit(df)
+    out = model.transform(df)
+    raw, prob, pred = out["rawPrediction"], out["probability"], out["prediction"]
+    assert raw.shape == prob.shape == (20000, 2)
+    np.testing.assert_allclose(raw[:, 0], -raw[:, 1])                       # [-s, s]
+    np.testing.assert_allclose(prob.sum(axis=1), 1.0, atol=1e-12)           # [1-p, p]
+    np.testing.assert_array_equal(pred, (prob[:, 1] > 0.5).astype(np.float64))
+    assert _auc(df["label"], prob[:, 1]) > 0.85
+    assert model.getBoosterNumTotalIterations() == 30 and model.getBoosterNumFeatures() == 12 and model.getBoosterNumClasses() == 1
+    imp = model.getFeatureImportances("split")
+    assert len(imp) == 12 and np.argmax(imp) in (0, 1, 2, 3)
+    # more iterations -> better training AUC (VerifyLightGBMClassifier.scala:385-397 uses numIterations at predict time)
+    few = model.setNumIterations(3).transform(df)["probability"][:, 1]
+    assert _auc(df["label"], few) < _auc(df["label"], prob[:, 1])
+
+
+def test_native_model_save_load_roundtrip(built, tmp_path):
+    from mmlspark_b200.lightgbm import LightGBMClassificationModel, LightGBMClassifier
+    df = _binary_frame(1)
+    model = LightGBMClassifier(numIterations=10, numTasks=1).fit(df)
+    path = str(tmp_path / "model.txt")
+    model.saveNativeModel(path)
+    m2 = LightGBMClassificationModel.loadNativeModelFromFile(path)
+    m3 = LightGBMClassificationModel.loadNativeModelFromString(model.getNativeModel())
+    a, b, c = model.transform(df)["probability"], m2.transform(df)["probability"], m3.transform(df)["probability"]
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, c)
+    # continue training from the saved model (modelString), like verifySaveBooster (:712-755)
+    cont = LightGBMClassifier(numIterations=5, numTasks=1, modelString=model.getNativeModel()).fit(df)
+    assert cont.getBoosterNumTotalIterations() == 15
+
+
+def test_model_string_parameter_block_and_delegate_lr(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier, LightGBMDelegate
+    df = _binary_frame(2, n=5000)
+    m = LightGBMClassifier(numIterations=3, numTasks=1, lambdaL1=0.1, lambdaL2=0.5).fit(df)
+    s = m.getNativeModel()
+    assert "[lambda_l1: 0.1]" in s and "[lambda_l2: 0.5]" in s                # :273-275
+
+    class D(LightGBMDelegate):
+        def getLearningRate(self, batchIndex, partitionId, curIters, trainParams, previousLearningRate):
+            return 0.005 if curIters >= 1 else previousLearningRate
+    m = LightGBMClassifier(numIterations=3, numTasks=1, delegate=D()).fit(df)
+    assert "learning_rate: 0.005" in m.getNativeModel()                        # :509
+    from mmlspark_b200.modeltext import parse_model
+    assert [t["shrinkage"] for t in parse_model(m.getNativeModel())["trees"]] == ["1", "0.005", "0.005"]
+    named = LightGBMClassifier(numIterations=2, numTasks=1, slotNames=["f%d" % i for i in range(12)]).fit(df)
+    assert "feature_names=f0 f1 f2" in named.getNativeModel()                  # :569-592
+
+
+def test_params_move_the_metric_the_right_way(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(3)
+    base = LightGBMClassifier(numIterations=20, numTasks=1).fit(df)
+    trees = lambda m: sum(1 for l in m.getNativeModel().split("\n") if l.startswith("num_leaves=") and l != "num_leaves=1")   # noqa: E731
+    leaves = lambda m: sum(int(l.split("=")[1]) for l in m.getNativeModel().split("\n") if l.startswith("num_leaves="))      # noqa: E731
+    strict = LightGBMClassifier(numIterations=20, numTasks=1, minGainToSplit=50.0).fit(df)                                   # :345-350
+    assert leaves(strict) < leaves(base)
+    shallow = LightGBMClassifier(numIterations=20, numTasks=1, maxDepth=2).fit(df)
+    assert leaves(shallow) <= 20 * 4 and trees(shallow) == 20
+    big_leaf = LightGBMClassifier(numIterations=20, numTasks=1, minDataInLeaf=2000).fit(df)
+    assert leaves(big_leaf) < leaves(base)
+    # maxDeltaStep clips leaf outputs (:375-383)
+    clipped = LightGBMClassifier(numIterations=5, numTasks=1, maxDeltaStep=0.1, learningRate=1.0).fit(df)
+    from mmlspark_b200.modeltext import parse_model
+    t1 = parse_model(clipped.getNativeModel())["trees"][1]
+    assert np.abs(t1["leaf_value"]).max() <= 0.1 + 1e-12
+
+
+def test_is_unbalance_and_weight_column(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(4, imbalance=0.95)
+    y = df["label"]
+    plain = LightGBMClassifier(numIterations=20, numTasks=1).fit(df).transform(df)["probability"][:, 1]
+    unb = LightGBMClassifier(numIterations=20, numTasks=1, isUnbalance=True).fit(df).transform(df)["probability"][:, 1]
+    assert unb[y == 1].mean() > plain[y == 1].mean() + 0.1                     # rare class gets more mass (:421-427)
+    w = np.where(y == 1, 20.0, 1.0)
+    wdf = df.with_column("w", w)
+    wt = LightGBMClassifier(numIterations=20, numTasks=1, weightCol="w").fit(wdf).transform(df)["probability"][:, 1]
+    assert wt[y == 1].mean() > plain[y == 1].mean() + 0.1                      # :399-419
+
+
+def test_validation_early_stopping(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(5, n=12000)
+    rng = np.random.default_rng(0)
+    vdf = df.with_column("valid", rng.random(12000) < 0.3)
+    for metric in ("auc", "binary_logloss", "binary_error"):                    # :429-461
+        m = LightGBMClassifier(numIterations=300, numTasks=1, learningRate=0.3, numLeaves=63, validationIndicatorCol="valid",
+                               earlyStoppingRound=5, metric=metric).fit(vdf)
+        assert 0 < m.getBoosterNumTotalIterations() < 300, metric
+        assert m.getBoosterBestIteration() >= 0 and m.getBoosterBestIteration() <= m.getBoosterNumTotalIterations()
+        out = m.transform(df)                                                   # predicts with numIterations = best iteration (Appendix D)
+        assert out["probability"].shape == (12000, 2)
+
+
+def test_leaf_and_shap_columns(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(6, n=3000)
+    m = LightGBMClassifier(numIterations=7, numLeaves=9, numTasks=1, leafPredictionCol="leaves", featuresShapCol="shap").fit(df)
+    out = m.transform(df)
+    assert out["leaves"].shape == (3000, 7) and (out["leaves"] == np.round(out["leaves"])).all() and out["leaves"].max() < 9
+    assert out["shap"].shape == (3000, 13)
+    np.testing.assert_allclose(out["shap"].sum(axis=1), out["rawPrediction"][:, 1], rtol=1e-8, atol=1e-8)
+    assert len(m.getFeatureShaps(df["features"][0])) == 13
+
+
+def test_multiclass_classifier(built):
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier
+    rng = np.random.default_rng(7)
+    n, F, K = 15000, 10, 4
+    X = rng.standard_normal((n, F))
+    y = np.argmax(X[:, :K] + 0.5 * rng.standard_normal((n, K)), axis=1).astype(np.float64)
+    df = Frame({"features": X, "label": y})
+    m = LightGBMClassifier(objective="multiclass", numIterations=20, numTasks=1).fit(df)
+    out = m.transform(df)
+    assert out["probability"].shape == (n, K)
+    np.testing.assert_allclose(out["probability"].sum(axis=1), 1.0, atol=1e-9)
+    assert (out["prediction"] == y).mean() > 0.7
+    assert m.getBoosterNumClasses() == K and m.getBoosterNumTotalModel() == 20 * K
+
+
+def test_regressor_and_custom_objective(built):
+    from mmlspark_b200.lightgbm import Frame, LightGBMRegressor
+    rng = np.random.default_rng(8)
+    n, F = 20000, 10
+    X = rng.standard_normal((n, F))
+    y = 3 * X[:, 0] + np.sin(2 * X[:, 1]) * 2 + X[:, 2] * X[:, 3] + 0.3 * rng.standard_normal(n)
+    df = Frame({"features": X, "label": y})
+    rmse = lambda m: float(np.sqrt(np.mean((m.transform(df)["prediction"] - y) ** 2)))   # noqa: E731
+    m10 = LightGBMRegressor(numIterations=10, numTasks=1).fit(df)
+    m50 = LightGBMRegressor(numIterations=50, numTasks=1).fit(df)
+    assert rmse(m50) < rmse(m10) < float(np.std(y))
+    assert abs(m50.predict(X[0]) - m50.transform(df)["prediction"][0]) < 1e-12
+
+    class L2(object):                                                          # FObjTrait.getGradient (params/FObjTrait.scala:16)
+        def getGradient(self, preds, labels):
+            return preds - labels, np.ones_like(preds)
+    mc = LightGBMRegressor(numIterations=10, numTasks=1, fobj=L2(), boostFromAverage=False).fit(df)
+    mb = LightGBMRegressor(numIterations=10, numTasks=1, boostFromAverage=False).fit(df)
+    np.testing.assert_allclose(mc.transform(df)["prediction"], mb.transform(df)["prediction"], rtol=1e-6, atol=1e-6)
+    bad = LightGBMRegressor(numIterations=2, numTasks=1, slotNames=["a"] * 3)   # wrong number of slot names fails early (VerifyLightGBMRegressor.scala:142-146)
+    with pytest.raises(Exception):
+        bad.fit(df)
+
+
+def test_ranker(built):
+    from mmlspark_b200.lightgbm import Frame, LightGBMRanker
+    rng = np.random.default_rng(9)
+    sizes = rng.integers(5, 30, 500)
+    q = np.repeat(np.arange(500), sizes)
+    n = len(q)
+    X = rng.standard_normal((n, 8))
+    rel = np.clip(np.round(X[:, 0] + 0.5 * X[:, 1] + 0.5 * rng.standard_normal(n) + 1.5), 0, 4)
+    perm = rng.permutation(n)
+    df = Frame({"features": X[perm], "label": rel[perm], "query": q[perm]})
+    m = LightGBMRanker(groupCol="query", numIterations=20, numTasks=1, minDataInLeaf=5).fit(df)
+    pred = m.transform(df)["prediction"]
+    assert np.corrcoef(pred, df["label"])[0, 1] > 0.6
+    assert "objective=lambdarank" in m.getNativeModel()
+    shap = m.getFeatureShaps(df["features"][0])
+    assert abs(sum(shap) - m.predict(df["features"][0])) < 1e-9               # VerifyLightGBMRanker.scala:124
+
+
+def test_batches_and_empty_partition_do_not_hang(built):
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(10, n=9000)
+    m = LightGBMClassifier(numIterations=5, numTasks=1, numBatches=3).fit(df)   # :278-281
+    assert m.getBoosterNumTotalIterations() == 15
+
+    class OneEmpty(LightGBMClassifier):                                         # empty partition -> "ignore" status (:594-606)
+        def _partitions(self, df, num_tasks):
+            n = df.num_rows()
+            return [slice(0, n), slice(n, n)]
+    m = OneEmpty(numIterations=4, numTasks=2).fit(df)
+    assert m.getBoosterNumTotalIterations() == 4
+
+
+def test_two_tasks_two_gpus(built):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(11)
+    m2 = LightGBMClassifier(numIterations=20, numTasks=2, defaultListenPort=24400).fit(df)     # numPartitions = 2 (:126)
+    m1 = LightGBMClassifier(numIterations=20, numTasks=1).fit(df)
+    a2 = _auc(df["label"], m2.transform(df)["probability"][:, 1])
+    a1 = _auc(df["label"], m1.transform(df)["probability"][:, 1])
+    assert abs(a1 - a2) < 0.01 and a2 > 0.85
