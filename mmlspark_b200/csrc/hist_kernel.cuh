@@ -24,9 +24,10 @@
 // RED.ADD.64.  Integer sums are exact and order-independent, so the result is bit-reproducible
 // run to run and across ranks (the NCCL reduction is an int64 sum).
 //
-// Bank mapping: a warp owns one row at a time, lane l owns feature l of the tile and the
-// sub-histogram planes are laid out [bin][lane], so lane l only ever touches bank l: every
-// ATOMS instruction is conflict-free by construction regardless of the bin distribution.
+// Bank mapping: the sub-histogram planes are laid out [bin][feature-of-tile], so feature f lives in
+// bank f.  A warp step covers 4 rows x 32 features; in each of its 4 sub-steps the 32 lanes handle 32
+// DIFFERENT features (a rotation by the lane's row selector), so every ATOMS instruction is
+// conflict-free by construction regardless of the bin distribution (ncu: 1.0 wavefront per ATOMS).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -37,9 +38,19 @@ constexpr int kTileFeat = 32;                      // features per tile == lanes
 constexpr int kBins = 256;                         // uint8 bin ids
 constexpr int kLoBits = 18;                        // low fixed-point field
 constexpr int kFlushRows = 1 << (32 - kLoBits);    // rows a sub-histogram may absorb (16384)
-constexpr int kStageRows = 256;                    // rows per staged sub-chunk
-constexpr int kStages = 3;                         // cp.async ring depth
-constexpr int kHistThreads = 512;
+#ifndef B200GBM_STAGE_ROWS
+#define B200GBM_STAGE_ROWS 512
+#endif
+#ifndef B200GBM_STAGES
+#define B200GBM_STAGES 3
+#endif
+#ifndef B200GBM_HIST_THREADS
+#define B200GBM_HIST_THREADS 512
+#endif
+constexpr int kStageRows = B200GBM_STAGE_ROWS;     // rows per staged sub-chunk
+constexpr int kStages = B200GBM_STAGES;            // cp.async ring depth
+constexpr int kHistThreads = B200GBM_HIST_THREADS;
+constexpr int kStageSlots = (kStageRows * 2 + kHistThreads - 1) / kHistThreads;   // half-rows a thread stages per stage
 constexpr int kHistWarps = kHistThreads / 32;
 constexpr int kPlaneWords = kBins * kTileFeat;     // 8192 words per plane
 constexpr int kHistSmemBytes =
@@ -103,14 +114,18 @@ k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tile
     const int nst = (nrows + kStageRows - 1) / kStageRows;
     const uint8_t* tbins = bins + static_cast<size_t>(tile) * rows_stride * 32;
 
-    // thread t stages half a row of bins (16 B); threads < 256 also stage one qgh word
-    const int srow = tid >> 1, shalf = tid & 1;
-    auto row_of = [&](int st) -> int {
-      int p = row0 + st * kStageRows + srow;
+    // a "slot" = half a row of bins (16 B); the thread that stages half 0 also stages the row's qgh word
+    auto row_of = [&](int st, int slot) -> int {
+      int hrow = slot * kHistThreads + tid;
+      if (hrow >= kStageRows * 2) return -1;
+      int p = row0 + st * kStageRows + (hrow >> 1);
       if (p >= row0 + nrows) return -1;
       return w.use_idx ? idx[w.begin + p] : (w.begin + p);
     };
-    auto issue = [&](int st, int r) {
+    auto issue = [&](int st, int slot, int r) {
+      int hrow = slot * kHistThreads + tid;
+      if (hrow >= kStageRows * 2) return;
+      int srow = hrow >> 1, shalf = hrow & 1;
       int buf = st % kStages;
       bool ok = r >= 0;
       size_t rr = ok ? static_cast<size_t>(r) : 0;
@@ -119,13 +134,18 @@ k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tile
       if (shalf == 0) cp_async16(stage_q + buf * kStageRows + srow, qgh + rr, ok);
     };
 
-    int rnext = row_of(0);
+    int rnext[kStageSlots];
+#pragma unroll
+    for (int sl = 0; sl < kStageSlots; ++sl) rnext[sl] = row_of(0, sl);
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
       if (s < nst) {
-        int r = rnext;
-        rnext = (s + 1 < nst) ? row_of(s + 1) : -1;
-        issue(s, r);
+#pragma unroll
+        for (int sl = 0; sl < kStageSlots; ++sl) {
+          int r = rnext[sl];
+          rnext[sl] = (s + 1 < nst) ? row_of(s + 1, sl) : -1;
+          issue(s, sl, r);
+        }
       }
       cp_async_commit();
     }
@@ -134,28 +154,38 @@ k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tile
       __syncthreads();
       int sn = s + kStages - 1;
       if (sn < nst) {
-        int r = rnext;
-        rnext = (sn + 1 < nst) ? row_of(sn + 1) : -1;
-        issue(sn, r);
+#pragma unroll
+        for (int sl = 0; sl < kStageSlots; ++sl) {
+          int r = rnext[sl];
+          rnext[sl] = (sn + 1 < nst) ? row_of(sn + 1, sl) : -1;
+          issue(sn, sl, r);
+        }
       }
       cp_async_commit();
 
       const int buf = s % kStages;
-      const unsigned char* sb = stage_bins + buf * kStageRows * 32;
+      const unsigned* sw = reinterpret_cast<const unsigned*>(stage_bins + buf * kStageRows * 32);   // 8 words per row
       const int4* sq = stage_q + buf * kStageRows;
-#pragma unroll 4
-      for (int k = 0; k < kStageRows / kHistWarps; ++k) {
-        int r = warp + k * kHistWarps;
-        unsigned b = sb[r * 32 + lane];
-        int4 q = sq[r];
-        unsigned a = b * 32u + lane;
-        atomicAdd(&plane[a], static_cast<unsigned>(q.x));
-        atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
-        if (NATOM == 4) {
+      // One warp step = 4 rows x 32 features.  Lane = (rsel = lane>>3, word = lane&7) reads the 4 bins of features
+      // 4*word..4*word+3 of row r0+rsel with ONE LDS.32 (the warp reads 128 contiguous bytes) and that row's 4
+      // fixed-point words with one LDS.128.  In sub-step k it handles feature 4*word + ((k+rsel)&3): for fixed k the map
+      // (rsel, word) -> feature is a bijection onto 0..31, and plane[.][bin*32+feature] puts feature f in bank f, so all
+      // 32 lanes hit distinct banks for ANY bin values: 16 conflict-free ATOMS per 128 cells, loads amortised 4x.
+      const int rsel = lane >> 3, wsel = lane & 7;
+#pragma unroll 2
+      for (int k4 = 0; k4 < kStageRows / (4 * kHistWarps); ++k4) {
+        const int r = (warp + k4 * kHistWarps) * 4 + rsel;
+        const unsigned word = sw[r * 8 + wsel];
+        const int4 q = sq[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int kk = (k + rsel) & 3;
+          const unsigned b = (word >> (8 * kk)) & 0xFFu;
+          const unsigned a = b * 32u + static_cast<unsigned>(wsel * 4 + kk);
+          atomicAdd(&plane[a], static_cast<unsigned>(q.x));
+          atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
           atomicAdd(&plane[2 * kPlaneWords + a], static_cast<unsigned>(q.z));
-          atomicAdd(&plane[3 * kPlaneWords + a], static_cast<unsigned>(q.w));
-        } else {
-          atomicAdd(&plane[2 * kPlaneWords + a], static_cast<unsigned>(q.z));
+          if (NATOM == 4) atomicAdd(&plane[3 * kPlaneWords + a], static_cast<unsigned>(q.w));
         }
       }
     }

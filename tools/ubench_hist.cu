@@ -33,6 +33,28 @@ ubench(int iters, unsigned long long* cyc_out, unsigned* sink) {
   for (int e = tid; e < 256; e += blockDim.x) sq[e] = make_int4(e - 100, e * 7 + 1, 3, e + 5);
   __syncthreads();
   long long t0 = clock64();
+  if (MODE == 9 || MODE == 10) {   // 4 rows x 32 features per warp step (the production mapping); 10 = 3 planes
+    const unsigned* sw = reinterpret_cast<const unsigned*>(sb);
+    const int rsel = lane >> 3, wsel = lane & 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+      for (int g4 = warp; g4 < 64; g4 += nwarp) {
+        const int r = g4 * 4 + rsel;
+        const unsigned word = sw[r * 8 + wsel];
+        const int4 q = sq[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int kk = (k + rsel) & 3;
+          const unsigned b = (word >> (8 * kk)) & 0xFFu;
+          const unsigned a = b * 32u + (unsigned)(wsel * 4 + kk);
+          atomicAdd(&plane[a], (unsigned)q.x); atomicAdd(&plane[kPlaneWords + a], (unsigned)q.y);
+          atomicAdd(&plane[2 * kPlaneWords + a], (unsigned)q.z);
+          if (MODE == 9) atomicAdd(&plane[3 * kPlaneWords + a], (unsigned)q.w);
+        }
+      }
+      __syncthreads();
+    }
+  } else
   for (int it = 0; it < iters; ++it) {
 #pragma unroll 4
     for (int r = warp; r < 256; r += nwarp) {
@@ -123,6 +145,8 @@ int main(int argc, char** argv) {
   const int it = 400;
   for (int threads : {512, 1024}) {
     printf("  \"t%d\": {", threads);
+    printf("\"u32x4_rows4x32_rotated\": %.3f, ", run_mode<9>(threads, it, nsm));
+    printf("\"u32x3_rows4x32_rotated\": %.3f, ", run_mode<10>(threads, it, nsm));
     printf("\"u32x4_ownerbank\": %.3f, ", run_mode<0>(threads, it, nsm));
     printf("\"u32x3_ownerbank\": %.3f, ", run_mode<6>(threads, it, nsm));
     printf("\"u32x2_ownerbank\": %.3f, ", run_mode<1>(threads, it, nsm));
