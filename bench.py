@@ -250,7 +250,7 @@ def main():
     algo_bytes = rows_rank0 * (F + 8.0) + nonroot_rows * 4.0 + launches * F * 255 * 16.0
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (tm["hist_ms"] / 1000.0) / 1e9 if tm["hist_ms"] > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k4_hist_build<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+    roofline = {"bound": "hbm", "kernel": "k4_hist_build_ws<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": peak_src, "traffic": None, "launches": launches, "avg_launch_ms": tm["hist_ms"] / max(launches, 1),
                 "cells_per_s": rows_rank0 * F / (tm["hist_ms"] / 1000.0) if tm["hist_ms"] > 0 else None,
                 "k4_share_of_step": tm["hist_ms"] / dev_ms if dev_ms > 0 else None,

@@ -422,7 +422,7 @@ void Dataset::GetBinsRowMajor(uint8_t* out) const {
 
 void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const {
   EnsureDevice();
-  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
   const int n = num_data;
   DevBuf<float> g, h; g.Alloc(n); h.Alloc(n);
   g.Upload(grad, n, stream); h.Upload(hess, n, stream);
@@ -440,8 +440,8 @@ void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx
   k_quantize<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, q.p, ctrl.p, 0);
   HistWork w{0, cnt, idx ? 1 : 0, 0};
   B200_CUDA(cudaMemcpyAsync(&ctrl.p->hist_work, &w, sizeof(w), cudaMemcpyHostToDevice, stream));
-  k4_hist_build<4><<<sms, kHistThreads, kHistSmemBytes, stream>>>(bins.p, rows_stride, num_tiles, q.p, didx.p, didx.p, &ctrl.p->hist_work,
-                                                                  reinterpret_cast<unsigned long long*>(H.p));
+  k4_hist_build_ws<4><<<sms, kWsThreads, kWsSmemBytes, stream>>>(bins.p, rows_stride, num_tiles, q.p, didx.p, didx.p, &ctrl.p->hist_work,
+                                                                 reinterpret_cast<unsigned long long*>(H.p));
   k_hist_to_double<<<sms * 4, 256, 0, stream>>>(H.p, D.p, elems, ctrl.p);
   B200_CUDA(cudaGetLastError());
   std::vector<double> hd(elems);
@@ -623,8 +623,8 @@ void Booster::InitTraining() {
   num_sms_ = prop.multiProcessorCount;
   B200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   B200_CUDA(cudaEventCreate(&ev_a_)); B200_CUDA(cudaEventCreate(&ev_b_));
-  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-  B200_CUDA(cudaFuncSetAttribute(k4_hist_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+  B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
 
   sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step;
   sp_.min_gain_to_split = cfg.min_gain_to_split; sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf;
@@ -826,11 +826,11 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     B200_CUDA(cudaMemsetAsync(H_.p, 0, slot_elems_ * sizeof(long long), s));
     if (profile_hist) { cudaEvent_t a, b; B200_CUDA(cudaEventCreate(&a)); B200_CUDA(cudaEventCreate(&b)); evs.push_back(a); evs.push_back(b); B200_CUDA(cudaEventRecord(a, s)); }
     if (const_hessian_)
-      k4_hist_build<3><<<num_sms_, kHistThreads, kHistSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
-                                                                      reinterpret_cast<unsigned long long*>(H_.p));
+      k4_hist_build_ws<3><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                     reinterpret_cast<unsigned long long*>(H_.p));
     else
-      k4_hist_build<4><<<num_sms_, kHistThreads, kHistSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
-                                                                      reinterpret_cast<unsigned long long*>(H_.p));
+      k4_hist_build_ws<4><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                     reinterpret_cast<unsigned long long*>(H_.p));
     if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
     if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
     k_scan<<<sgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);

@@ -220,4 +220,198 @@ k4_hist_build(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tile
   }
 }
 
+
+// ===================================================================================================
+// K4 v3 — warp-specialised variant: one PRODUCER warp stages rows into a ring of shared-memory stages,
+// 16 CONSUMER warps do nothing but the conflict-free scatter.  Stages are handed over with mbarriers
+// (full / empty), so there is no block-wide barrier per stage and the producer runs ahead across work
+// items (it prefetches the next item while the consumers flush the current sub-histogram).
+//   * contiguous row ranges (root pass, use_idx == 0): TMA bulk copies — one elected lane issues
+//     cp.async.bulk (UBLKCP) for the stage's bins (rows*32 B) and qgh (rows*16 B), completion is signalled
+//     by the mbarrier's transaction count;
+//   * index-list leaves: the 32 producer lanes issue 16-byte cp.async gathers (LDGSTS) and arrive on the
+//     mbarrier with cp.async.mbarrier.arrive.noinc when their copies have landed.
+constexpr int kWsConsumerWarps = 16;
+#ifndef B200GBM_WS_PRODUCERS
+#define B200GBM_WS_PRODUCERS 2
+#endif
+constexpr int kWsProducerWarps = B200GBM_WS_PRODUCERS;            // 1 lane issues the TMA bulk copies; all lanes share the gathers
+constexpr int kWsThreads = (kWsConsumerWarps + kWsProducerWarps) * 32;
+constexpr int kWsStageRows = 512;
+constexpr int kWsStages = 3;
+constexpr int kWsSmemBytes = 4 * kPlaneWords * 4 + kWsStages * (kWsStageRows * 32 + kWsStageRows * 16) + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NATOM>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tiles, const int4* __restrict__ qgh,
+                 const int* __restrict__ idx0, const int* __restrict__ idx1, const HistWork* __restrict__ work,
+                 unsigned long long* __restrict__ hist) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned* plane = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned char* stage_bins = smem_raw + 4 * kPlaneWords * 4;
+  int4* stage_q = reinterpret_cast<int4*>(stage_bins + kWsStages * kWsStageRows * 32);
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(stage_q) + kWsStages * kWsStageRows * 16);
+  unsigned long long* empty_bar = full_bar + kWsStages;
+
+  const HistWork w = *work;
+  const int n = w.count;
+  if (n <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* __restrict__ idx = w.buf ? idx1 : idx0;
+
+  long long cells_rows = static_cast<long long>(n) * num_tiles;
+  int rpi = static_cast<int>((cells_rows + gridDim.x - 1) / gridDim.x);
+  rpi = max(rpi, 2048);
+  rpi = min(rpi, kFlushRows);
+  rpi = (rpi + kWsStageRows - 1) / kWsStageRows * kWsStageRows;
+  const int chunks = (n + rpi - 1) / rpi;
+  const int items = chunks * num_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < kWsStages; ++i) { mbar_init(&full_bar[i], kWsProducerWarps * 32); mbar_init(&empty_bar[i], kWsConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  for (int e = tid; e < 4 * kPlaneWords; e += kWsThreads) plane[e] = 0u;
+  __syncthreads();
+
+  unsigned gs = 0;   // global stage counter (same sequence on both sides)
+  if (warp >= kWsConsumerWarps) {
+    // ------------------------------------------------------------------ producer warps
+    const int ptid = tid - kWsConsumerWarps * 32;                 // 0 .. kWsProducerWarps*32-1
+    constexpr int kPT = kWsProducerWarps * 32;
+    constexpr int kPerLane = kWsStageRows / kPT;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int tile = item % num_tiles, chunk = item / num_tiles;
+      const int row0 = chunk * rpi;
+      const int nrows = min(rpi, n - row0);
+      const int nst = (nrows + kWsStageRows - 1) / kWsStageRows;
+      const uint8_t* tbins = bins + static_cast<size_t>(tile) * rows_stride * 32;
+      for (int s = 0; s < nst; ++s, ++gs) {
+        const int slot = gs % kWsStages;
+        mbar_wait(&empty_bar[slot], ((gs / kWsStages) & 1u) ^ 1u);
+        const int p0 = row0 + s * kWsStageRows;
+        const int rows = min(kWsStageRows, row0 + nrows - p0);
+        unsigned char* db = stage_bins + slot * kWsStageRows * 32;
+        int4* dq = stage_q + slot * kWsStageRows;
+        if (!w.use_idx) {
+          if (ptid == 0) {
+            mbar_arrive_expect_tx(&full_bar[slot], static_cast<unsigned>(rows) * 48u);
+            const size_t r = static_cast<size_t>(w.begin + p0);
+            tma_bulk_g2s(db, tbins + r * 32, static_cast<unsigned>(rows) * 32u, &full_bar[slot]);
+            tma_bulk_g2s(dq, qgh + r, static_cast<unsigned>(rows) * 16u, &full_bar[slot]);
+          } else {
+            mbar_arrive(&full_bar[slot]);
+          }
+        } else {
+          const int* ip = idx + w.begin + p0;
+          int rr[kPerLane];
+#pragma unroll
+          for (int k = 0; k < kPerLane; ++k) { const int j = ptid + k * kPT; rr[k] = j < rows ? ip[j] : -1; }
+#pragma unroll
+          for (int k = 0; k < kPerLane; ++k) {
+            const int j = ptid + k * kPT;
+            if (rr[k] >= 0) {
+              const size_t r = static_cast<size_t>(rr[k]);
+              cp_async16(db + j * 32, tbins + r * 32, true);
+              cp_async16(db + j * 32 + 16, tbins + r * 32 + 16, true);
+              cp_async16(dq + j, qgh + r, true);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[slot]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    const int rsel = lane >> 3, wsel = lane & 7;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int tile = item % num_tiles, chunk = item / num_tiles;
+      const int row0 = chunk * rpi;
+      const int nrows = min(rpi, n - row0);
+      const int nst = (nrows + kWsStageRows - 1) / kWsStageRows;
+      for (int s = 0; s < nst; ++s, ++gs) {
+        const int slot = gs % kWsStages;
+        mbar_wait(&full_bar[slot], (gs / kWsStages) & 1u);
+        const int rows = min(kWsStageRows, nrows - s * kWsStageRows);
+        const unsigned* sw = reinterpret_cast<const unsigned*>(stage_bins + slot * kWsStageRows * 32);
+        const int4* sq = stage_q + slot * kWsStageRows;
+        const int groups = (rows + 3) >> 2;
+#pragma unroll 2
+        for (int g = warp; g < groups; g += kWsConsumerWarps) {
+          const int r = g * 4 + rsel;
+          if (r < rows) {
+            const unsigned word = sw[r * 8 + wsel];
+            const int4 q = sq[r];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int kk = (k + rsel) & 3;
+              const unsigned b = (word >> (8 * kk)) & 0xFFu;
+              const unsigned a = b * 32u + static_cast<unsigned>(wsel * 4 + kk);
+              atomicAdd(&plane[a], static_cast<unsigned>(q.x));
+              atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
+              atomicAdd(&plane[2 * kPlaneWords + a], static_cast<unsigned>(q.z));
+              if (NATOM == 4) atomicAdd(&plane[3 * kPlaneWords + a], static_cast<unsigned>(q.w));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+      }
+      // all consumers finished this item: flush the sub-histogram (consumer-only named barrier; the producer keeps staging)
+      asm volatile("bar.sync 1, %0;\n" ::"n"(kWsConsumerWarps * 32) : "memory");
+      for (int e = tid; e < kPlaneWords; e += kWsConsumerWarps * 32) {
+        unsigned ghi = plane[e], glo = plane[kPlaneWords + e];
+        unsigned hhi = plane[2 * kPlaneWords + e];
+        unsigned hlo = (NATOM == 4) ? plane[3 * kPlaneWords + e] : 0u;
+        if (ghi | glo | hhi | hlo) {
+          const int f = tile * 32 + (e & 31);
+          const int b = e >> 5;
+          long long g = (static_cast<long long>(static_cast<int>(ghi)) << kLoBits) + static_cast<long long>(glo);
+          long long h = (NATOM == 4) ? (static_cast<long long>(static_cast<int>(hhi)) << kLoBits) + static_cast<long long>(hlo)
+                                     : static_cast<long long>(hhi);
+          const size_t o = (static_cast<size_t>(f) * kBins + b) * 2;
+          if (g) atomicAdd(&hist[o], static_cast<unsigned long long>(g));
+          if (h) atomicAdd(&hist[o + 1], static_cast<unsigned long long>(h));
+          plane[e] = 0u;
+          plane[kPlaneWords + e] = 0u;
+          plane[2 * kPlaneWords + e] = 0u;
+          if (NATOM == 4) plane[3 * kPlaneWords + e] = 0u;
+        }
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(kWsConsumerWarps * 32) : "memory");
+    }
+  }
+}
+
 }  // namespace b200gbm

@@ -144,6 +144,7 @@ int main(int argc, char** argv) {
   printf(" \"smem_scatter_cells_per_cycle_per_sm\": {\n");
   const int it = 400;
   for (int threads : {512, 1024}) {
+    if (argc > 3 && atoi(argv[3]) == 1) { printf("  \"t%d\": {}%s\n", threads, threads == 512 ? "," : ""); continue; }
     printf("  \"t%d\": {", threads);
     printf("\"u32x4_rows4x32_rotated\": %.3f, ", run_mode<9>(threads, it, nsm));
     printf("\"u32x3_rows4x32_rotated\": %.3f, ", run_mode<10>(threads, it, nsm));
@@ -175,6 +176,9 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   CK(cudaFuncSetAttribute(k4_hist_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
   CK(cudaFuncSetAttribute(k4_hist_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+  CK(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+  CK(cudaFuncSetAttribute(k4_hist_build_ws<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+  const bool use_ws = argc > 2 && atoi(argv[2]) == 1;
 
   // correctness on the first 1M rows (contiguous) and on a strided index list
   {
@@ -183,8 +187,13 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_work, hw, sizeof(hw), cudaMemcpyHostToDevice));
     gen_idx<<<nsm, 256>>>(d_idx, n_chk / 3, 3);
     CK(cudaMemset(d_hist, 0, slot_elems * 8 * 2));
+    if (use_ws) {
+      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
+    } else {
     k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
     k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
+    }
     CK(cudaDeviceSynchronize());
     std::vector<long long> got(slot_elems * 2), want(slot_elems * 2, 0);
     CK(cudaMemcpy(got.data(), d_hist, slot_elems * 16, cudaMemcpyDeviceToHost));
@@ -217,7 +226,10 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 2; ++r) {
       CK(cudaMemsetAsync(d_hist, 0, slot_elems * 8));
       CK(cudaEventRecord(e0));
-      if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+      if (use_ws) {
+        if (natom == 4) k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+        else k4_hist_build_ws<3><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+      } else if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
       else k4_hist_build<3><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
