@@ -289,13 +289,19 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int* __restrict__ idx = w.buf ? idx1 : idx0;
 
+  // Work items are (tile, row chunk) pairs in TILE-MAJOR order; every CTA takes one contiguous range of them, so
+  // consecutive items of a CTA mostly belong to the same feature tile and the sub-histogram is flushed only when the
+  // tile changes or the 2^14-row field headroom is used up (small and medium leaves: one flush per CTA).
   long long cells_rows = static_cast<long long>(n) * num_tiles;
-  int rpi = static_cast<int>((cells_rows + gridDim.x - 1) / gridDim.x);
-  rpi = max(rpi, 2048);
-  rpi = min(rpi, kFlushRows);
+  int rpi = static_cast<int>((cells_rows + 4LL * gridDim.x - 1) / (4LL * gridDim.x));
   rpi = (rpi + kWsStageRows - 1) / kWsStageRows * kWsStageRows;
+  rpi = max(rpi, kWsStageRows);
+  rpi = min(rpi, kFlushRows);
   const int chunks = (n + rpi - 1) / rpi;
-  const int items = chunks * num_tiles;
+  const long long items = static_cast<long long>(chunks) * num_tiles;
+  const int i0 = static_cast<int>(items * blockIdx.x / gridDim.x);
+  const int i1 = static_cast<int>(items * (blockIdx.x + 1) / gridDim.x);
+  if (i0 >= i1) return;
 
   if (tid == 0) {
     for (int i = 0; i < kWsStages; ++i) { mbar_init(&full_bar[i], kWsProducerWarps * 32); mbar_init(&empty_bar[i], kWsConsumerWarps); }
@@ -310,8 +316,8 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
     const int ptid = tid - kWsConsumerWarps * 32;                 // 0 .. kWsProducerWarps*32-1
     constexpr int kPT = kWsProducerWarps * 32;
     constexpr int kPerLane = kWsStageRows / kPT;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int tile = item % num_tiles, chunk = item / num_tiles;
+    for (int item = i0; item < i1; ++item) {
+      const int tile = item / chunks, chunk = item - tile * chunks;
       const int row0 = chunk * rpi;
       const int nrows = min(rpi, n - row0);
       const int nst = (nrows + kWsStageRows - 1) / kWsStageRows;
@@ -355,8 +361,9 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
   } else {
     // ------------------------------------------------------------------ consumer warps
     const int rsel = lane >> 3, wsel = lane & 7;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int tile = item % num_tiles, chunk = item / num_tiles;
+    int acc_rows = 0;                                             // rows absorbed by the sub-histogram since the last flush
+    for (int item = i0; item < i1; ++item) {
+      const int tile = item / chunks, chunk = item - tile * chunks;
       const int row0 = chunk * rpi;
       const int nrows = min(rpi, n - row0);
       const int nst = (nrows + kWsStageRows - 1) / kWsStageRows;
@@ -388,7 +395,16 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);
       }
-      // all consumers finished this item: flush the sub-histogram (consumer-only named barrier; the producer keeps staging)
+      acc_rows += nrows;
+      bool flush = (item + 1 == i1);
+      if (!flush) {
+        const int ntile = (item + 1) / chunks, nchunk = (item + 1) - ntile * chunks;
+        const int nnext = min(rpi, n - nchunk * rpi);
+        flush = (ntile != tile) || (acc_rows + nnext > kFlushRows);
+      }
+      if (!flush) continue;
+      acc_rows = 0;
+      // all consumers finished: flush the sub-histogram (consumer-only named barrier; the producers keep staging)
       asm volatile("bar.sync 1, %0;\n" ::"n"(kWsConsumerWarps * 32) : "memory");
       for (int e = tid; e < kPlaneWords; e += kWsConsumerWarps * 32) {
         unsigned ghi = plane[e], glo = plane[kPlaneWords + e];
