@@ -130,8 +130,19 @@ def cpu_reference_run(n_total, F, sample_rows, steps, warmup, use_gpu_generator=
         from mmlspark_b200 import capi
         X, y = capi.synthetic_rows(rows, F, SEED, KIND_BINARY)       # generator only; no product compute on this arm
     else:
+        # same distribution as the device generator (csrc/c_api.cu syn_x / syn_label), drawn with numpy so that the reference arm
+        # touches none of the product's code
         rng = np.random.default_rng(SEED)
-        X = rng.random((sample_rows, F)); y = (rng.random(sample_rows) < 0.5).astype(np.float32)
+        U = rng.random((sample_rows, F), dtype=np.float32)
+        m = min(F, 16)
+        s = (np.sin(6.2831853 * U[:, :m]) * (1.0 + 0.1 * np.arange(m, dtype=np.float32))).sum(axis=1)
+        if F >= 2:
+            s += 8.0 * (U[:, 0] - 0.5) * (U[:, 1] - 0.5)
+        y = (rng.random(sample_rows) < 1.0 / (1.0 + np.exp(-s))).astype(np.float32)
+        X = U.astype(np.float64)
+        X *= (1.0 + (np.arange(F) % 7))
+        X -= (np.arange(F) % 5)
+        del U
     ods = O.OracleDataset(X, DS_PARAMS).set_field("label", y)
     ob = O.OracleBooster(ods, booster_params(1))
     for _ in range(warmup):
@@ -171,7 +182,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        ips_s, ips_x, info = cpu_reference_run(N, F, args.cpu_sample_rows, max(args.steps, 1), max(args.warmup, 1), use_gpu_generator=True)
+        ips_s, ips_x, info = cpu_reference_run(N, F, args.cpu_sample_rows, max(args.steps, 1), max(args.warmup, 1), use_gpu_generator=False)
         line = {"impl": "reference", "metric": "boosting_iters_per_sec", "value": ips_x, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 / ips_x, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64 histograms over u8 bins (fp32 gradients)", "data": "synthetic", "config": config,
@@ -273,6 +284,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int64 fixed-point histograms over u8 bins (fp32 gradients, fp64 split gains)", "data": "synthetic", "config": config,
             "hist_rows_x_feats_per_sec": hist_rows_all * F / (hist_ms / 1000.0) if hist_ms > 0 else None,
+            "histogram_reduce": ("fused reduce-scatter+scan over NVLink peer memory (k_scan_dp)" if bst.get_info()["fused_peer_reduce"] else
+                                 ("ncclAllReduce int64" if world > 1 else "none (1 rank)")),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"], "clocks": clocks,
             "dataset_build_s": build_s}
     print(json.dumps(line))

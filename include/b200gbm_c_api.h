@@ -181,6 +181,8 @@ int B200GBM_DatasetHistogram(DatasetHandle handle, const float* grad, const floa
 int B200GBM_BoosterSetProfile(BoosterHandle handle, int profile_hist);
 int B200GBM_BoosterGetTiming(BoosterHandle handle, double* out6, int reset);
 int B200GBM_BoosterGetScores(BoosterHandle handle, int data_idx, double* out);    /* raw scores, class-major */
+/* out = {num_machines, rank, fused_peer_reduce (1 = K5 reduces over NVLink peer memory, 0 = NCCL allreduce), constant_hessian} */
+int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4);
 
 #ifdef __cplusplus
 }

@@ -382,6 +382,11 @@ class Booster:
         check(load().B200GBM_BoosterGetTiming(self.handle, _ptr(out), C.c_int(1 if reset else 0)))
         return dict(hist_ms=out[0], total_ms=out[1], hist_rows=int(out[2]), hist_launches=int(out[3]), launches=int(out[4]), iterations=int(out[5]))
 
+    def get_info(self):
+        out = np.zeros(4, dtype=np.int32)
+        check(load().B200GBM_BoosterGetInfo(self.handle, _ptr(out)))
+        return dict(num_machines=int(out[0]), rank=int(out[1]), fused_peer_reduce=bool(out[2]), constant_hessian=bool(out[3]))
+
     def get_scores(self, data_idx=0):
         n = C.c_int64(0)
         check(load().LGBM_BoosterGetNumPredict(self.handle, C.c_int(data_idx), C.byref(n)))

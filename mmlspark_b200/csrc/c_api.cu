@@ -539,6 +539,11 @@ int B200GBM_BoosterGetTiming(BoosterHandle handle, double* out6, int reset) {
   if (reset) b->timing = Booster::Timing();
   API_END();
 }
+int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4) {
+  API_BEGIN();
+  BS(handle)->GetInfo(out4);
+  API_END();
+}
 int B200GBM_BoosterGetScores(BoosterHandle handle, int data_idx, double* out) {
   API_BEGIN();
   BS(handle)->GetRawScores(data_idx, out);

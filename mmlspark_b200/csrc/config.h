@@ -55,7 +55,7 @@ struct Config {
   bool is_unbalance = false;
   double scale_pos_weight = 1.0, sigmoid = 1.0;
   bool boost_from_average = true;
-  double alpha = 0.9, tweedie_variance_power = 1.5;
+  double alpha = 0.9, tweedie_variance_power = 1.5, fair_c = 1.0, poisson_max_delta_step = 0.7;
   int lambdarank_truncation_level = 30;
   bool lambdarank_norm = true;
   std::vector<double> label_gain;
@@ -170,7 +170,7 @@ struct Config {
     S("max_bin_by_feature", &max_bin_by_feature);
     I("num_class", &num_class); B("is_unbalance", &is_unbalance); D("scale_pos_weight", &scale_pos_weight);
     D("sigmoid", &sigmoid); B("boost_from_average", &boost_from_average); D("alpha", &alpha);
-    D("tweedie_variance_power", &tweedie_variance_power); I("lambdarank_truncation_level", &lambdarank_truncation_level);
+    D("tweedie_variance_power", &tweedie_variance_power); D("fair_c", &fair_c); D("poisson_max_delta_step", &poisson_max_delta_step); I("lambdarank_truncation_level", &lambdarank_truncation_level);
     B("lambdarank_norm", &lambdarank_norm); I("num_machines", &num_machines);
     {
       auto it = raw.find("label_gain");
@@ -236,7 +236,7 @@ struct Config {
     s << "[label_column: ]\n[weight_column: ]\n[group_column: ]\n[ignore_column: ]\n[categorical_feature: " << join_i(categorical_feature) << "]\n";
     s << "[forcedbins_filename: ]\n[objective_seed: 5]\n[num_class: " << num_class << "]\n[is_unbalance: " << is_unbalance << "]\n";
     s << "[scale_pos_weight: " << Num(scale_pos_weight) << "]\n[sigmoid: " << Num(sigmoid) << "]\n[boost_from_average: " << boost_from_average << "]\n";
-    s << "[reg_sqrt: 0]\n[alpha: " << Num(alpha) << "]\n[fair_c: 1]\n[poisson_max_delta_step: 0.7]\n";
+    s << "[reg_sqrt: 0]\n[alpha: " << Num(alpha) << "]\n[fair_c: " << Num(fair_c) << "]\n[poisson_max_delta_step: " << Num(poisson_max_delta_step) << "]\n";
     s << "[tweedie_variance_power: " << Num(tweedie_variance_power) << "]\n[lambdarank_truncation_level: " << lambdarank_truncation_level << "]\n";
     s << "[lambdarank_norm: " << lambdarank_norm << "]\n[label_gain: " << join_d(label_gain) << "]\n[eval_at: " << join_i(eval_at) << "]\n";
     s << "[multi_error_top_k: 1]\n[auc_mu_weights: ]\n[num_machines: " << num_machines << "]\n[local_listen_port: 12400]\n";

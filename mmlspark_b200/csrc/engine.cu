@@ -9,6 +9,7 @@
 #include <sys/select.h>
 #include <sys/socket.h>
 #include <unistd.h>
+#include <sys/types.h>
 
 #include <algorithm>
 #include <chrono>
@@ -576,11 +577,16 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   device_ = CurrentDevice();
   cfg.Parse(params);
   if (cfg.boosting != "gbdt") Fatal("boosting_type=" + cfg.boosting + " is not implemented by this build yet (gbdt only)");
-  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank")
+  {
+    static const char* kRegVar[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
+    for (int k = 1; k <= 5; ++k) if (cfg.objective == kRegVar[k]) regvar_kind_ = k;
+  }
+  if (cfg.objective == "regression_l1" || cfg.objective == "l1" || cfg.objective == "quantile" || cfg.objective == "mape")
+    Fatal("objective=" + cfg.objective + " needs leaf-output renewal (weighted percentiles), which this build does not implement yet");
+  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_)
     Fatal("Unknown/unsupported objective type name: " + cfg.objective);
   if (cfg.bagging_freq > 0 && (cfg.bagging_fraction < 1.0 || cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
     Fatal("bagging is not implemented by this build yet");
-  if (cfg.feature_fraction < 1.0) Fatal("feature_fraction < 1 is not implemented by this build yet");
   if (cfg.num_leaves < 2) Fatal("num_leaves should be >= 2");
   if (train->label.empty()) Fatal("label should not be empty for training");
   if (cfg.objective == "multiclass" && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
@@ -601,6 +607,7 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
 
 Booster::~Booster() {
   for (auto* v : valids_) delete v;
+  for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   if (tree_host_) cudaFreeHost(tree_host_);
   if (ctrl_host_) cudaFreeHost(ctrl_host_);
   if (leaves_host_) cudaFreeHost(leaves_host_);
@@ -674,6 +681,8 @@ void Booster::InitTraining() {
   const_hessian_ = false;
   if (cfg.objective == "regression") {
     const_hessian_ = train->weight.empty();
+  } else if (regvar_kind_) {
+    if (regvar_kind_ >= 3) for (int i = 0; i < n; ++i) if (train->label[i] < 0) Fatal("[" + cfg.objective + "]: at least one target label is negative");
   } else if (cfg.objective == "binary") {
     double cnt[2] = {0, 0};
     for (int i = 0; i < n; ++i) cnt[train->label[i] > 0 ? 1 : 0] += 1;
@@ -736,16 +745,106 @@ void Booster::InitTraining() {
     if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
     B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
   }
+  if (parallel_) SetupPeerReduce();
+  // ColSampler: one draw at init, then one per tree ([UPSTREAM] ColSampler::SetTrainingData / ResetByTree)
+  col_rand_ = LcgRandom(cfg.feature_fraction_seed);
+  feature_used_host_.assign(train->nf_pad, 0);
+  for (int u = 0; u < train->nf; ++u) feature_used_host_[u] = 1;
+  feature_used_.Alloc(train->nf_pad);
+  feature_used_.Upload(feature_used_host_.data(), train->nf_pad, stream_);
+  ResetFeaturesByTree();
   B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// Peer-memory set-up for the fused reduce+scan (k_scan_dp / k_pick_dp): every rank publishes its scratch histogram, mailbox and
+// flag block; ranks in the same process exchange raw pointers (peer access), ranks in other processes CUDA-IPC handles.
+struct PeerInfo {
+  long long pid;
+  int device, ok;
+  unsigned long long ptr[3];
+  cudaIpcMemHandle_t ipc[3];
+};
+void Booster::SetupPeerReduce() {
+  const char* env = std::getenv("B200GBM_FUSED_REDUCE");
+  const int R = Net().world, me = Net().rank;
+  mailbox_.Alloc(static_cast<size_t>(kMaxPeers) * 2); mailbox_.Zero(stream_);
+  peer_flags_.Alloc(32); peer_flags_.Zero(stream_);
+  peer_error_.Alloc(1); peer_error_.Zero(stream_);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  PeerInfo mine{};
+  mine.pid = static_cast<long long>(getpid()); mine.device = device_;
+  // Default = NCCL: measured on 8xB200 (100M x 512, profiles/r01_fused_vs_nccl_8gpu.md) the in-switch ncclAllReduce of the 2 MB
+  // histogram is ~3 % faster end to end than the fused peer-memory reduce-scatter (two cross-GPU flag barriers per split).
+  mine.ok = (R <= kMaxPeers && env && std::atoi(env) == 1) ? 1 : 0;
+  void* bufs[3] = {H_.p, mailbox_.p, peer_flags_.p};
+  for (int i = 0; i < 3; ++i) {
+    mine.ptr[i] = reinterpret_cast<unsigned long long>(bufs[i]);
+    if (cudaIpcGetMemHandle(&mine.ipc[i], bufs[i]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  }
+  std::vector<PeerInfo> all(R);
+  {
+    DevBuf<unsigned char> ds, dr; ds.Alloc(sizeof(PeerInfo)); dr.Alloc(sizeof(PeerInfo) * R);
+    B200_CUDA(cudaMemcpyAsync(ds.p, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, stream_));
+    B200_NCCL(ncclAllGather(ds.p, dr.p, sizeof(PeerInfo), ncclChar, Net().comm, stream_));
+    B200_CUDA(cudaMemcpyAsync(all.data(), dr.p, sizeof(PeerInfo) * R, cudaMemcpyDeviceToHost, stream_));
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  }
+  int ok = 1;
+  for (int r = 0; r < R; ++r) ok &= all[r].ok;
+  PeerTables pt{};
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      void* p3[3];
+      if (r == me) { for (int i = 0; i < 3; ++i) p3[i] = bufs[i]; }
+      else if (all[r].pid == mine.pid) {          // rank-thread of the same process (the reference's local mode)
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, device_, all[r].device);
+        if (!can) { ok = 0; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+        cudaGetLastError();
+        for (int i = 0; i < 3; ++i) p3[i] = reinterpret_cast<void*>(all[r].ptr[i]);
+      } else {                                    // one process per GPU (torchrun): CUDA IPC
+        for (int i = 0; i < 3; ++i) {
+          if (cudaIpcOpenMemHandle(&p3[i], all[r].ipc[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+          ipc_opened_.push_back(p3[i]);
+        }
+        if (!ok) break;
+      }
+      pt.H[r] = static_cast<const long long*>(p3[0]); pt.mail[r] = static_cast<SplitCand*>(p3[1]); pt.flags[r] = static_cast<unsigned*>(p3[2]);
+    }
+  }
+  // every rank must take the same path: agree on `ok`
+  double okd = ok ? 1.0 : 0.0;
+  AllReduceHost(&okd, 1, ncclMin, stream_);
+  fused_ = okd > 0.5;
+  if (!fused_) return;
+  const int tiles_per_rank = (train->num_tiles + R - 1) / R;
+  pt.rank = me; pt.world = R;
+  pt.feat0 = std::min(train->nf_pad, me * tiles_per_rank * 32);
+  pt.feat1 = std::min(train->nf_pad, (me + 1) * tiles_per_rank * 32);
+  pt.error = peer_error_.p;
+  peers_ = pt;
+}
+
+void Booster::ResetFeaturesByTree() {
+  if (cfg.feature_fraction >= 1.0) return;
+  const int total = train->nf;
+  int cnt = std::max(static_cast<int>(total * cfg.feature_fraction + 0.5), std::min(2, total));
+  std::fill(feature_used_host_.begin(), feature_used_host_.end(), 0);
+  for (int i : col_rand_.Sample(total, cnt)) feature_used_host_[i] = 1;
+  B200_CUDA(cudaStreamSynchronize(stream_));      // the previous tree must not still be reading the mask
+  feature_used_.Upload(feature_used_host_.data(), train->nf_pad, stream_);
 }
 
 double Booster::ObjectiveInitScore(int k) {
   const int n = train->num_data;
-  if (cfg.objective == "regression") {
+  if (cfg.objective == "regression" || regvar_kind_) {
     double suml = 0, sumw = 0;
     if (!train->weight.empty()) for (int i = 0; i < n; ++i) { suml += static_cast<double>(train->label[i]) * train->weight[i]; sumw += train->weight[i]; }
     else { sumw = n; for (int i = 0; i < n; ++i) suml += train->label[i]; }
     double v = suml / sumw;
+    if (regvar_kind_ >= 3) v = v > 0 ? std::log(v) : -std::numeric_limits<double>::infinity();
     if (parallel_) { AllReduceHost(&v, 1, ncclSum, stream_); v /= Net().world; }   // GlobalSyncUpByMean (R11)
     return v;
   }
@@ -783,6 +882,9 @@ void Booster::ComputeGradients() {
   const float* w = train->weight.empty() ? nullptr : train->d_weight.p;
   if (cfg.objective == "regression") {
     k_grad_l2<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n);
+  } else if (regvar_kind_) {
+    k_grad_regvar<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, regvar_kind_, cfg.alpha, cfg.fair_c,
+                                             cfg.poisson_max_delta_step, cfg.tweedie_variance_power);
   } else if (cfg.objective == "binary") {
     if (binary_need_train_)
       k_grad_binary<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, cfg.sigmoid, binary_w_[0], binary_w_[1]);
@@ -816,7 +918,8 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   k_set_scale<<<1, 1, 0, s>>>(ctrl, const_hessian_ ? 1 : 0, 1.0);
   k_quantize<<<egrid, 256, 0, s>>>(g, h, n, qgh_.p, ctrl, const_hessian_ ? 1 : 0);
   if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->root_q[0], &ctrl->root_q[0], 3, ncclInt64, ncclSum, Net().comm, s));
-  k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, n, nullptr);
+  ResetFeaturesByTree();
+  k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, n, feature_used_.p);
   timing.launches += 4;
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, num_sms_ * 8));
   const dim3 sgrid((d.nf + 7) / 8, 2);
@@ -832,9 +935,17 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k4_hist_build_ws<4><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
     if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
-    if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
-    k_scan<<<sgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
-    k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
+    if (fused_) {
+      // C2+K5+C3 fused over NVLink peer memory: signal "histogram ready", then the scan reduces its owned slice from all peers
+      ++epoch_;
+      const dim3 dgrid(std::max(1, (peers_.feat1 - peers_.feat0 + 7) / 8), 2);
+      k_scan_dp<<<dgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, peers_, pool_.p, slot_elems_, flags_.p, cands_.p, sp_, epoch_);
+      k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
+    } else {
+      if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2 (fallback)
+      k_scan<<<sgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+      k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
+    }
     k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
     k_part_scan<<<1, 1024, 0, s>>>(ctrl, part_chunks_.p);
     k_part_scatter<<<pgrid, 256, 0, s>>>(ctrl, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
@@ -855,6 +966,11 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     for (auto e : evs) cudaEventDestroy(e);
   }
   timing.hist_rows += ctrl_host_->trace_rows;
+  if (fused_) {
+    int err = 0;
+    B200_CUDA(cudaMemcpy(&err, peer_error_.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) Fatal("data-parallel training: a peer rank stopped responding (peer-memory barrier timed out)");
+  }
   // ---- host copy of the tree
   const unsigned char* hb = tree_host_;
   auto at = [&](const void* devp) { return hb + (static_cast<const unsigned char*>(devp) - tree_blob_.p); };
@@ -1097,7 +1213,24 @@ std::vector<double> Booster::GetEval(int data_idx) {
     return v[0] / v[1];
   };
   for (auto& m : cfg.metric) {
-    if (m == "l2" || m == "rmse" || m == "l1") {
+    if (m == "huber" || m == "fair" || m == "poisson" || m == "gamma" || m == "tweedie") {
+      double loss = 0, sw = 0;
+      const double rho = cfg.tweedie_variance_power, c = cfg.fair_c, a = cfg.alpha;
+      for (int i = 0; i < n; ++i) {
+        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
+        double sc = raw[i], l;
+        if (m == "huber") { double d = sc - lab; l = std::fabs(d) <= a ? 0.5 * d * d : a * (std::fabs(d) - 0.5 * a); }
+        else if (m == "fair") { double x = std::fabs(sc - lab); l = c * x - c * c * std::log(1.0 + x / c); }
+        else {
+          sc = std::exp(sc);                                  // ConvertOutput
+          if (m == "poisson") { sc = std::max(sc, 1e-10); l = sc - lab * std::log(sc); }
+          else if (m == "gamma") { double theta = -1.0 / sc, b = -(-theta > 0 ? std::log(-theta) : -INFINITY); double cc = (lab > 0 ? std::log(lab) : -INFINITY) - (lab > 0 ? std::log(lab) : -INFINITY); l = -((lab * theta - b) + cc); }
+          else { sc = std::max(sc, 1e-10); l = -lab * std::exp((1 - rho) * std::log(sc)) / (1 - rho) + std::exp((2 - rho) * std::log(sc)) / (2 - rho); }
+        }
+        loss += l * wi; sw += wi;
+      }
+      out.push_back(avg(loss, sw));
+    } else if (m == "l2" || m == "rmse" || m == "l1") {
       double loss = 0, sw = 0;
       for (int i = 0; i < n; ++i) {
         double wi = w.empty() ? 1.0 : w[i], d = raw[i] - y[i];

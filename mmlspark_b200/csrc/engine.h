@@ -136,6 +136,7 @@ class Booster {
   void GetPredict(int data_idx, int64_t* out_len, double* out);
   int64_t NumPredict(int data_idx) const;
   void GetRawScores(int data_idx, double* out);
+  void GetInfo(int* out4) const { out4[0] = parallel_ ? Net().world : 1; out4[1] = parallel_ ? Net().rank : 0; out4[2] = fused_ ? 1 : 0; out4[3] = const_hessian_ ? 1 : 0; }
   std::string SaveModelToString(int start_iteration, int num_iteration, int importance_type) const;
   std::string DumpModelJson(int start_iteration, int num_iteration) const;
 
@@ -172,6 +173,11 @@ class Booster {
   double binary_w_[2] = {1.0, 1.0};
   bool binary_need_train_ = true;
   std::vector<double> class_init_probs_;
+  int regvar_kind_ = 0;                 // 1 huber, 2 fair, 3 poisson, 4 gamma, 5 tweedie
+  LcgRandom col_rand_{2};               // ColSampler (feature_fraction)
+  std::vector<uint8_t> feature_used_host_;
+  DevBuf<uint8_t> feature_used_;
+  void ResetFeaturesByTree();
   SplitParams sp_{};
   // device state
   DevBuf<double> score_;        // [K][n]
@@ -198,6 +204,15 @@ class Booster {
   DevBuf<float> lr_sig_table_;
   double lr_min_in_ = -50, lr_max_in_ = 50, lr_idx_factor_ = 0;
   int lr_max_q_ = 0;
+  // fused data-parallel reduce (peer memory over NVLink); falls back to NCCL when peers cannot map each other
+  bool fused_ = false;
+  PeerTables peers_{};
+  DevBuf<SplitCand> mailbox_;
+  DevBuf<unsigned> peer_flags_;
+  DevBuf<int> peer_error_;
+  std::vector<void*> ipc_opened_;
+  unsigned epoch_ = 0;
+  void SetupPeerReduce();
   std::vector<ValidSet*> valids_;
   int num_sms_ = 148;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;

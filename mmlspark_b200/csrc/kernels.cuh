@@ -134,6 +134,21 @@ __global__ void k_grad_l2(const double* __restrict__ score, const float* __restr
     else { g[i] = static_cast<float>(score[i] - label[i]); h[i] = 1.0f; }
   }
 }
+// [UPSTREAM RegressionHuberLoss / FairLoss / PoissonLoss / GammaLoss / TweedieLoss ::GetGradients]; kind 1..5
+__global__ void k_grad_regvar(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                              float* __restrict__ g, float* __restrict__ h, int n, int kind, double alpha, double c, double mds, double rho) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double s = score[i], lab = label[i];
+    double gg, hh;
+    if (kind == 1) { const double diff = s - lab; gg = fabs(diff) <= alpha ? diff : d_sign(diff) * alpha; hh = 1.0; }
+    else if (kind == 2) { const double x = s - lab; gg = c * x / (fabs(x) + c); hh = c * c / ((fabs(x) + c) * (fabs(x) + c)); }
+    else if (kind == 3) { gg = exp(s) - lab; hh = exp(s + mds); }
+    else if (kind == 4) { gg = 1.0 - lab * exp(-s); hh = lab * exp(-s); }
+    else { gg = -lab * exp((1 - rho) * s) + exp((2 - rho) * s); hh = -lab * (1 - rho) * exp((1 - rho) * s) + (2 - rho) * exp((2 - rho) * s); }
+    if (weight) { gg *= weight[i]; hh *= weight[i]; }
+    g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
+  }
+}
 // [UPSTREAM BinaryLogloss::GetGradients]
 __global__ void k_grad_binary(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
                               float* __restrict__ g, float* __restrict__ h, int n, double sigmoid, double w_neg, double w_pos) {
@@ -415,39 +430,10 @@ __device__ __forceinline__ long long warp_prefix_excl(long long v, int lane) {  
   return inc - v;
 }
 
-__global__ void __launch_bounds__(256)
-k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta,
-       const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
-       SplitCand* __restrict__ cands, SplitParams p) {
-  if (!ctrl->go) return;
-  const int which = blockIdx.y;
-  const int leaf = which ? ctrl->larger : ctrl->smaller;
-  if (leaf < 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int u = blockIdx.x * 8 + warp;
-  if (u >= p.nf) return;
-  SplitCand out;
-  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
-  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
-  if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
-
-  const LeafState& L = leaves[leaf];
-  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
-  const long long* src = H + static_cast<size_t>(u) * 512;
-  long long qg[8], qh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int b = lane * 8 + j;
-    longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
-    if (which) {
-      longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2);
-      s.x = pr.x - s.x; s.y = pr.y - s.y;
-    }
-    *reinterpret_cast<longlong2*>(dst + b * 2) = s;
-    qg[j] = s.x; qh[j] = s.y;
-  }
-  const FeatMeta m = meta[u];
-  const double inv_g = ctrl->inv_g, inv_h = ctrl->inv_h;
+// the per-feature scan shared by k_scan and k_scan_dp: qg/qh = this lane's 8 bins of the (global) histogram
+__device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
+                                               double inv_g, double inv_h, const SplitParams& p, uint8_t* flag, SplitCand* outp) {
+  SplitCand& out = *outp;
   const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
   const int num_data = L.global_count;
   const double cnt_factor = num_data / sum_h;
@@ -554,7 +540,167 @@ k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, 
       out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = best_thr;
       out.left_count = best_lc; out.default_left = best_dl;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta,
+       const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
+       SplitCand* __restrict__ cands, SplitParams p) {
+  if (!ctrl->go) return;
+  const int which = blockIdx.y;
+  const int leaf = which ? ctrl->larger : ctrl->smaller;
+  if (leaf < 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = blockIdx.x * 8 + warp;
+  if (u >= p.nf) return;
+  SplitCand out;
+  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
+  if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
+
+  const LeafState& L = leaves[leaf];
+  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
+  const long long* src = H + static_cast<size_t>(u) * 512;
+  long long qg[8], qh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = lane * 8 + j;
+    longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
+    if (which) {
+      longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2);
+      s.x = pr.x - s.x; s.y = pr.y - s.y;
+    }
+    *reinterpret_cast<longlong2*>(dst + b * 2) = s;
+    qg[j] = s.x; qh[j] = s.y;
+  }
+  d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
+  if (lane == 0) {
     cands[which * p.nf_pad + u] = out;
+  }
+}
+
+// ---------------------------------------------------------------- fused data-parallel reduce + scan (C2 + K5 + C3)
+// Replaces  K4 -> ncclAllReduce(histogram) -> K5  by LightGBM's reduce-scatter scheme executed over NVLink peer
+// memory inside the scan kernel: rank r owns a contiguous slice of feature tiles; after a flag barrier ("all local
+// histograms are complete") its scan warps read the slice from EVERY rank's scratch histogram with P2P loads, sum it
+// (exact int64), scan only the owned features, and post the rank's two best candidates into every peer's mailbox.
+constexpr int kMaxPeers = 16;
+struct PeerTables {
+  const long long* H[kMaxPeers];       // every rank's scratch histogram (own entry = local pointer)
+  SplitCand* mail[kMaxPeers];          // every rank's mailbox [world][2]
+  unsigned* flags[kMaxPeers];          // every rank's flag block: [0..15] = "hist ready" epochs, [16..31] = "candidates posted"
+  int rank, world, feat0, feat1;       // owned inner-feature range [feat0, feat1)
+  int* error;                          // set when a spin-wait times out
+};
+
+__device__ __forceinline__ void peer_wait(const volatile unsigned* f, int world, unsigned epoch, int* error) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    while (static_cast<int>(f[r] - epoch) < 0) {
+      if (clock64() - t0 > 4000000000LL) { *error = 1; return; }   // ~2 s: a peer died; fail instead of hanging the GPU
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+// one small kernel after K4: tell every peer that this rank's scratch histogram is complete
+__global__ void k_peer_signal_hist(PeerTables pt, unsigned epoch) {
+  __threadfence_system();
+  const int r = threadIdx.x;
+  if (r < pt.world) *reinterpret_cast<volatile unsigned*>(&pt.flags[r][pt.rank]) = epoch;
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_dp(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta, PeerTables pt,
+          long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* __restrict__ cands, SplitParams p,
+          unsigned epoch) {
+  if (!ctrl->go) return;
+  const int which = blockIdx.y;
+  const int leaf = which ? ctrl->larger : ctrl->smaller;
+  if (leaf < 0) return;
+  // "my scratch histogram is complete" (K4 finished: stream order) -> every peer; then wait for all peers
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < pt.world) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(&pt.flags[threadIdx.x][pt.rank]) = epoch;
+  }
+  if (threadIdx.x == 0) peer_wait(pt.flags[pt.rank], pt.world, epoch, pt.error);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = pt.feat0 + blockIdx.x * 8 + warp;
+  if (u >= pt.feat1 || u >= p.nf) return;
+  SplitCand out;
+  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
+  if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
+
+  const LeafState& L = leaves[leaf];
+  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
+  long long qg[8], qh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { qg[j] = 0; qh[j] = 0; }
+  // reduce-scatter: sum the owned slice over all ranks.  P2P loads bypass L1 (volatile); 4 peers are in flight at a time so
+  // the ~2 us NVLink round trips overlap instead of serialising.
+  for (int r0 = 0; r0 < pt.world; r0 += 4) {
+    longlong2 v[4][8];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = min(r0 + rr, pt.world - 1);
+      const long long* src = pt.H[r] + static_cast<size_t>(u) * 512;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.volatile.global.v2.s64 {%0, %1}, [%2];\n" : "=l"(v[rr][j].x), "=l"(v[rr][j].y) : "l"(src + (lane * 8 + j) * 2));
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      if (r0 + rr < pt.world) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { qg[j] += v[rr][j].x; qh[j] += v[rr][j].y; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = lane * 8 + j;
+    if (which) {
+      longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2);
+      qg[j] = pr.x - qg[j]; qh[j] = pr.y - qh[j];
+    }
+    longlong2 sv; sv.x = qg[j]; sv.y = qh[j];
+    *reinterpret_cast<longlong2*>(dst + b * 2) = sv;
+  }
+  d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
+  if (lane == 0) cands[which * p.nf_pad + u] = out;
+}
+
+// leaf choice by warp 0: ArgMax over leaves with SplitInfo::operator> (gain desc, real feature asc, first index), stop on gain <= 0
+__device__ __forceinline__ void d_choose_leaf(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitParams& p, int lane) {
+  double bg = kNegInf; int bf = 0x7fffffff, bl = 0x7fffffff;
+  const int nl = ctrl->num_leaves;
+  for (int l = lane; l < nl; l += 32) {
+    const double g = leaves[l].best.gain;
+    const int fi = leaves[l].best.feature;
+    const int f = fi < 0 ? 0x7fffffff : meta[fi].real_index;
+    if (g > bg || (g == bg && (f < bf || (f == bf && l < bl)))) { bg = g; bf = f; bl = l; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, bg, o);
+    const int of = __shfl_xor_sync(0xffffffffu, bf, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (og > bg || (og == bg && (of < bf || (of == bf && ol < bl)))) { bg = og; bf = of; bl = ol; }
+  }
+  if (lane != 0) return;
+  const int best_leaf = bl == 0x7fffffff ? 0 : bl;
+  const LeafBest& b = leaves[best_leaf].best;
+  if (!(b.gain > 0.0) || ctrl->num_leaves >= p.num_leaves) {
+    ctrl->finished = 1; ctrl->split_leaf = -1; ctrl->part_count = 0;
+  } else {
+    const LeafState& L = leaves[best_leaf];
+    const FeatMeta fm = meta[b.feature];
+    ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
+    ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
+    ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
+    ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
+    ctrl->part_left_total = 0;
   }
 }
 
@@ -605,28 +751,94 @@ k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, con
       __syncthreads();
     }
   }
-  if (threadIdx.x == 0 && !ctrl->finished) {
-    int best_leaf = 0;
-    for (int l = 1; l < ctrl->num_leaves; ++l) {
-      const LeafBest& a = leaves[l].best;
-      const LeafBest& b = leaves[best_leaf].best;
-      const int fa = a.feature < 0 ? 0x7fffffff : meta[a.feature].real_index;
-      const int fb = b.feature < 0 ? 0x7fffffff : meta[b.feature].real_index;
-      if (a.gain > b.gain || (a.gain == b.gain && fa < fb)) best_leaf = l;
-    }
-    const LeafBest& b = leaves[best_leaf].best;
-    if (!(b.gain > 0.0) || ctrl->num_leaves >= p.num_leaves) {
-      ctrl->finished = 1; ctrl->split_leaf = -1; ctrl->part_count = 0;
-    } else {
-      const LeafState& L = leaves[best_leaf];
-      const FeatMeta fm = meta[b.feature];
-      ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
-      ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
-      ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
-      ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
-      ctrl->part_left_total = 0;
+  __syncthreads();
+  if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
+}
+
+// data-parallel pick: local argmax over the OWNED features, exchange of the per-rank winners through the peers'
+// mailboxes (C3, SyncUpGlobalBestSplit), global argmax with the same tie-breaks on every rank, then the usual leaf choice.
+__global__ void __launch_bounds__(256)
+k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* __restrict__ cands, SplitParams p,
+          PeerTables pt, unsigned epoch) {
+  __shared__ double s_gain[256];
+  __shared__ int s_feat[256], s_idx[256];
+  const bool go = ctrl->go != 0;
+  if (go) {
+    for (int which = 0; which < 2; ++which) {
+      const int leaf = which ? ctrl->larger : ctrl->smaller;
+      double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
+      if (leaf >= 0) {
+        for (int u = pt.feat0 + threadIdx.x; u < pt.feat1 && u < p.nf; u += blockDim.x) {
+          const SplitCand& c = cands[which * p.nf_pad + u];
+          const int rf = meta[u].real_index;
+          if (c.gain > bg || (c.gain == bg && rf < bf)) { bg = c.gain; bf = rf; bi = u; }
+        }
+      }
+      s_gain[threadIdx.x] = bg; s_feat[threadIdx.x] = bf; s_idx[threadIdx.x] = bi;
+      __syncthreads();
+      for (int s = 128; s; s >>= 1) {
+        if (threadIdx.x < s) {
+          double og = s_gain[threadIdx.x + s]; int of = s_feat[threadIdx.x + s];
+          if (og > s_gain[threadIdx.x] || (og == s_gain[threadIdx.x] && of < s_feat[threadIdx.x])) {
+            s_gain[threadIdx.x] = og; s_feat[threadIdx.x] = of; s_idx[threadIdx.x] = s_idx[threadIdx.x + s];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < pt.world) {      // post this rank's winner into every peer's mailbox
+        SplitCand c;
+        c.gain = kNegInf; c.left_g = 0; c.left_h = 0; c.threshold = 0; c.left_count = 0; c.default_left = 1; c.feature = -1;
+        if (s_idx[0] >= 0 && s_gain[0] > kNegInf) c = cands[which * p.nf_pad + s_idx[0]];
+        SplitCand* dst = pt.mail[threadIdx.x] + pt.rank * 2 + which;
+        volatile double* dd = reinterpret_cast<volatile double*>(dst);
+        dd[0] = c.gain; dd[1] = c.left_g; dd[2] = c.left_h;
+        volatile int* di = reinterpret_cast<volatile int*>(dd + 3);
+        di[0] = c.threshold; di[1] = c.left_count; di[2] = c.default_left; di[3] = c.feature;
+      }
+      __syncthreads();
     }
   }
+  // barrier B: "candidates posted" (also means: every peer is done reading this rank's scratch histogram)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pt.world) *reinterpret_cast<volatile unsigned*>(&pt.flags[threadIdx.x][16 + pt.rank]) = epoch;
+  if (threadIdx.x == 0) peer_wait(pt.flags[pt.rank] + 16, pt.world, epoch, pt.error);
+  __syncthreads();
+  if (threadIdx.x == 0 && go) {
+    for (int which = 0; which < 2; ++which) {
+      const int leaf = which ? ctrl->larger : ctrl->smaller;
+      if (leaf < 0) continue;
+      SplitCand best;
+      best.gain = kNegInf; best.feature = -1; best.left_g = best.left_h = 0; best.threshold = 0; best.left_count = 0; best.default_left = 1;
+      int best_rf = 0x7fffffff;
+      const SplitCand* mb = pt.mail[pt.rank];
+      for (int r = 0; r < pt.world; ++r) {
+        SplitCand c;
+        const volatile double* dd = reinterpret_cast<const volatile double*>(mb + r * 2 + which);
+        c.gain = dd[0]; c.left_g = dd[1]; c.left_h = dd[2];
+        const volatile int* di = reinterpret_cast<const volatile int*>(dd + 3);
+        c.threshold = di[0]; c.left_count = di[1]; c.default_left = di[2]; c.feature = di[3];
+        const int rf = c.feature < 0 ? 0x7fffffff : meta[c.feature].real_index;
+        if (c.gain > best.gain || (c.gain == best.gain && rf < best_rf)) { best = c; best_rf = rf; }
+      }
+      LeafState& L = leaves[leaf];
+      LeafBest b;
+      b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
+      b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.pad = 0;
+      if (best.feature >= 0 && best.gain > kNegInf) {
+        const double sum_h = L.sum_h + 2 * kEpsD;
+        b.gain = best.gain; b.feature = best.feature; b.threshold = best.threshold; b.default_left = best.default_left;
+        b.left_count = best.left_count; b.right_count = L.global_count - best.left_count;
+        b.left_g = best.left_g; b.left_h = best.left_h - kEpsD;
+        b.right_g = L.sum_g - best.left_g; b.right_h = sum_h - best.left_h - kEpsD;
+        b.left_out = d_calc_output(best.left_g, best.left_h, p);
+        b.right_out = d_calc_output(L.sum_g - best.left_g, sum_h - best.left_h, p);
+      }
+      L.best = b;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
 }
 
 // ---------------------------------------------------------------- K7 row partition (stable)

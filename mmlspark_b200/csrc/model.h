@@ -383,6 +383,8 @@ struct HostModel {
       double s = 0;
       for (int k = 0; k < num_class; ++k) { out[k] = std::exp(raw[k] - mx); s += out[k]; }
       for (int k = 0; k < num_class; ++k) out[k] /= s;
+    } else if (o.rfind("poisson", 0) == 0 || o.rfind("gamma", 0) == 0 || o.rfind("tweedie", 0) == 0) {
+      out[0] = std::exp(raw[0]);
     } else {
       for (int k = 0; k < num_tree_per_iteration; ++k) out[k] = raw[k];
     }

@@ -73,6 +73,8 @@ struct Config {
   std::vector<int> categorical_feature;
   int num_machines = 1;
   double feature_fraction = 1.0;
+  int feature_fraction_seed = 2;
+  double alpha = 0.9, fair_c = 1.0, poisson_max_delta_step = 0.7, tweedie_variance_power = 1.5;
   std::string tree_learner = "serial";
   int verbosity = 1;
   std::map<std::string, std::string> raw;
@@ -135,7 +137,9 @@ struct Config {
     getb("use_missing", use_missing); getb("zero_as_missing", zero_as_missing);
     getb("feature_pre_filter", feature_pre_filter); geti("lambdarank_truncation_level", lambdarank_truncation_level);
     getb("lambdarank_norm", lambdarank_norm); geti("num_machines", num_machines);
-    getd("feature_fraction", feature_fraction); geti("verbosity", verbosity);
+    getd("feature_fraction", feature_fraction); geti("verbosity", verbosity); geti("feature_fraction_seed", feature_fraction_seed);
+    getd("alpha", alpha); getd("fair_c", fair_c); getd("poisson_max_delta_step", poisson_max_delta_step);
+    getd("tweedie_variance_power", tweedie_variance_power);
     auto split_list = [&](const char* k, auto& out, auto conv) {
       auto it = raw.find(k);
       if (it == raw.end() || it->second.empty()) return;
@@ -471,6 +475,40 @@ struct RegressionL2 : Objective {
   std::string ToString() const override { return "regression"; }
 };
 
+// [UPSTREAM regression_objective.hpp] huber / fair / poisson / gamma / tweedie: elementwise variants of L2
+struct RegressionVariant : RegressionL2 {
+  int kind;   // 1 huber, 2 fair, 3 poisson, 4 gamma, 5 tweedie
+  explicit RegressionVariant(int k) : kind(k) {}
+  void GetGradients(const double* score, float* g, float* h) const override {
+    const int n = ds->n;
+    const float* y = ds->label.data();
+    const float* w = ds->weight.empty() ? nullptr : ds->weight.data();
+    const double alpha = cfg.alpha, c = cfg.fair_c, mds = cfg.poisson_max_delta_step, rho = cfg.tweedie_variance_power;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double gg, hh;
+      const double s = score[i], lab = y[i];
+      if (kind == 1) { const double diff = s - lab; gg = std::fabs(diff) <= alpha ? diff : ((diff > 0.0) - (diff < 0.0)) * alpha; hh = 1.0; }
+      else if (kind == 2) { const double x = s - lab; gg = c * x / (std::fabs(x) + c); hh = c * c / ((std::fabs(x) + c) * (std::fabs(x) + c)); }
+      else if (kind == 3) { gg = std::exp(s) - lab; hh = std::exp(s + mds); }
+      else if (kind == 4) { gg = 1.0 - lab * std::exp(-s); hh = lab * std::exp(-s); }
+      else { gg = -lab * std::exp((1 - rho) * s) + std::exp((2 - rho) * s); hh = -lab * (1 - rho) * std::exp((1 - rho) * s) + (2 - rho) * std::exp((2 - rho) * s); }
+      if (w) { gg *= w[i]; hh *= w[i]; }
+      g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
+    }
+  }
+  double BoostFromScore(int k, int r0, int r1) const override {
+    double m = RegressionL2::BoostFromScore(k, r0, r1);
+    if (kind >= 3) return m > 0 ? std::log(m) : -std::numeric_limits<double>::infinity();
+    return m;
+  }
+  bool IsConstantHessian() const override { return false; }
+  std::string ToString() const override {
+    static const char* names[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
+    return names[kind];
+  }
+};
+
 struct BinaryLogloss : Objective {
   double label_weights[2] = {1.0, 1.0};
   void Init(const Dataset* d, const Config& c) override {
@@ -676,6 +714,11 @@ struct LambdarankNDCG : Objective {
 
 static Objective* CreateObjective(const Config& c) {
   if (c.objective == "regression") return new RegressionL2();
+  if (c.objective == "huber") return new RegressionVariant(1);
+  if (c.objective == "fair") return new RegressionVariant(2);
+  if (c.objective == "poisson") return new RegressionVariant(3);
+  if (c.objective == "gamma") return new RegressionVariant(4);
+  if (c.objective == "tweedie") return new RegressionVariant(5);
   if (c.objective == "binary") return new BinaryLogloss();
   if (c.objective == "multiclass") return new MulticlassSoftmax();
   if (c.objective == "lambdarank") return new LambdarankNDCG();
@@ -984,6 +1027,8 @@ struct TreeLearner {
   std::vector<float> og, oh;                           // ordered gradients
   std::vector<SplitRec>* trace = nullptr;
   int cur_tree = 0;
+  std::vector<uint8_t> feature_used;                   // ColSampler::is_feature_used_ (by tree)
+  Random col_rand{2};
   double hist_seconds = 0;
   long long hist_cells = 0;
 
@@ -998,6 +1043,16 @@ struct TreeLearner {
     splittable.assign(L, std::vector<uint8_t>());
     best.assign(L, SplitInfo());
     leaf_sum_g.assign(L, 0); leaf_sum_h.assign(L, 0);
+    col_rand = Random(c.feature_fraction_seed);
+    feature_used.assign(nf, 1);
+    ResetByTree();    // [UPSTREAM ColSampler::SetTrainingData draws once at init, then once per tree]
+  }
+  void ResetByTree() {
+    if (cfg.feature_fraction >= 1.0) return;
+    int total = nf;
+    int cnt = std::max(RoundInt(total * cfg.feature_fraction), std::min(2, total));
+    std::fill(feature_used.begin(), feature_used.end(), 0);
+    for (int i : col_rand.Sample(total, cnt)) feature_used[i] = 1;
   }
   static double now() {
 #ifdef _OPENMP
@@ -1062,7 +1117,8 @@ struct TreeLearner {
 #pragma omp parallel for schedule(static) reduction(+ : sg, sh)
     for (int i = 0; i < n; ++i) { sg += g[i]; sh += h[i]; }
     leaf_sum_g[0] = sg; leaf_sum_h[0] = sh;
-    splittable[0].assign(nf, 1);
+    ResetByTree();
+    splittable[0].assign(feature_used.begin(), feature_used.end());
     int left_leaf = 0, right_leaf = -1;
     for (int split = 0; split < L - 1; ++split) {
       // BeforeFindBestSplit

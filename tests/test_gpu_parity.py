@@ -288,3 +288,58 @@ def test_determinism_run_to_run(built):
         strs.append(b.save_model_to_string())
         b.free()
     assert strs[0] == strs[1]
+
+
+@pytest.mark.parametrize("objective", ["huber", "fair", "poisson", "gamma", "tweedie"])
+def test_regression_objective_variants(built, objective):
+    """LightGBMRegressor.objective values without leaf renewal (LightGBMRegressor.scala:46, TrainParams.scala:165-179)."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(51)
+    n, F = 30000, 14
+    X = rng.standard_normal((n, F))
+    mu = 0.8 * X[:, 0] + 0.5 * np.sin(2 * X[:, 1]) + 0.3 * X[:, 2] * X[:, 3]
+    if objective in ("poisson", "tweedie"):
+        y = rng.poisson(np.exp(mu)).astype(np.float32)
+    elif objective == "gamma":
+        y = (rng.gamma(2.0, np.exp(mu) / 2.0) + 1e-3).astype(np.float32)
+    else:
+        y = (mu + 0.3 * rng.standard_t(3, n)).astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params(objective, "alpha=0.9 tweedie_variance_power=1.5", leaves=15)
+    b, ob, m, om = _train_both(ds, ods, params, 12)
+    compare_models(m, om)
+    assert m["header"]["objective"] == objective
+    raw = b.predict_for_mat(X[:50], predict_type=1)[:, 0]
+    norm = b.predict_for_mat(X[:50])[:, 0]
+    if objective in ("poisson", "gamma", "tweedie"):
+        np.testing.assert_allclose(norm, np.exp(raw), rtol=1e-12)          # ConvertOutput = exp
+    else:
+        np.testing.assert_array_equal(norm, raw)
+    ev = b.get_eval(0)
+    assert b.eval_names() == [objective] and np.isfinite(ev).all()
+
+
+def test_unsupported_objective_fails_loudly(built):
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((500, 3)); y = rng.standard_normal(500).astype(np.float32)
+    ds, _ = _make(X, y)
+    for obj in ("regression_l1", "quantile", "not_an_objective"):
+        with pytest.raises(capi.LightGBMError):
+            capi.Booster(ds, "objective=%s" % obj)
+    with pytest.raises(capi.LightGBMError):
+        capi.Booster(ds, "objective=regression boosting_type=dart")
+
+
+def test_feature_fraction_column_sampling(built):
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(61)
+    n, F = 20000, 24
+    X = rng.standard_normal((n, F))
+    y = (X[:, :6].sum(axis=1) + 0.5 * rng.standard_normal(n)).astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params("regression", "", leaves=15).replace("feature_fraction=1.0", "feature_fraction=0.4")
+    b, ob, m, om = _train_both(ds, ods, params, 10)
+    compare_models(m, om)
+    used = [set(t["split_feature"].tolist()) for t in m["trees"]]
+    assert all(len(u) <= 10 for u in used) and len(set().union(*used)) > 10      # <= round(24*0.4) features per tree, different per tree
