@@ -374,6 +374,21 @@ class Booster:
         return out[:n.value].reshape(nrow, -1)
 
     # --- engine extensions
+    def predict_device(self, X, predict_type=PREDICT_NORMAL, start_iteration=0, num_iteration=-1, return_ms=False):
+        """Batched GPU prediction (B200GBM_BoosterPredictForMatDevice); X: float32/float64 [nrow, ncol] host array."""
+        X = np.ascontiguousarray(X)
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        nrow, ncol = X.shape
+        n = C.c_int64(0)
+        check(load().LGBM_BoosterCalcNumPredict(self.handle, C.c_int(nrow), C.c_int(predict_type), C.c_int(start_iteration), C.c_int(num_iteration), C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.float64)
+        ms = C.c_double(0)
+        check(load().B200GBM_BoosterPredictForMatDevice(self.handle, _ptr(X), C.c_int(_np_dtype_code(X)), C.c_int64(nrow), C.c_int32(ncol), C.c_int(predict_type),
+                                                        C.c_int(start_iteration), C.c_int(num_iteration), C.byref(n), _ptr(out), C.byref(ms)))
+        res = out[:n.value].reshape(nrow, -1)
+        return (res, ms.value) if return_ms else res
+
     def set_profile(self, on=True):
         check(load().B200GBM_BoosterSetProfile(self.handle, C.c_int(1 if on else 0)))
 

@@ -539,6 +539,14 @@ int B200GBM_BoosterGetTiming(BoosterHandle handle, double* out6, int reset) {
   if (reset) b->timing = Booster::Timing();
   API_END();
 }
+int B200GBM_BoosterPredictForMatDevice(BoosterHandle handle, const void* data, int data_type, int64_t nrow, int32_t ncol, int predict_type,
+                                       int start_iteration, int num_iteration, int64_t* out_len, double* out_result, double* elapsed_ms) {
+  API_BEGIN();
+  Booster* b = BS(handle);
+  *out_len = b->PredictBatch(data, data_type, nrow, ncol, predict_type, start_iteration, num_iteration, out_result);
+  if (elapsed_ms) *elapsed_ms = b->last_predict_ms;
+  API_END();
+}
 int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4) {
   API_BEGIN();
   BS(handle)->GetInfo(out4);

@@ -1307,6 +1307,93 @@ void Booster::GetRawScores(int data_idx, double* out) {
   B200_CUDA(cudaStreamSynchronize(stream_));
 }
 
+void Booster::UploadForest() {
+  if (forest_ && forest_->trees == model.trees.size()) return;
+  forest_.reset(new ForestBufs());
+  ForestBufs& f = *forest_;
+  const size_t T = model.trees.size();
+  std::vector<int> toff(T + 1, 0), loff(T + 1, 0), nl(T), sf, dt, lc, rc;
+  std::vector<double> thr, lv;
+  for (size_t t = 0; t < T; ++t) {
+    const HostTree& tr = *model.trees[t];
+    nl[t] = tr.num_leaves;
+    toff[t + 1] = toff[t] + std::max(tr.num_leaves - 1, 0);
+    loff[t + 1] = loff[t] + tr.num_leaves;
+    for (int i = 0; i < tr.num_leaves - 1; ++i) {
+      sf.push_back(tr.split_feature[i]); dt.push_back(tr.decision_type[i]); lc.push_back(tr.left_child[i]); rc.push_back(tr.right_child[i]);
+      thr.push_back(tr.threshold[i]);
+    }
+    for (int i = 0; i < tr.num_leaves; ++i) lv.push_back(tr.leaf_value[i]);
+  }
+  if (!stream_) B200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  auto up_i = [&](DevBuf<int>& d, std::vector<int>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
+  auto up_d = [&](DevBuf<double>& d, std::vector<double>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
+  up_i(f.tree_offset, toff); up_i(f.leaf_offset, loff); up_i(f.num_leaves, nl); up_i(f.split_feature, sf); up_i(f.decision_type, dt);
+  up_i(f.left_child, lc); up_i(f.right_child, rc); up_d(f.threshold, thr); up_d(f.leaf_value, lv);
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  f.trees = T;
+}
+
+int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int ncol, int predict_type, int start_iteration, int num_iteration,
+                              double* out) {
+  EnsureDevice();
+  if (data_type != 0 && data_type != 1) Fatal("PredictBatch: unknown data type");
+  if (predict_type < 0 || predict_type > 2) Fatal("PredictBatch supports normal / raw-score / leaf-index prediction (SHAP stays on the host predictor)");
+  if (ncol < model.max_feature_idx + 1) Fatal("PredictBatch: the matrix has fewer columns than the model has features");
+  UploadForest();
+  const ForestBufs& fb = *forest_;
+  ForestDev f{fb.tree_offset.p, fb.leaf_offset.p, fb.num_leaves.p, fb.split_feature.p, fb.threshold.p, fb.decision_type.p, fb.left_child.p, fb.right_child.p, fb.leaf_value.p};
+  int t0, t1;
+  model.IterRange(start_iteration, num_iteration, &t0, &t1);
+  const int Kc = model.num_tree_per_iteration;
+  const int64_t per_row = predict_type == 2 ? (t1 - t0) : Kc;
+  const size_t esz = data_type == 0 ? 4 : 8;
+  const bool on_device = IsDevicePointer(data);
+  const int64_t chunk = on_device ? nrow : std::max<int64_t>(1, std::min<int64_t>(nrow, (512LL << 20) / (static_cast<int64_t>(ncol) * esz)));
+  DevBuf<unsigned char> xin;
+  if (!on_device) xin.Alloc(static_cast<size_t>(chunk) * ncol * esz);
+  DevBuf<double> dout; dout.Alloc(static_cast<size_t>(std::min(chunk, nrow)) * per_row);
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, stream_));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, CurrentDevice());
+  for (int64_t r0 = 0; r0 < nrow; r0 += chunk) {
+    const int64_t rows = std::min(chunk, nrow - r0);
+    const void* x = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esz;
+    if (!on_device) { B200_CUDA(cudaMemcpyAsync(xin.p, x, static_cast<size_t>(rows) * ncol * esz, cudaMemcpyHostToDevice, stream_)); x = xin.p; }
+    const int grid = static_cast<int>(std::min<int64_t>((rows * per_row + 255) / 256, static_cast<int64_t>(sms) * 16));
+    if (predict_type == 2) {
+      if (data_type == 0) k_predict_leaf<float><<<grid, 256, 0, stream_>>>(f, static_cast<const float*>(x), rows, ncol, t0, t1, dout.p);
+      else k_predict_leaf<double><<<grid, 256, 0, stream_>>>(f, static_cast<const double*>(x), rows, ncol, t0, t1, dout.p);
+    } else {
+      if (data_type == 0) k_predict_raw<float><<<grid, 256, 0, stream_>>>(f, static_cast<const float*>(x), rows, ncol, Kc, t0, t1, dout.p);
+      else k_predict_raw<double><<<grid, 256, 0, stream_>>>(f, static_cast<const double*>(x), rows, ncol, Kc, t0, t1, dout.p);
+    }
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(out + r0 * per_row, dout.p, static_cast<size_t>(rows) * per_row * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  }
+  B200_CUDA(cudaEventRecord(e1, stream_));
+  B200_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  last_predict_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (predict_type == 0) {          // objective transform on the host, identical to the single-row predictor
+    std::vector<double> r(Kc), o(Kc);
+    const bool avg = model.average_output && t1 > t0;
+    for (int64_t i = 0; i < nrow; ++i) {
+      double* p = out + i * Kc;
+      if (avg) for (int k = 0; k < Kc; ++k) p[k] /= ((t1 - t0) / Kc);
+      for (int k = 0; k < Kc; ++k) r[k] = p[k];
+      model.Convert(r.data(), o.data());
+      for (int k = 0; k < Kc; ++k) p[k] = o[k];
+    }
+  }
+  return nrow * per_row;
+}
+
 void Booster::ExportLastHistogram(double* out) {
   EnsureDevice();
   DevBuf<double> d; d.Alloc(slot_elems_);

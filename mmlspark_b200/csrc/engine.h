@@ -136,6 +136,10 @@ class Booster {
   void GetPredict(int data_idx, int64_t* out_len, double* out);
   int64_t NumPredict(int data_idx) const;
   void GetRawScores(int data_idx, double* out);
+  // batched GPU prediction over a row-major matrix (host or device pointer); predict_type 0 normal, 1 raw, 2 leaf index.
+  // Returns the number of doubles written to `out` (host).  last_predict_ms = kernel time (CUDA events), incl. H2D for host input.
+  int64_t PredictBatch(const void* data, int data_type, int64_t nrow, int ncol, int predict_type, int start_iteration, int num_iteration, double* out);
+  double last_predict_ms = 0.0;
   void GetInfo(int* out4) const { out4[0] = parallel_ ? Net().world : 1; out4[1] = parallel_ ? Net().rank : 0; out4[2] = fused_ ? 1 : 0; out4[3] = const_hessian_ ? 1 : 0; }
   std::string SaveModelToString(int start_iteration, int num_iteration, int importance_type) const;
   std::string DumpModelJson(int start_iteration, int num_iteration) const;
@@ -213,6 +217,10 @@ class Booster {
   std::vector<void*> ipc_opened_;
   unsigned epoch_ = 0;
   void SetupPeerReduce();
+  // flattened forest for PredictBatch
+  struct ForestBufs { DevBuf<int> tree_offset, leaf_offset, num_leaves, split_feature, decision_type, left_child, right_child; DevBuf<double> threshold, leaf_value; size_t trees = 0; };
+  std::unique_ptr<ForestBufs> forest_;
+  void UploadForest();
   std::vector<ValidSet*> valids_;
   int num_sms_ = 148;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;

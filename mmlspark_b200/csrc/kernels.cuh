@@ -1002,6 +1002,63 @@ k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t
   }
 }
 
+// ---------------------------------------------------------------- batched prediction
+// Flattened forest on the device; one thread per (row, class) walks the trees of its class in model order, so the raw
+// score is the same sequence of fp64 additions as the host predictor (HostModel::PredictRow) => bit-identical.
+struct ForestDev {
+  const int* tree_offset;        // [num_trees+1] node offset of each tree (a tree with L leaves has L-1 nodes)
+  const int* leaf_offset;        // [num_trees+1]
+  const int* num_leaves;         // [num_trees]
+  const int* split_feature;      // per node: real feature index
+  const double* threshold;
+  const int* decision_type;
+  const int* left_child;
+  const int* right_child;
+  const double* leaf_value;
+};
+template <typename T>
+__device__ __forceinline__ int d_tree_leaf(const ForestDev& f, int t, const T* __restrict__ row) {
+  if (f.num_leaves[t] <= 1) return 0;
+  const int nb = f.tree_offset[t];
+  int node = 0;
+  while (node >= 0) {
+    const int g = nb + node;
+    double fval = static_cast<double>(row[f.split_feature[g]]);
+    const int dt = f.decision_type[g];
+    const int mt = (dt >> 2) & 3;
+    if (isnan(fval) && mt != 2) fval = 0.0;
+    bool left;
+    if ((mt == 1 && fabs(fval) <= 1e-35) || (mt == 2 && isnan(fval))) left = (dt & 2) != 0;
+    else left = fval <= f.threshold[g];
+    node = left ? f.left_child[g] : f.right_child[g];
+  }
+  return ~node;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_predict_raw(ForestDev f, const T* __restrict__ X, long long nrow, int ncol, int K, int t0, int t1, double* __restrict__ out) {
+  const long long total = nrow * K;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / K;
+    const int k = static_cast<int>(e - r * K);
+    const T* row = X + r * ncol;
+    double acc = 0.0;
+    for (int t = t0 + k; t < t1; t += K) acc += f.leaf_value[f.leaf_offset[t] + d_tree_leaf(f, t, row)];
+    out[e] = acc;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_predict_leaf(ForestDev f, const T* __restrict__ X, long long nrow, int ncol, int t0, int t1, double* __restrict__ out) {
+  const int nt = t1 - t0;
+  const long long total = nrow * nt;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / nt;
+    const int t = t0 + static_cast<int>(e - r * nt);
+    out[e] = static_cast<double>(d_tree_leaf(f, t, X + r * ncol));
+  }
+}
+
 // histogram int64 -> fp64 (debug / parity export)
 __global__ void k_hist_to_double(const long long* __restrict__ H, double* __restrict__ out, size_t elems, const TreeCtrl* ctrl) {
   const double ig = ctrl->inv_g, ih = ctrl->inv_h;

@@ -106,8 +106,9 @@ class LightGBMBooster:
         return self._handle().predict_for_mat_single(features, capi.PREDICT_CONTRIB, self.startIteration, self.numIterations)
 
     def score_batch(self, X, raw, classification):
+        """transform(): one batched GPU prediction instead of the reference's per-row UDF; same values as score()."""
         kind = capi.PREDICT_RAW_SCORE if raw else capi.PREDICT_NORMAL
-        out = self._handle().predict_for_mat(X, kind, self.startIteration, self.numIterations)
+        out = self._handle().predict_device(X, kind, self.startIteration, self.numIterations)
         if classification and self.numClasses == 1:
             p = out[:, 0]
             return np.stack([-p, p], axis=1) if raw else np.stack([1 - p, p], axis=1)
@@ -154,7 +155,8 @@ class _ModelBase(Params):
 
     def _extra_columns(self, out, X):
         if self.get("leafPredictionCol"):
-            out = out.with_column(self.get("leafPredictionCol"), np.stack([self.booster.predictLeaf(r) for r in X]))
+            out = out.with_column(self.get("leafPredictionCol"), self.booster._handle().predict_device(
+                X, capi.PREDICT_LEAF_INDEX, self.booster.startIteration, self.booster.numIterations))
         if self.get("featuresShapCol"):
             out = out.with_column(self.get("featuresShapCol"), np.stack([self.booster.featuresShap(r) for r in X]))
         return out

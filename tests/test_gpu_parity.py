@@ -343,3 +343,38 @@ def test_feature_fraction_column_sampling(built):
     compare_models(m, om)
     used = [set(t["split_feature"].tolist()) for t in m["trees"]]
     assert all(len(u) <= 10 for u in used) and len(set().union(*used)) > 10      # <= round(24*0.4) features per tree, different per tree
+
+
+def test_batched_gpu_prediction_bit_exact_with_host_predictor(built):
+    """B200GBM_BoosterPredictForMatDevice against the host single-row predictor the reference's UDFs use."""
+    import json
+    import os
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(71)
+    n, F = 50000, 20
+    X = rng.standard_normal((n, F))
+    X[rng.random((n, F)) < 0.05] = np.nan
+    y = (np.nan_to_num(X[:, 0]) + np.nan_to_num(X[:, 1]) ** 2 + 0.3 * rng.standard_normal(n) > 0.8).astype(np.float32)
+    ds, _ = _make(X, y)
+    b = capi.Booster(ds, _classifier_params("binary", "is_unbalance=false", leaves=31))
+    for _ in range(20):
+        b.update_one_iter()
+    for pt in (capi.PREDICT_RAW_SCORE, capi.PREDICT_NORMAL, capi.PREDICT_LEAF_INDEX):
+        dev = b.predict_device(X, pt)
+        host = b.predict_for_mat(X, pt)
+        assert dev.shape == host.shape
+        np.testing.assert_array_equal(dev, host)
+    np.testing.assert_array_equal(b.predict_device(X, capi.PREDICT_RAW_SCORE, 3, 5), b.predict_for_mat(X, capi.PREDICT_RAW_SCORE, 3, 5))
+    # float32 input and a prediction-only booster loaded from the model text
+    b2 = capi.Booster(model_str=b.save_model_to_string())
+    X32 = X.astype(np.float32)
+    np.testing.assert_array_equal(b2.predict_device(X32, capi.PREDICT_RAW_SCORE), b.predict_for_mat(X32.astype(np.float64), capi.PREDICT_RAW_SCORE))
+    # multiclass golden model
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")))["models"]["multiclass"]["model"]
+    mc = capi.Booster(model_str=g)
+    Xm = rng.standard_normal((3000, 10))
+    np.testing.assert_array_equal(mc.predict_device(Xm, capi.PREDICT_RAW_SCORE), mc.predict_for_mat(Xm, capi.PREDICT_RAW_SCORE))
+    np.testing.assert_array_equal(mc.predict_device(Xm), mc.predict_for_mat(Xm))
+    big = np.tile(X32, (20, 1))
+    out, ms = b.predict_device(big, capi.PREDICT_RAW_SCORE, return_ms=True)
+    print("GPU batch predict: %d rows x %d feats x 20 trees in %.2f ms (incl. H2D/D2H) = %.1f Mrows/s" % (big.shape[0], F, ms, big.shape[0] / ms / 1e3))
