@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <limits>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -60,6 +61,10 @@ struct FeatureBins {
   int num_bin = 1;
   int missing_type = MISSING_NONE;
   bool trivial = true;
+  bool categorical = false;
+  std::vector<int> bin_to_cat;      // categorical: bin -> category value; bin 0 = -1 (NaN, negative, rare or unseen categories)
+  std::vector<int> sorted_cats;     // categories in ascending order ...
+  std::vector<int> sorted_bins;     // ... and the bin of each (device lookup table = binary search over sorted_cats)
   uint32_t default_bin = 0;
   uint32_t most_freq_bin = 0;
   double sparse_rate = 1.0;
@@ -67,6 +72,13 @@ struct FeatureBins {
   std::vector<double> upper;   // upper[b] = inclusive upper bound of bin b; NaN bin (if any) is last
 
   uint32_t ValueToBin(double v) const {
+    if (categorical) {
+      if (std::isnan(v)) return 0;
+      const int iv = static_cast<int>(v);
+      if (iv < 0) return 0;
+      auto it = std::lower_bound(sorted_cats.begin(), sorted_cats.end(), iv);
+      return (it != sorted_cats.end() && *it == iv) ? static_cast<uint32_t>(sorted_bins[it - sorted_cats.begin()]) : 0u;
+    }
     if (std::isnan(v)) {
       if (missing_type == MISSING_NAN) return static_cast<uint32_t>(num_bin - 1);
       v = 0.0;
@@ -80,6 +92,11 @@ struct FeatureBins {
   }
   std::string InfoString() const {
     if (trivial) return "none";
+    if (categorical) {
+      std::string r;
+      for (size_t i = 0; i < bin_to_cat.size(); ++i) r += (i ? ":" : "") + std::to_string(bin_to_cat[i]);
+      return r;
+    }
     char buf[96];
     snprintf(buf, sizeof(buf), "[%.17g:%.17g]", min_val, max_val);
     return buf;
@@ -174,6 +191,69 @@ inline std::vector<double> ZeroAsOneBin(const Distinct& d, int max_bin, int tota
 }
 
 }  // namespace binfind
+
+// Categorical feature: integer categories ranked by sample count; bin 0 is the catch-all (NaN / negative / rare / unseen),
+// categories are kept until 99 % of the non-missing mass is covered and at least min(#distinct, max_bin) bins exist
+// ([UPSTREAM] BinMapper::FindBin, CategoricalBin branch).
+inline FeatureBins FindCategoricalBins(std::vector<double>* nonzero, int total_sample, int max_bin, int min_data_in_bin, int filter_cnt,
+                                       bool pre_filter) {
+  FeatureBins fb;
+  fb.categorical = true;
+  std::vector<double>& v = *nonzero;
+  int n_nan = 0;
+  std::map<int, int> count_of;     // category -> samples (ascending by category)
+  for (double x : v) {
+    if (std::isnan(x)) { ++n_nan; continue; }
+    const int c = static_cast<int>(x);
+    if (c < 0) ++n_nan; else ++count_of[c];
+  }
+  const int n_zero = total_sample - static_cast<int>(v.size());
+  if (n_zero > 0) count_of[0] += n_zero;            // the implied zeros are category 0
+  struct CC { int cat, cnt; };
+  std::vector<CC> ranked;
+  for (auto& kv : count_of) ranked.push_back({kv.first, kv.second});
+  std::stable_sort(ranked.begin(), ranked.end(), [](const CC& a, const CC& b) { return a.cnt > b.cnt; });
+  fb.num_bin = 1;
+  fb.bin_to_cat.assign(1, -1);
+  std::vector<int> in_bin(1, 0);
+  const int rest = total_sample - n_nan;
+  if (rest > 0) {
+    const int cut = static_cast<int>(rest * 0.99f + 0.5);
+    int distinct = static_cast<int>(ranked.size()) + (n_nan > 0 ? 1 : 0);
+    const int want_bins = std::min(distinct, max_bin);
+    int used = 0;
+    size_t k = 0;
+    while (k < ranked.size() && (used < cut || fb.num_bin < want_bins)) {
+      if (ranked[k].cnt < min_data_in_bin && k > 1) break;
+      fb.bin_to_cat.push_back(ranked[k].cat);
+      in_bin.push_back(ranked[k].cnt);
+      used += ranked[k].cnt;
+      ++fb.num_bin; ++k;
+    }
+    fb.missing_type = (k == ranked.size() && n_nan == 0) ? MISSING_NONE : MISSING_NAN;
+    in_bin[0] = total_sample - used;
+  }
+  std::vector<std::pair<int, int>> byc;
+  for (int b = 1; b < fb.num_bin; ++b) byc.emplace_back(fb.bin_to_cat[b], b);
+  std::sort(byc.begin(), byc.end());
+  for (auto& p : byc) { fb.sorted_cats.push_back(p.first); fb.sorted_bins.push_back(p.second); }
+  fb.min_val = byc.empty() ? 0 : byc.front().first;
+  fb.max_val = byc.empty() ? 0 : byc.back().first;
+  fb.trivial = fb.num_bin <= 1;
+  if (!fb.trivial && pre_filter && in_bin.size() <= 2) {
+    bool ok = false;
+    for (size_t b = 0; b + 1 < in_bin.size(); ++b) ok |= in_bin[b] >= filter_cnt && total_sample - in_bin[b] >= filter_cnt;
+    if (!ok) fb.trivial = true;
+  }
+  if (!fb.trivial) {
+    fb.default_bin = fb.ValueToBin(0.0);
+    fb.most_freq_bin = static_cast<uint32_t>(std::max_element(in_bin.begin(), in_bin.end()) - in_bin.begin());
+    double rate = static_cast<double>(in_bin[fb.most_freq_bin]) / total_sample;
+    if (fb.most_freq_bin != fb.default_bin && rate < kSparseThr) fb.most_freq_bin = fb.default_bin;
+    fb.sparse_rate = static_cast<double>(in_bin[fb.most_freq_bin]) / total_sample;
+  }
+  return fb;
+}
 
 // nonzero: sampled values with |v| > 1e-35 or NaN (consumed); total_sample: rows sampled (zeros implied)
 inline FeatureBins FindFeatureBins(std::vector<double>* nonzero, int total_sample, int max_bin, int min_data_in_bin,

@@ -199,18 +199,29 @@ static bool IsDevicePointer(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-constexpr int kMapperRecord = 8 + 256;
+constexpr int kMapperRecord = 10 + 256;
 static void PackMapper(const FeatureBins& fb, double* r) {
   r[0] = fb.num_bin; r[1] = fb.missing_type; r[2] = fb.trivial; r[3] = fb.default_bin; r[4] = fb.most_freq_bin;
-  r[5] = fb.sparse_rate; r[6] = fb.min_val; r[7] = fb.max_val;
-  for (int i = 0; i < 256; ++i) r[8 + i] = i < static_cast<int>(fb.upper.size()) ? fb.upper[i] : 0.0;
+  r[5] = fb.sparse_rate; r[6] = fb.min_val; r[7] = fb.max_val; r[8] = fb.categorical; r[9] = 0;
+  for (int i = 0; i < 256; ++i) {
+    if (fb.categorical) r[10 + i] = i < static_cast<int>(fb.bin_to_cat.size()) ? fb.bin_to_cat[i] : 0.0;
+    else r[10 + i] = i < static_cast<int>(fb.upper.size()) ? fb.upper[i] : 0.0;
+  }
 }
 static FeatureBins UnpackMapper(const double* r) {
   FeatureBins fb;
   fb.num_bin = static_cast<int>(r[0]); fb.missing_type = static_cast<int>(r[1]); fb.trivial = r[2] != 0;
   fb.default_bin = static_cast<uint32_t>(r[3]); fb.most_freq_bin = static_cast<uint32_t>(r[4]);
-  fb.sparse_rate = r[5]; fb.min_val = r[6]; fb.max_val = r[7];
-  fb.upper.assign(r + 8, r + 8 + fb.num_bin);
+  fb.sparse_rate = r[5]; fb.min_val = r[6]; fb.max_val = r[7]; fb.categorical = r[8] != 0;
+  if (fb.categorical) {
+    for (int b = 0; b < fb.num_bin; ++b) fb.bin_to_cat.push_back(static_cast<int>(r[10 + b]));
+    std::vector<std::pair<int, int>> byc;
+    for (int b = 1; b < fb.num_bin; ++b) byc.emplace_back(fb.bin_to_cat[b], b);
+    std::sort(byc.begin(), byc.end());
+    for (auto& p : byc) { fb.sorted_cats.push_back(p.first); fb.sorted_bins.push_back(p.second); }
+  } else {
+    fb.upper.assign(r + 10, r + 10 + fb.num_bin);
+  }
   return fb;
 }
 
@@ -218,7 +229,6 @@ void Dataset::FindBins(const void* data, bool on_device, int data_type, int is_r
   const int n = num_data, F = num_total_features;
   if (cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
   if (cfg.max_bin < 2) Fatal("max_bin should be >= 2");
-  if (!cfg.categorical_feature.empty()) Fatal("categorical_feature is not supported by this build yet (numerical features only)");
   if (cfg.zero_as_missing) Fatal("zero_as_missing=true is not supported by this build");
   LcgRandom rnd(cfg.data_random_seed);
   int sample_cnt = n < cfg.bin_construct_sample_cnt ? n : cfg.bin_construct_sample_cnt;
@@ -277,9 +287,15 @@ void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sam
   mappers.assign(F, FeatureBins());
 #pragma omp parallel for schedule(dynamic)
   for (int f = f0; f < f1; ++f) {
-    mappers[f] = FindFeatureBins(&nz[f], sample_cnt, cfg.max_bin, cfg.min_data_in_bin, filter_cnt, cfg.feature_pre_filter, cfg.use_missing,
-                                 cfg.zero_as_missing);
+    const bool is_cat = std::find(cfg.categorical_feature.begin(), cfg.categorical_feature.end(), f) != cfg.categorical_feature.end();
+    if (is_cat) mappers[f] = FindCategoricalBins(&nz[f], sample_cnt, cfg.max_bin, cfg.min_data_in_bin, filter_cnt, cfg.feature_pre_filter);
+    else mappers[f] = FindFeatureBins(&nz[f], sample_cnt, cfg.max_bin, cfg.min_data_in_bin, filter_cnt, cfg.feature_pre_filter, cfg.use_missing,
+                                      cfg.zero_as_missing);
   }
+  for (int f = f0; f < f1; ++f)
+    if (mappers[f].num_bin > 256)
+      Fatal("categorical feature " + std::to_string(f) + " needs " + std::to_string(mappers[f].num_bin) +
+            " bins to cover 99% of its mass; this build stores bins as uint8 (<= 256 bins per feature)");
   if (world > 1) {   // C5: all-gather the serialized mappers
     std::vector<double> send(static_cast<size_t>(step) * kMapperRecord, 0.0), recv(static_cast<size_t>(world) * step * kMapperRecord);
     for (int f = f0; f < f1; ++f) PackMapper(mappers[f], &send[static_cast<size_t>(f - f0) * kMapperRecord]);
@@ -305,14 +321,26 @@ void Dataset::UploadMeta() {
   nf_pad = num_tiles * 32;
   meta_host.assign(nf_pad, FeatMeta{1, 0, 0, 0, 0, 0, 0, 0});
   std::vector<double> ubh(static_cast<size_t>(nf_pad) * 256, 0.0);
+  std::vector<uint8_t> cbh(static_cast<size_t>(nf_pad) * 256, 0);
+  has_categorical = false;
   for (int u = 0; u < nf; ++u) {
     const FeatureBins& fb = mappers[used[u]];
-    meta_host[u] = FeatMeta{fb.num_bin, fb.missing_type, static_cast<int>(fb.default_bin), fb.most_freq_bin == 0 ? 1 : 0, used[u], 0, 0, 0};
-    for (int b = 0; b < fb.num_bin; ++b) ubh[static_cast<size_t>(u) * 256 + b] = fb.upper[b];
+    meta_host[u] = FeatMeta{fb.num_bin, fb.missing_type, static_cast<int>(fb.default_bin), fb.most_freq_bin == 0 ? 1 : 0, used[u],
+                            fb.categorical ? 1 : 0, static_cast<int>(fb.sorted_cats.size()), 0};
+    if (fb.categorical) {
+      has_categorical = true;
+      for (size_t i = 0; i < fb.sorted_cats.size(); ++i) {
+        ubh[static_cast<size_t>(u) * 256 + i] = fb.sorted_cats[i];
+        cbh[static_cast<size_t>(u) * 256 + i] = static_cast<uint8_t>(fb.sorted_bins[i]);
+      }
+    } else {
+      for (int b = 0; b < fb.num_bin; ++b) ubh[static_cast<size_t>(u) * 256 + b] = fb.upper[b];
+    }
   }
-  meta.Alloc(nf_pad); ub.Alloc(ubh.size());
+  meta.Alloc(nf_pad); ub.Alloc(ubh.size()); catbin.Alloc(cbh.size());
   meta.Upload(meta_host.data(), nf_pad, stream);
   ub.Upload(ubh.data(), ubh.size(), stream);
+  catbin.Upload(cbh.data(), cbh.size(), stream);
   B200_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -322,7 +350,7 @@ static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long 
   B200_CUDA(cudaFuncSetAttribute(k_bin_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   dim3 grid(static_cast<unsigned>(std::min<long long>((nrow + 7) / 8, 148 * 8)), d.num_tiles);
   if (grid.x == 0) grid.x = 1;
-  k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.nf, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
+  k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.catbin.p, d.nf, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -382,7 +410,6 @@ Dataset* Dataset::CreateFromSampledColumn(double** sample_data, int** sample_ind
   d->num_data = num_total_row; d->num_total_features = ncol;
   d->cfg.Parse(params);
   if (d->cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
-  if (!d->cfg.categorical_feature.empty()) Fatal("categorical_feature is not supported by this build yet (numerical features only)");
   std::vector<std::vector<double>> nz(ncol);
   for (int f = 0; f < ncol; ++f) nz[f].assign(sample_data[f], sample_data[f] + num_per_col[f]);
   d->FindBinsFromColumns(&nz, num_sample_row);
@@ -564,6 +591,7 @@ void Dataset::SetFeatureNames(const char** names, int n) {
 
 // =============================================================================== booster
 static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
+constexpr int kScanSmem = 8 * (768 + 32) * 8;     // k_scan: per-warp scratch of the categorical split search
 
 Booster::Booster(const std::string& model_text) {
   std::unique_ptr<HostModel> m = HostModel::FromString(model_text);
@@ -632,11 +660,18 @@ void Booster::InitTraining() {
   B200_CUDA(cudaEventCreate(&ev_a_)); B200_CUDA(cudaEventCreate(&ev_b_));
   B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
   B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+  B200_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
 
   sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step;
   sp_.min_gain_to_split = cfg.min_gain_to_split; sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf;
   sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth; sp_.num_leaves = L; sp_.parallel = parallel_ ? 1 : 0;
   sp_.nf = train->nf; sp_.nf_pad = train->nf_pad; sp_.num_tiles = train->num_tiles; sp_.pad = 0;
+  {   // categorical split search parameters: native defaults unless given
+    auto gd = [&](const char* k, double d) { auto it = cfg.raw.find(k); return (it != cfg.raw.end() && !it->second.empty()) ? std::atof(it->second.c_str()) : d; };
+    sp_.cat_l2 = gd("cat_l2", 10.0); sp_.cat_smooth = gd("cat_smooth", 10.0);
+    sp_.max_cat_threshold = static_cast<int>(gd("max_cat_threshold", 32)); sp_.max_cat_to_onehot = static_cast<int>(gd("max_cat_to_onehot", 4));
+    sp_.min_data_per_group = static_cast<int>(gd("min_data_per_group", 100)); sp_.pad3 = 0;
+  }
 
   score_.Alloc(static_cast<size_t>(K) * n); score_.Zero(stream_);
   grad_.Alloc(static_cast<size_t>(K) * n); hess_.Alloc(static_cast<size_t>(K) * n);
@@ -654,7 +689,7 @@ void Booster::InitTraining() {
     auto take = [&](size_t bytes) { size_t o = off; off += Align16(bytes); return o; };
     size_t o_lc = take(4 * (L - 1)), o_rc = take(4 * (L - 1)), o_sf = take(4 * (L - 1)), o_tb = take(4 * (L - 1)), o_dt = take(4 * (L - 1));
     size_t o_sg = take(4 * (L - 1)), o_lv = take(8 * L), o_lw = take(8 * L), o_lcn = take(4 * L), o_iv = take(8 * (L - 1)), o_iw = take(8 * (L - 1));
-    size_t o_ic = take(4 * (L - 1)), o_lp = take(4 * L), o_ld = take(4 * L), o_nl = take(16);
+    size_t o_ic = take(4 * (L - 1)), o_lp = take(4 * L), o_ld = take(4 * L), o_nl = take(16), o_cb = take(32 * (L - 1));
     tree_blob_bytes_ = off;
     tree_blob_.Alloc(off);
     unsigned char* b = tree_blob_.p;
@@ -666,6 +701,7 @@ void Booster::InitTraining() {
     tree_dev_.internal_weight = reinterpret_cast<double*>(b + o_iw); tree_dev_.internal_count = reinterpret_cast<int*>(b + o_ic);
     tree_dev_.leaf_parent = reinterpret_cast<int*>(b + o_lp); tree_dev_.leaf_depth = reinterpret_cast<int*>(b + o_ld);
     tree_dev_.num_leaves = reinterpret_cast<int*>(b + o_nl);
+    tree_dev_.cat_bits = reinterpret_cast<unsigned*>(b + o_cb);
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&tree_host_), off));
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctrl_host_), sizeof(TreeCtrl)));
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&leaves_host_), sizeof(LeafState) * L));
@@ -745,7 +781,7 @@ void Booster::InitTraining() {
     if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
     B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
   }
-  if (parallel_) SetupPeerReduce();
+  if (parallel_ && !train->has_categorical) SetupPeerReduce();
   // ColSampler: one draw at init, then one per tree ([UPSTREAM] ColSampler::SetTrainingData / ResetByTree)
   col_rand_ = LcgRandom(cfg.feature_fraction_seed);
   feature_used_host_.assign(train->nf_pad, 0);
@@ -943,7 +979,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
     } else {
       if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2 (fallback)
-      k_scan<<<sgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+      k_scan<<<sgrid, 256, kScanSmem, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
       k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
     }
     k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
@@ -990,13 +1026,21 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     const double* iw = reinterpret_cast<const double*>(at(tree_dev_.internal_weight));
     const int* ic = reinterpret_cast<const int*>(at(tree_dev_.internal_count));
     const int* ld = reinterpret_cast<const int*>(at(tree_dev_.leaf_depth));
+    const unsigned* cb = reinterpret_cast<const unsigned*>(at(tree_dev_.cat_bits));
     for (int i = 0; i < nl - 1; ++i) {
       out->left_child[i] = lc[i]; out->right_child[i] = rc[i]; out->split_feature_inner[i] = sf[i];
       out->split_feature[i] = d.used[sf[i]]; out->threshold_in_bin[i] = static_cast<uint32_t>(tb[i]);
-      double thr = d.mappers[d.used[sf[i]]].upper[tb[i]];
-      if (std::isnan(thr)) thr = 0.0; else if (thr >= 1e300) thr = 1e300; else if (thr <= -1e300) thr = -1e300;
-      out->threshold[i] = thr;
       out->decision_type[i] = static_cast<int8_t>(dt[i]); out->split_gain[i] = sg[i];
+      const FeatureBins& fbm = d.mappers[d.used[sf[i]]];
+      if (dt[i] & 1) {          // categorical node: bins of the inner bitset -> category values ([UPSTREAM] RealThreshold per bin)
+        std::vector<int> cats;
+        for (int b = 0; b < fbm.num_bin; ++b) if ((cb[i * 8 + (b >> 5)] >> (b & 31)) & 1u) cats.push_back(fbm.bin_to_cat[b]);
+        out->AddCategoricalNode(i, cats);
+      } else {
+        double thr = fbm.upper[tb[i]];
+        if (std::isnan(thr)) thr = 0.0; else if (thr >= 1e300) thr = 1e300; else if (thr <= -1e300) thr = -1e300;
+        out->threshold[i] = thr;
+      }
       out->internal_value[i] = iv[i]; out->internal_weight[i] = iw[i]; out->internal_count[i] = ic[i];
     }
     for (int i = 0; i < nl; ++i) { out->leaf_value[i] = lv[i]; out->leaf_weight[i] = lw[i]; out->leaf_count[i] = lcn[i]; out->leaf_depth[i] = ld[i]; }
@@ -1312,7 +1356,8 @@ void Booster::UploadForest() {
   forest_.reset(new ForestBufs());
   ForestBufs& f = *forest_;
   const size_t T = model.trees.size();
-  std::vector<int> toff(T + 1, 0), loff(T + 1, 0), nl(T), sf, dt, lc, rc;
+  std::vector<int> toff(T + 1, 0), loff(T + 1, 0), nl(T), sf, dt, lc, rc, cbeg, clen;
+  std::vector<unsigned> cwords;
   std::vector<double> thr, lv;
   for (size_t t = 0; t < T; ++t) {
     const HostTree& tr = *model.trees[t];
@@ -1322,6 +1367,11 @@ void Booster::UploadForest() {
     for (int i = 0; i < tr.num_leaves - 1; ++i) {
       sf.push_back(tr.split_feature[i]); dt.push_back(tr.decision_type[i]); lc.push_back(tr.left_child[i]); rc.push_back(tr.right_child[i]);
       thr.push_back(tr.threshold[i]);
+      if (tr.decision_type[i] & 1) {
+        const int ci = static_cast<int>(tr.threshold[i]);
+        cbeg.push_back(static_cast<int>(cwords.size())); clen.push_back(tr.cat_boundaries[ci + 1] - tr.cat_boundaries[ci]);
+        for (int w = tr.cat_boundaries[ci]; w < tr.cat_boundaries[ci + 1]; ++w) cwords.push_back(tr.cat_threshold[w]);
+      } else { cbeg.push_back(0); clen.push_back(0); }
     }
     for (int i = 0; i < tr.num_leaves; ++i) lv.push_back(tr.leaf_value[i]);
   }
@@ -1329,7 +1379,9 @@ void Booster::UploadForest() {
   auto up_i = [&](DevBuf<int>& d, std::vector<int>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
   auto up_d = [&](DevBuf<double>& d, std::vector<double>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
   up_i(f.tree_offset, toff); up_i(f.leaf_offset, loff); up_i(f.num_leaves, nl); up_i(f.split_feature, sf); up_i(f.decision_type, dt);
-  up_i(f.left_child, lc); up_i(f.right_child, rc); up_d(f.threshold, thr); up_d(f.leaf_value, lv);
+  up_i(f.left_child, lc); up_i(f.right_child, rc); up_d(f.threshold, thr); up_d(f.leaf_value, lv); up_i(f.cat_begin, cbeg); up_i(f.cat_len, clen);
+  f.cat_words.Alloc(std::max<size_t>(cwords.size(), 1));
+  if (!cwords.empty()) f.cat_words.Upload(cwords.data(), cwords.size(), stream_);
   B200_CUDA(cudaStreamSynchronize(stream_));
   f.trees = T;
 }
@@ -1342,7 +1394,8 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
   if (ncol < model.max_feature_idx + 1) Fatal("PredictBatch: the matrix has fewer columns than the model has features");
   UploadForest();
   const ForestBufs& fb = *forest_;
-  ForestDev f{fb.tree_offset.p, fb.leaf_offset.p, fb.num_leaves.p, fb.split_feature.p, fb.threshold.p, fb.decision_type.p, fb.left_child.p, fb.right_child.p, fb.leaf_value.p};
+  ForestDev f{fb.tree_offset.p, fb.leaf_offset.p, fb.num_leaves.p, fb.split_feature.p, fb.threshold.p, fb.decision_type.p, fb.left_child.p, fb.right_child.p, fb.leaf_value.p,
+              fb.cat_begin.p, fb.cat_len.p, fb.cat_words.p};
   int t0, t1;
   model.IterRange(start_iteration, num_iteration, &t0, &t1);
   const int Kc = model.num_tree_per_iteration;

@@ -97,7 +97,9 @@ class Dataset {
   size_t rows_stride = 0;
   DevBuf<uint8_t> bins;                      // [num_tiles][rows_stride][32]
   DevBuf<FeatMeta> meta;
-  DevBuf<double> ub;                         // [nf][256]
+  DevBuf<double> ub;                         // [nf][256] bin upper bounds (categorical: sorted category values)
+  DevBuf<uint8_t> catbin;                    // [nf][256] categorical: bin of the i-th sorted category
+  bool has_categorical = false;
   std::vector<float> label, weight;
   std::vector<double> init_score;
   std::vector<int32_t> query_boundaries, group_sizes;
@@ -218,7 +220,7 @@ class Booster {
   unsigned epoch_ = 0;
   void SetupPeerReduce();
   // flattened forest for PredictBatch
-  struct ForestBufs { DevBuf<int> tree_offset, leaf_offset, num_leaves, split_feature, decision_type, left_child, right_child; DevBuf<double> threshold, leaf_value; size_t trees = 0; };
+  struct ForestBufs { DevBuf<int> tree_offset, leaf_offset, num_leaves, split_feature, decision_type, left_child, right_child, cat_begin, cat_len; DevBuf<double> threshold, leaf_value; DevBuf<unsigned> cat_words; size_t trees = 0; };
   std::unique_ptr<ForestBufs> forest_;
   void UploadForest();
   std::vector<ValidSet*> valids_;

@@ -17,26 +17,34 @@ struct FeatMeta {          // per inner (used) feature
   int default_bin;
   int offset;              // 1 iff most_freq_bin == 0  ([UPSTREAM] storage convention, affects NaN forward scan)
   int real_index;
-  int pad0, pad1, pad2;
+  int is_categorical;      // bins are category ranks; splits are bin bitsets
+  int num_sorted_cats;     // categorical: entries of the sorted category table (ub row = categories, catbin row = their bins)
+  int pad2;
 };
 
 struct SplitParams {
   double l1, l2, max_delta_step, min_gain_to_split, min_sum_hessian;
   int min_data_in_leaf, max_depth, num_leaves, parallel;
   int nf, nf_pad, num_tiles, pad;
+  double cat_l2, cat_smooth;                                   // categorical split search ([UPSTREAM] defaults 10, 10)
+  int max_cat_threshold, max_cat_to_onehot, min_data_per_group, pad3;   // 32, 4, 100
 };
 
 struct SplitCand {         // best threshold of one (leaf, feature)
   double gain;             // best_gain - min_gain_shift, or -inf
   double left_g, left_h;   // best_sum_left_gradient / _hessian (hessian still carries +kEpsilon)
   int threshold, left_count, default_left, feature;   // feature = inner index
+  double l2_extra;         // cat_l2 for a many-vs-many categorical split (leaf outputs use lambda_l2 + l2_extra)
+  unsigned cat_bits[8];    // categorical: bins that go LEFT
+  int is_cat, pad;
 };
 
 struct LeafBest {
   double gain;
   double left_g, left_h, right_g, right_h;   // sums as stored in SplitInfo (epsilon removed)
   double left_out, right_out;
-  int feature, threshold, default_left, left_count, right_count, pad;
+  int feature, threshold, default_left, left_count, right_count, is_cat;
+  unsigned cat_bits[8];
 };
 
 struct LeafState {
@@ -49,7 +57,8 @@ struct LeafState {
 struct TreeCtrl {
   int num_leaves, left_leaf, right_leaf, smaller, larger, go, finished, split_leaf;
   int split_feature, split_threshold, split_default_left, split_missing_type, split_num_bin, new_leaf, pending, pad;
-  int part_begin, part_count, part_buf, part_identity, part_left_total, smaller_rows, round, pad2;
+  int part_begin, part_count, part_buf, part_identity, part_left_total, smaller_rows, round, split_is_cat;
+  unsigned split_cat_bits[8];
   HistWork hist_work;
   unsigned absmax_bits[2];     // max|g|, max|h| as float bits (non-negative floats order like uints)
   int exp_g, exp_h;            // fixed-point exponents: q = rint(x * 2^exp)
@@ -62,6 +71,7 @@ struct TreeDev {               // SoA tree under construction (sizes: num_leaves
   int* left_child; int* right_child; int* split_feature_inner; int* threshold_bin; int* decision_type;
   float* split_gain; double* leaf_value; double* leaf_weight; int* leaf_count; double* internal_value;
   double* internal_weight; int* internal_count; int* leaf_parent; int* leaf_depth; int* num_leaves;
+  unsigned* cat_bits;          // [num_leaves-1][8] inner (bin) bitset of categorical nodes
 };
 
 // ---------------------------------------------------------------- helpers
@@ -91,7 +101,8 @@ __device__ __forceinline__ double d_leaf_gain(double g, double h, const SplitPar
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, long long ld, const FeatMeta* __restrict__ meta,
-           const double* __restrict__ ub, int nf, uint8_t* __restrict__ bins, long long rows_stride, long long row_offset) {
+           const double* __restrict__ ub, const uint8_t* __restrict__ catbin, int nf, uint8_t* __restrict__ bins, long long rows_stride,
+           long long row_offset) {
   extern __shared__ double s_ub[];   // [256 bins][32 lanes]: lane l always hits bank pair 2l -> no conflicts beyond the 64-bit 2-phase
   const int tile = blockIdx.y;
   for (int e = threadIdx.x; e < 32 * 256; e += blockDim.x) {
@@ -102,23 +113,34 @@ k_bin_rows(const T* __restrict__ X, long long nrow, int ncol, int row_major, lon
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u = tile * 32 + lane;
   FeatMeta m;
-  m.num_bin = 1; m.missing_type = 0; m.real_index = 0;
+  m.num_bin = 1; m.missing_type = 0; m.real_index = 0; m.is_categorical = 0; m.num_sorted_cats = 0;
   if (u < nf) m = meta[u];
   const double* myub = s_ub + lane;
   for (long long r = blockIdx.x * 8LL + warp; r < nrow; r += gridDim.x * 8LL) {
     unsigned bin = 0;
     if (u < nf) {
       double v = row_major ? static_cast<double>(X[r * ld + m.real_index]) : static_cast<double>(X[static_cast<long long>(m.real_index) * ld + r]);
-      if (isnan(v)) {
-        if (m.missing_type == 2) bin = m.num_bin - 1; else v = 0.0;
-      }
-      if (!isnan(v)) {
-        int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
-        while (lo < hi) {
-          int mid = (hi + lo - 1) / 2;
-          if (v <= myub[mid * 32]) hi = mid; else lo = mid + 1;
+      if (m.is_categorical) {     // category -> bin: binary search in the sorted category table; NaN / negative / unseen -> bin 0
+        if (!isnan(v)) {
+          const int iv = static_cast<int>(v);
+          if (iv >= 0) {
+            int lo = 0, hi = m.num_sorted_cats;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (static_cast<int>(myub[mid * 32]) < iv) lo = mid + 1; else hi = mid; }
+            if (lo < m.num_sorted_cats && static_cast<int>(myub[lo * 32]) == iv) bin = catbin[static_cast<size_t>(u) * 256 + lo];
+          }
         }
-        bin = lo;
+      } else {
+        if (isnan(v)) {
+          if (m.missing_type == 2) bin = m.num_bin - 1; else v = 0.0;
+        }
+        if (!isnan(v)) {
+          int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
+          while (lo < hi) {
+            int mid = (hi + lo - 1) / 2;
+            if (v <= myub[mid * 32]) hi = mid; else lo = mid + 1;
+          }
+          bin = lo;
+        }
       }
     }
     bins[(static_cast<size_t>(tile) * rows_stride + row_offset + r) * 32 + lane] = static_cast<uint8_t>(bin);
@@ -369,8 +391,14 @@ k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
       tree.leaf_weight[nl] = b.right_h; tree.leaf_count[nl] = b.right_count;
       tree.leaf_depth[nl] = tree.leaf_depth[leaf] + 1; tree.leaf_depth[leaf] += 1;
       const FeatMeta fm = meta[b.feature];
-      tree.decision_type[node] = (b.default_left ? 2 : 0) | (fm.missing_type << 2);
-      tree.threshold_bin[node] = b.threshold;
+      if (b.is_cat) {
+        tree.decision_type[node] = 1 | (fm.missing_type << 2);
+        tree.threshold_bin[node] = 0;
+      } else {
+        tree.decision_type[node] = (b.default_left ? 2 : 0) | (fm.missing_type << 2);
+        tree.threshold_bin[node] = b.threshold;
+      }
+      for (int wd = 0; wd < 8; ++wd) tree.cat_bits[node * 8 + wd] = b.is_cat ? b.cat_bits[wd] : 0u;
       ctrl->num_leaves += 1; *tree.num_leaves = ctrl->num_leaves;
       // data partition bookkeeping: children live in the other index buffer
       const int dst_buf = L.identity ? 0 : (L.buf ^ 1);
@@ -543,6 +571,143 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
   }
 }
 
+// Categorical split search for one feature by one warp (FeatureHistogram::FindBestThresholdCategoricalInner [UPSTREAM]):
+// one-hot when num_bin <= max_cat_to_onehot; otherwise the bins holding >= cat_smooth rows are ranked by g/(h+cat_smooth)
+// (stable, ties by bin) and accumulated from both ends, at most max_cat_threshold bins, lambda_l2 += cat_l2.
+// ws = this warp's shared scratch: g[256], h[256], ctr[256] doubles + order[256] bytes.
+__device__ __forceinline__ void d_scan_feature_cat(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
+                                                   double inv_g, double inv_h, const SplitParams& p, uint8_t* flag, SplitCand* outp, double* ws) {
+  SplitCand& out = *outp;
+  double* sg = ws; double* sh = ws + 256; double* sc = ws + 512;
+  unsigned char* order = reinterpret_cast<unsigned char*>(ws + 768);
+  const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
+  const int num_data = L.global_count;
+  const double cnt_factor = num_data / sum_h;
+  SplitParams pshift = p;
+  if (!(p.max_delta_step > 0)) pshift.max_delta_step = 0;
+  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, pshift) + p.min_gain_to_split;
+  const bool onehot = m.num_bin <= p.max_cat_to_onehot;
+  bool any_valid = false;
+  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
+  int best_t = 0x7fffffff, best_lc = 0;
+  unsigned used_mask = 0;      // bit j: my bin j is "used" (enough rows)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = lane * 8 + j;
+    const double g = static_cast<double>(qg[j]) * inv_g, h = static_cast<double>(qh[j]) * inv_h;
+    sg[b] = g; sh[b] = h;
+    const int cnt = static_cast<int>(h * cnt_factor + 0.5);
+    const bool in_range = b >= 1 && b < m.num_bin;
+    if (onehot) {
+      if (in_range && !(cnt < p.min_data_in_leaf || h < p.min_sum_hessian)) {
+        const int other = num_data - cnt;
+        const double oh = sum_h - h - kEpsD;
+        if (other >= p.min_data_in_leaf && oh >= p.min_sum_hessian) {
+          const double gain = d_leaf_gain(sum_g - g, oh, p) + d_leaf_gain(g, h + kEpsD, p);
+          if (gain > min_gain_shift) {
+            any_valid = true;
+            if (gain > best_gain) { best_gain = gain; best_t = b; best_lg = g; best_lh = h + kEpsD; best_lc = cnt; }
+          }
+        }
+      }
+    } else {
+      const bool used = in_range && cnt >= p.cat_smooth;
+      if (used) used_mask |= 1u << j;
+      sc[b] = g / (h + p.cat_smooth);
+    }
+  }
+  __syncwarp();
+  if (onehot) {
+    for (int o = 16; o; o >>= 1) {        // first seen = smallest bin wins ties
+      const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, best_t, o), oc = __shfl_xor_sync(0xffffffffu, best_lc, o);
+      const double olg = __shfl_xor_sync(0xffffffffu, best_lg, o), olh = __shfl_xor_sync(0xffffffffu, best_lh, o);
+      if (og > best_gain || (og == best_gain && ot < best_t)) { best_gain = og; best_t = ot; best_lg = olg; best_lh = olh; best_lc = oc; }
+    }
+    any_valid = __any_sync(0xffffffffu, any_valid);
+    if (lane == 0) {
+      *flag = any_valid ? 1 : 0;
+      if (any_valid) {
+        out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = 0; out.left_count = best_lc;
+        out.default_left = 0; out.is_cat = 1; out.l2_extra = 0;
+        out.cat_bits[best_t >> 5] |= 1u << (best_t & 31);
+      }
+    }
+    return;
+  }
+  // ---- rank the used bins by ctr (stable): rank = #{used j : ctr_j < ctr_i  or (== and j < i)}
+  // every lane needs the global used set: 8 words via ballots of the per-bin flags
+  unsigned used_words[8];
+#pragma unroll
+  for (int wd = 0; wd < 8; ++wd) used_words[wd] = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // bin = lane*8 + j  -> word = lane>>2, bit = (lane&3)*8 + j
+    const unsigned bal = __ballot_sync(0xffffffffu, (used_mask >> j) & 1u);
+    for (int l = 0; l < 32; ++l) if ((bal >> l) & 1u) used_words[l >> 2] |= 1u << (((l & 3) << 3) + j);
+  }
+  int used_bin = 0;
+#pragma unroll
+  for (int wd = 0; wd < 8; ++wd) used_bin += __popc(used_words[wd]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (!((used_mask >> j) & 1u)) continue;
+    const int bi = lane * 8 + j;
+    const double ci = sc[bi];
+    int rank = 0;
+    for (int wd = 0; wd < 8; ++wd) {
+      unsigned wbits = used_words[wd];
+      while (wbits) {
+        const int bj = wd * 32 + __ffs(wbits) - 1;
+        wbits &= wbits - 1;
+        const double cj = sc[bj];
+        rank += (cj < ci) || (cj == ci && bj < bi);
+      }
+    }
+    order[rank] = static_cast<unsigned char>(bi);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    SplitParams pc = p;
+    pc.l2 += p.cat_l2;
+    const int max_num_cat = min(p.max_cat_threshold, (used_bin + 1) / 2);
+    int best_i = -1, best_dir = 1;
+    for (int d = 0; d < 2; ++d) {
+      const int dir = d == 0 ? 1 : -1;
+      int pos = d == 0 ? 0 : used_bin - 1;
+      int cnt_cur_group = 0, left_count = 0;
+      double slg = 0.0, slh = kEpsD;
+      for (int i = 0; i < used_bin && i < max_num_cat; ++i) {
+        const int t = order[pos];
+        pos += dir;
+        const double g = sg[t], h = sh[t];
+        const int cnt = static_cast<int>(h * cnt_factor + 0.5);
+        slg += g; slh += h; left_count += cnt; cnt_cur_group += cnt;
+        if (left_count < p.min_data_in_leaf || slh < p.min_sum_hessian) continue;
+        const int right_count = num_data - left_count;
+        if (right_count < p.min_data_in_leaf || right_count < p.min_data_per_group) break;
+        const double srh = sum_h - slh;
+        if (srh < p.min_sum_hessian) break;
+        if (cnt_cur_group < p.min_data_per_group) continue;
+        cnt_cur_group = 0;
+        const double gain = d_leaf_gain(slg, slh, pc) + d_leaf_gain(sum_g - slg, srh, pc);
+        if (gain <= min_gain_shift) continue;
+        any_valid = true;
+        if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_lc = left_count; best_i = i; best_dir = dir; }
+      }
+    }
+    *flag = any_valid ? 1 : 0;
+    if (any_valid) {
+      out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = 0; out.left_count = best_lc;
+      out.default_left = 0; out.is_cat = 1; out.l2_extra = p.cat_l2;
+      for (int i = 0; i <= best_i; ++i) {
+        const int t = best_dir == 1 ? order[i] : order[used_bin - 1 - i];
+        out.cat_bits[t >> 5] |= 1u << (t & 31);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta,
        const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
@@ -556,6 +721,8 @@ k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, 
   if (u >= p.nf) return;
   SplitCand out;
   out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+  out.l2_extra = 0; out.is_cat = 0; out.pad = 0;
+  for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
   uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
   if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
 
@@ -574,7 +741,12 @@ k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, 
     *reinterpret_cast<longlong2*>(dst + b * 2) = s;
     qg[j] = s.x; qh[j] = s.y;
   }
-  d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
+  if (meta[u].is_categorical) {
+    extern __shared__ double scan_ws[];      // 8 warps x (3*256 doubles + 256 bytes)
+    d_scan_feature_cat(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out, scan_ws + warp * (768 + 32));
+  } else {
+    d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
+  }
   if (lane == 0) {
     cands[which * p.nf_pad + u] = out;
   }
@@ -631,6 +803,8 @@ k_scan_dp(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leave
   if (u >= pt.feat1 || u >= p.nf) return;
   SplitCand out;
   out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+  out.l2_extra = 0; out.is_cat = 0; out.pad = 0;
+  for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
   uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
   if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
 
@@ -699,6 +873,8 @@ __device__ __forceinline__ void d_choose_leaf(TreeCtrl* ctrl, LeafState* leaves,
     ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
     ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
     ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
+    ctrl->split_is_cat = b.is_cat;
+    for (int wd = 0; wd < 8; ++wd) ctrl->split_cat_bits[wd] = b.cat_bits[wd];
     ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
     ctrl->part_left_total = 0;
   }
@@ -735,7 +911,8 @@ k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, con
         LeafState& L = leaves[leaf];
         LeafBest b;
         b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.pad = 0;
+        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
+        for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
         if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
           const SplitCand& c = cands[which * p.nf_pad + s_idx[0]];
           const double sum_h = L.sum_h + 2 * kEpsD;
@@ -743,8 +920,12 @@ k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, con
           b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
           b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
           b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
-          b.left_out = d_calc_output(c.left_g, c.left_h, p);
-          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, p);
+          SplitParams pc = p;
+          pc.l2 += c.l2_extra;
+          b.left_out = d_calc_output(c.left_g, c.left_h, pc);
+          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, pc);
+          b.is_cat = c.is_cat;
+          for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = c.cat_bits[wd];
         }
         L.best = b;
       }
@@ -824,7 +1005,8 @@ k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, 
       LeafState& L = leaves[leaf];
       LeafBest b;
       b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-      b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.pad = 0;
+      b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
+      for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
       if (best.feature >= 0 && best.gain > kNegInf) {
         const double sum_h = L.sum_h + 2 * kEpsD;
         b.gain = best.gain; b.feature = best.feature; b.threshold = best.threshold; b.default_left = best.default_left;
@@ -844,6 +1026,7 @@ k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, 
 // ---------------------------------------------------------------- K7 row partition (stable)
 constexpr int kPartChunk = 2048;     // rows per chunk = 256 threads x 8
 __device__ __forceinline__ bool d_goes_left(unsigned bin, const TreeCtrl* c) {
+  if (c->split_is_cat) return (c->split_cat_bits[bin >> 5] >> (bin & 31u)) & 1u;
   if (c->split_missing_type == 2 && bin == static_cast<unsigned>(c->split_num_bin - 1)) return c->split_default_left != 0;
   return bin <= static_cast<unsigned>(c->split_threshold);
 }
@@ -992,7 +1175,8 @@ k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t
       const unsigned bin = bins[(static_cast<size_t>(f >> 5) * rows_stride + i) * 32 + (f & 31)];
       const int dt = tree.decision_type[node];
       bool left;
-      if (((dt >> 2) & 3) == 2 && bin == static_cast<unsigned>(meta[f].num_bin - 1)) left = dt & 2;
+      if (dt & 1) left = (tree.cat_bits[node * 8 + (bin >> 5)] >> (bin & 31u)) & 1u;
+      else if (((dt >> 2) & 3) == 2 && bin == static_cast<unsigned>(meta[f].num_bin - 1)) left = dt & 2;
       else left = bin <= static_cast<unsigned>(tree.threshold_bin[node]);
       node = left ? tree.left_child[node] : tree.right_child[node];
     }
@@ -1015,6 +1199,9 @@ struct ForestDev {
   const int* left_child;
   const int* right_child;
   const double* leaf_value;
+  const int* cat_begin;          // per node: categorical nodes index their category bitset in cat_words
+  const int* cat_len;
+  const unsigned* cat_words;
 };
 template <typename T>
 __device__ __forceinline__ int d_tree_leaf(const ForestDev& f, int t, const T* __restrict__ row) {
@@ -1026,8 +1213,18 @@ __device__ __forceinline__ int d_tree_leaf(const ForestDev& f, int t, const T* _
     double fval = static_cast<double>(row[f.split_feature[g]]);
     const int dt = f.decision_type[g];
     const int mt = (dt >> 2) & 3;
-    if (isnan(fval) && mt != 2) fval = 0.0;
     bool left;
+    if (dt & 1) {                 // categorical decision
+      left = false;
+      if (!(isnan(fval) && mt == 2)) {
+        const int iv = isnan(fval) ? 0 : static_cast<int>(fval);
+        const int w = iv >> 5;
+        if (iv >= 0 && w < f.cat_len[g]) left = (f.cat_words[f.cat_begin[g] + w] >> (iv & 31)) & 1u;
+      }
+      node = left ? f.left_child[g] : f.right_child[g];
+      continue;
+    }
+    if (isnan(fval) && mt != 2) fval = 0.0;
     if ((mt == 1 && fabs(fval) <= 1e-35) || (mt == 2 && isnan(fval))) left = (dt & 2) != 0;
     else left = fval <= f.threshold[g];
     node = left ? f.left_child[g] : f.right_child[g];

@@ -32,6 +32,29 @@ struct HostTree {
   std::vector<double> threshold, leaf_value, leaf_weight, internal_value, internal_weight;
   std::vector<float> split_gain;
   std::vector<int8_t> decision_type;
+  // categorical splits ([UPSTREAM] Tree::cat_boundaries_ / cat_threshold_): node's threshold = index i, its bitset over
+  // CATEGORY VALUES is cat_threshold[cat_boundaries[i] .. cat_boundaries[i+1])
+  std::vector<int> cat_boundaries{0};
+  std::vector<uint32_t> cat_threshold;
+
+  static bool InBitset(const uint32_t* bits, int n, int pos) {
+    const int w = pos / 32;
+    if (pos < 0 || w >= n) return false;
+    return (bits[w] >> (pos % 32)) & 1u;
+  }
+  void AddCategoricalNode(int node, const std::vector<int>& categories) {
+    std::vector<uint32_t> bits;
+    for (int c : categories) {
+      const size_t w = static_cast<size_t>(c) / 32;
+      if (bits.size() < w + 1) bits.resize(w + 1, 0u);
+      bits[w] |= 1u << (c % 32);
+    }
+    threshold[node] = num_cat;
+    threshold_in_bin[node] = static_cast<uint32_t>(num_cat);
+    ++num_cat;
+    cat_boundaries.push_back(cat_boundaries.back() + static_cast<int>(bits.size()));
+    cat_threshold.insert(cat_threshold.end(), bits.begin(), bits.end());
+  }
 
   void Resize(int nl) {
     num_leaves = nl;
@@ -56,6 +79,16 @@ struct HostTree {
 
   inline int Decide(double fval, int node) const {
     int mt = (decision_type[node] >> 2) & 3;
+    if (decision_type[node] & 1) {       // [UPSTREAM] Tree::CategoricalDecision
+      if (std::isnan(fval)) {
+        if (mt == MISSING_NAN) return right_child[node];
+        fval = 0.0;
+      }
+      const int iv = static_cast<int>(fval);
+      if (iv < 0) return right_child[node];
+      const int ci = static_cast<int>(threshold[node]);
+      return InBitset(cat_threshold.data() + cat_boundaries[ci], cat_boundaries[ci + 1] - cat_boundaries[ci], iv) ? left_child[node] : right_child[node];
+    }
     if (std::isnan(fval) && mt != MISSING_NAN) fval = 0.0;
     if ((mt == MISSING_ZERO && std::fabs(fval) <= kZeroThr) || (mt == MISSING_NAN && std::isnan(fval)))
       return (decision_type[node] & 2) ? left_child[node] : right_child[node];
@@ -177,6 +210,10 @@ struct HostTree {
     s << "internal_value=" << Join(internal_value, nl - 1, "%g") << '\n';
     s << "internal_weight=" << Join(internal_weight, nl - 1, "%g") << '\n';
     s << "internal_count=" << Join(internal_count, nl - 1, "%lld") << '\n';
+    if (num_cat > 0) {
+      s << "cat_boundaries=" << Join(cat_boundaries, num_cat + 1, "%lld") << '\n';
+      s << "cat_threshold=" << Join(cat_threshold, static_cast<int>(cat_threshold.size()), "%lld") << '\n';
+    }
     s << "is_linear=0\n";
     char buf[64];
     snprintf(buf, sizeof(buf), "%g", shrinkage);
@@ -194,7 +231,6 @@ struct HostTree {
     t.Resize(nl);
     auto it = kv.find("num_cat");
     t.num_cat = it == kv.end() ? 0 : std::atoi(it->second.c_str());
-    if (t.num_cat > 0) throw std::runtime_error("categorical splits are not supported by this build");
     auto fill_d = [&](const char* k, std::vector<double>& v, int n, bool req) {
       auto f = kv.find(k);
       if (f == kv.end()) { if (req && n > 0) need(k); return; }
@@ -223,6 +259,12 @@ struct HostTree {
       fill_d("internal_weight", t.internal_weight, nl - 1, false);
       fill_i("internal_count", t.internal_count, nl - 1, false);
       t.split_feature_inner = t.split_feature;
+      if (t.num_cat > 0) {
+        t.cat_boundaries.assign(t.num_cat + 1, 0);
+        fill_i("cat_boundaries", t.cat_boundaries, t.num_cat + 1, true);
+        t.cat_threshold.assign(t.cat_boundaries.back(), 0u);
+        fill_i("cat_threshold", t.cat_threshold, t.cat_boundaries.back(), true);
+      }
       // recompute leaf depths
       std::vector<std::pair<int, int>> st{{0, 0}};
       while (!st.empty()) {

@@ -3,7 +3,7 @@
 Format: SURVEY.md Appendix B.3; writer = csrc/model.h (HostModel::ToString)."""
 import numpy as np
 
-INT_KEYS = ("split_feature", "decision_type", "left_child", "right_child", "leaf_count", "internal_count")
+INT_KEYS = ("split_feature", "decision_type", "left_child", "right_child", "leaf_count", "internal_count", "cat_boundaries", "cat_threshold")
 FLOAT_KEYS = ("split_gain", "threshold", "leaf_value", "leaf_weight", "internal_value", "internal_weight")
 
 
@@ -57,6 +57,10 @@ def compare_models(a, b, value_tol=1e-5, gain_tol=1e-5, check_counts=True):
             for k in ("split_feature", "decision_type", "left_child", "right_child"):
                 assert np.array_equal(ta[k], tb[k]), "tree %d: %s differs\n%s\n%s" % (ti, k, ta[k], tb[k])
             assert np.array_equal(ta["threshold"], tb["threshold"]), "tree %d: thresholds differ" % ti
+            assert ta.get("num_cat", 0) == tb.get("num_cat", 0), "tree %d: num_cat differs" % ti
+            if ta.get("num_cat", 0) > 0:
+                for k in ("cat_boundaries", "cat_threshold"):
+                    assert np.array_equal(ta[k], tb[k]), "tree %d: %s differs\n%s\n%s" % (ti, k, ta[k], tb[k])
             if check_counts:
                 for k in ("leaf_count", "internal_count"):
                     assert np.array_equal(ta[k], tb[k]), "tree %d: %s differs\n%s\n%s" % (ti, k, ta[k], tb[k])

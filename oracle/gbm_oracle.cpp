@@ -75,6 +75,8 @@ struct Config {
   double feature_fraction = 1.0;
   int feature_fraction_seed = 2;
   double alpha = 0.9, fair_c = 1.0, poisson_max_delta_step = 0.7, tweedie_variance_power = 1.5;
+  int max_cat_threshold = 32, max_cat_to_onehot = 4, min_data_per_group = 100;
+  double cat_l2 = 10.0, cat_smooth = 10.0;
   std::string tree_learner = "serial";
   int verbosity = 1;
   std::map<std::string, std::string> raw;
@@ -140,6 +142,8 @@ struct Config {
     getd("feature_fraction", feature_fraction); geti("verbosity", verbosity); geti("feature_fraction_seed", feature_fraction_seed);
     getd("alpha", alpha); getd("fair_c", fair_c); getd("poisson_max_delta_step", poisson_max_delta_step);
     getd("tweedie_variance_power", tweedie_variance_power);
+    geti("max_cat_threshold", max_cat_threshold); geti("max_cat_to_onehot", max_cat_to_onehot); geti("min_data_per_group", min_data_per_group);
+    getd("cat_l2", cat_l2); getd("cat_smooth", cat_smooth);
     auto split_list = [&](const char* k, auto& out, auto conv) {
       auto it = raw.find(k);
       if (it == raw.end() || it->second.empty()) return;
@@ -273,12 +277,22 @@ struct BinMapper {
   int num_bin = 1;
   int missing_type = kMissNone;
   bool is_trivial = true;
+  bool is_categorical = false;
   double sparse_rate = 1.0;
   std::vector<double> upper;
+  std::vector<int> bin_2_cat;            // categorical: bin -> category value (bin 0 = -1: NaN / rare / unseen)
+  std::map<int, int> cat_2_bin;
   double min_val = 0, max_val = 0;
   uint32_t default_bin = 0, most_freq_bin = 0;
 
   uint32_t ValueToBin(double value) const {
+    if (is_categorical) {
+      if (std::isnan(value)) return 0;
+      int iv = static_cast<int>(value);
+      if (iv < 0) return 0;
+      auto it = cat_2_bin.find(iv);
+      return it == cat_2_bin.end() ? 0 : it->second;
+    }
     if (std::isnan(value)) {
       if (missing_type == kMissNaN) return num_bin - 1;
       value = 0.0;
@@ -294,7 +308,8 @@ struct BinMapper {
 
   // values: the non-zero (|v|>1e-35 or NaN) sampled values of one feature (modified in place)
   void FindBin(double* values, int num_sample_values, size_t total_sample_cnt, int max_bin, int min_data_in_bin,
-               int min_split_data, bool pre_filter, bool use_missing, bool zero_as_missing) {
+               int min_split_data, bool pre_filter, bool use_missing, bool zero_as_missing, bool categorical = false) {
+    is_categorical = categorical;
     int na_cnt = 0, tmp = 0;
     for (int i = 0; i < num_sample_values; ++i) if (!std::isnan(values[i])) values[tmp++] = values[i];
     if (!use_missing) missing_type = kMissNone;
@@ -324,6 +339,61 @@ struct BinMapper {
     max_val = dv.back();
     int nd = static_cast<int>(dv.size());
     std::vector<int> cnt_in_bin;
+    if (categorical) {
+      // [UPSTREAM BinMapper::FindBin, CategoricalBin branch] ints; negatives -> NaN; sorted by count; kept until 99 % of the mass
+      std::vector<int> dvi, cti;
+      for (int i = 0; i < nd; ++i) {
+        int val = static_cast<int>(dv[i]);
+        if (val < 0) na_cnt += counts[i];
+        else if (dvi.empty() || val != dvi.back()) { dvi.push_back(val); cti.push_back(counts[i]); }
+        else cti.back() += counts[i];
+      }
+      num_bin = 1;
+      bin_2_cat.assign(1, -1); cat_2_bin.clear(); cat_2_bin[-1] = 0;
+      cnt_in_bin.assign(1, 0);
+      int rest_cnt = static_cast<int>(total_sample_cnt - na_cnt);
+      if (rest_cnt > 0) {
+        std::vector<int> order(dvi.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cti[a] > cti[b]; });    // SortForPair(counts, values, 0, true)
+        int cut_cnt = RoundIntLocal((total_sample_cnt - na_cnt) * 0.99f);
+        int used_cnt = 0;
+        int distinct_cnt = static_cast<int>(dvi.size());
+        if (na_cnt > 0) ++distinct_cnt;
+        int mb = std::min(distinct_cnt, max_bin);
+        size_t cur = 0;
+        while (cur < order.size() && (used_cnt < cut_cnt || num_bin < mb)) {
+          int o = order[cur];
+          if (cti[o] < min_data_in_bin && cur > 1) break;
+          bin_2_cat.push_back(dvi[o]);
+          cat_2_bin[dvi[o]] = num_bin;
+          used_cnt += cti[o];
+          cnt_in_bin.push_back(cti[o]);
+          ++num_bin; ++cur;
+        }
+        missing_type = (cur == order.size() && na_cnt == 0) ? kMissNone : kMissNaN;
+        cnt_in_bin[0] = static_cast<int>(total_sample_cnt - used_cnt);
+      }
+      is_trivial = num_bin <= 1;
+      if (!is_trivial && pre_filter) {
+        bool need = true;
+        if (cnt_in_bin.size() <= 2) {
+          for (size_t i = 0; i + 1 < cnt_in_bin.size(); ++i) {
+            int sum_left = cnt_in_bin[i];
+            if (sum_left >= min_split_data && static_cast<int>(total_sample_cnt) - sum_left >= min_split_data) { need = false; break; }
+          }
+        } else need = false;
+        if (need) is_trivial = true;
+      }
+      if (!is_trivial) {
+        default_bin = ValueToBin(0);
+        most_freq_bin = static_cast<uint32_t>(std::max_element(cnt_in_bin.begin(), cnt_in_bin.end()) - cnt_in_bin.begin());
+        double max_sparse_rate = static_cast<double>(cnt_in_bin[most_freq_bin]) / total_sample_cnt;
+        if (most_freq_bin != default_bin && max_sparse_rate < kSparseThreshold) most_freq_bin = default_bin;
+        sparse_rate = static_cast<double>(cnt_in_bin[most_freq_bin]) / total_sample_cnt;
+      } else sparse_rate = 1.0;
+      return;
+    }
     if (missing_type == kMissZero) {
       upper = FindBinWithZeroAsOneBin(dv.data(), counts.data(), nd, max_bin, static_cast<int>(total_sample_cnt), min_data_in_bin);
       if (upper.size() == 2) missing_type = kMissNone;
@@ -362,8 +432,14 @@ struct BinMapper {
       sparse_rate = 1.0;
     }
   }
+  static int RoundIntLocal(double x) { return static_cast<int>(x + 0.5); }
   std::string info_string() const {
     if (is_trivial) return "none";
+    if (is_categorical) {
+      std::string r;
+      for (size_t i = 0; i < bin_2_cat.size(); ++i) r += (i ? ":" : "") + std::to_string(bin_2_cat[i]);
+      return r;
+    }
     char buf[96];
     snprintf(buf, sizeof(buf), "[%.17g:%.17g]", min_val, max_val);
     return buf;
@@ -416,8 +492,9 @@ struct Dataset {
           double v = Xr[static_cast<size_t>(i) * F + f];
           if (std::fabs(v) > kZeroThreshold || std::isnan(v)) vals.push_back(v);
         }
+        bool is_cat = std::find(cfg.categorical_feature.begin(), cfg.categorical_feature.end(), f) != cfg.categorical_feature.end();
         mappers[f].FindBin(vals.data(), static_cast<int>(vals.size()), sample_cnt, cfg.max_bin, cfg.min_data_in_bin,
-                           filter_cnt, cfg.feature_pre_filter, cfg.use_missing, cfg.zero_as_missing);
+                           filter_cnt, cfg.feature_pre_filter, cfg.use_missing, cfg.zero_as_missing, is_cat);
       }
       row_off += ln;
     }
@@ -734,6 +811,7 @@ struct SplitInfo {
   double gain = kMinScore;
   double left_sum_gradient = 0, left_sum_hessian = 0, right_sum_gradient = 0, right_sum_hessian = 0;
   bool default_left = true;
+  std::vector<uint32_t> cat_threshold;   // categorical split: bins that go LEFT
   bool better_than(const SplitInfo& o) const {     // operator>
     double lg = gain, og = o.gain;
     if (std::isnan(lg)) lg = kMinScore;
@@ -748,7 +826,8 @@ inline double Sign(double x) { return (x > 0.0) - (x < 0.0); }
 inline double ThresholdL1(double s, double l1) { double r = std::max(0.0, std::fabs(s) - l1); return Sign(s) * r; }
 inline int RoundInt(double x) { return static_cast<int>(x + 0.5); }
 
-struct SplitCfg { double l1, l2, max_delta_step, min_gain_to_split, min_sum_hessian; int min_data_in_leaf; };
+struct SplitCfg { double l1, l2, max_delta_step, min_gain_to_split, min_sum_hessian; int min_data_in_leaf;
+                  int max_cat_threshold = 32, max_cat_to_onehot = 4, min_data_per_group = 100; double cat_l2 = 10.0, cat_smooth = 10.0; };
 
 inline double CalcOutput(double g, double h, const SplitCfg& c) {
   double ret = (c.l1 > 0) ? -ThresholdL1(g, c.l1) / (h + c.l2) : -g / (h + c.l2);
@@ -877,6 +956,118 @@ static void FindBestThresholdNumerical(const double* hist, const ScanMeta& m, co
   }
 }
 
+// FeatureHistogram::FindBestThresholdCategoricalInner [UPSTREAM]: one-hot for <= max_cat_to_onehot bins, otherwise bins with
+// enough data sorted by g/(h+cat_smooth) and scanned from both ends (many-vs-many), lambda_l2 += cat_l2.
+static void FindBestThresholdCategorical(const double* hist, const ScanMeta& m, const SplitCfg& c0, double sum_gradient, double sum_hessian_in,
+                                         int num_data, SplitInfo* output, bool* is_splittable) {
+  output->default_left = false;
+  output->gain = kMinScore;
+  const double sum_hessian = sum_hessian_in + 2 * kEpsilon;
+  *is_splittable = false;
+  double best_gain = kMinScore, best_sum_left_gradient = 0, best_sum_left_hessian = 0;
+  int best_left_count = 0;
+  SplitCfg c = c0;
+  SplitCfg cshift = c0; cshift.max_delta_step = 0;
+  double gain_shift = (c0.max_delta_step > 0) ? LeafGainGivenOutput(sum_gradient, sum_hessian, c0, 0.0 /* parent_output unused w/o smoothing */)
+                                              : LeafGain(sum_gradient, sum_hessian, cshift);
+  if (c0.max_delta_step > 0) gain_shift = LeafGain(sum_gradient, sum_hessian, c0);
+  const double min_gain_shift = gain_shift + c0.min_gain_to_split;
+  auto GRAD = [&](int b) { return hist[b * 2]; };
+  auto HESS = [&](int b) { return hist[b * 2 + 1]; };
+  const bool use_onehot = m.num_bin <= c0.max_cat_to_onehot;
+  int best_threshold = -1, best_dir = 1;
+  const double cnt_factor = num_data / sum_hessian;
+  std::vector<int> sorted_idx;
+  int used_bin = -1;
+  if (use_onehot) {
+    for (int t = 1; t < m.num_bin; ++t) {
+      const double grad = GRAD(t), hess = HESS(t);
+      int cnt = RoundInt(hess * cnt_factor);
+      if (cnt < c.min_data_in_leaf || hess < c.min_sum_hessian) continue;
+      int other_count = num_data - cnt;
+      if (other_count < c.min_data_in_leaf) continue;
+      double sum_other_hessian = sum_hessian - hess - kEpsilon;
+      if (sum_other_hessian < c.min_sum_hessian) continue;
+      double sum_other_gradient = sum_gradient - grad;
+      double current_gain = LeafGain(sum_other_gradient, sum_other_hessian, c) + LeafGain(grad, hess + kEpsilon, c);
+      if (current_gain <= min_gain_shift) continue;
+      *is_splittable = true;
+      if (current_gain > best_gain) {
+        best_threshold = t; best_sum_left_gradient = grad; best_sum_left_hessian = hess + kEpsilon; best_left_count = cnt; best_gain = current_gain;
+      }
+    }
+  } else {
+    for (int i = 1; i < m.num_bin; ++i) if (RoundInt(HESS(i) * cnt_factor) >= c.cat_smooth) sorted_idx.push_back(i);
+    used_bin = static_cast<int>(sorted_idx.size());
+    c.l2 += c.cat_l2;
+    auto ctr = [&](int i) { return GRAD(i) / (HESS(i) + c.cat_smooth); };
+    std::stable_sort(sorted_idx.begin(), sorted_idx.end(), [&](int i, int j) { return ctr(i) < ctr(j); });
+    const int max_num_cat = std::min(c.max_cat_threshold, (used_bin + 1) / 2);
+    const int dirs[2] = {1, -1};
+    const int starts[2] = {0, used_bin - 1};
+    for (int out_i = 0; out_i < 2; ++out_i) {
+      int dir = dirs[out_i], start_pos = starts[out_i];
+      int cnt_cur_group = 0, left_count = 0;
+      double sum_left_gradient = 0.0, sum_left_hessian = kEpsilon;
+      for (int i = 0; i < used_bin && i < max_num_cat; ++i) {
+        int t = sorted_idx[start_pos];
+        start_pos += dir;
+        const double grad = GRAD(t), hess = HESS(t);
+        int cnt = RoundInt(hess * cnt_factor);
+        sum_left_gradient += grad; sum_left_hessian += hess; left_count += cnt; cnt_cur_group += cnt;
+        if (left_count < c.min_data_in_leaf || sum_left_hessian < c.min_sum_hessian) continue;
+        int right_count = num_data - left_count;
+        if (right_count < c.min_data_in_leaf || right_count < c.min_data_per_group) break;
+        double sum_right_hessian = sum_hessian - sum_left_hessian;
+        if (sum_right_hessian < c.min_sum_hessian) break;
+        if (cnt_cur_group < c.min_data_per_group) continue;
+        cnt_cur_group = 0;
+        double sum_right_gradient = sum_gradient - sum_left_gradient;
+        double current_gain = LeafGain(sum_left_gradient, sum_left_hessian, c) + LeafGain(sum_right_gradient, sum_right_hessian, c);
+        if (current_gain <= min_gain_shift) continue;
+        *is_splittable = true;
+        if (current_gain > best_gain) {
+          best_left_count = left_count; best_sum_left_gradient = sum_left_gradient; best_sum_left_hessian = sum_left_hessian;
+          best_threshold = i; best_gain = current_gain; best_dir = dir;
+        }
+      }
+    }
+  }
+  if (*is_splittable) {
+    output->left_output = CalcOutput(best_sum_left_gradient, best_sum_left_hessian, c);
+    output->left_count = best_left_count;
+    output->left_sum_gradient = best_sum_left_gradient;
+    output->left_sum_hessian = best_sum_left_hessian - kEpsilon;
+    output->right_output = CalcOutput(sum_gradient - best_sum_left_gradient, sum_hessian - best_sum_left_hessian, c);
+    output->right_count = num_data - best_left_count;
+    output->right_sum_gradient = sum_gradient - best_sum_left_gradient;
+    output->right_sum_hessian = sum_hessian - best_sum_left_hessian - kEpsilon;
+    output->gain = best_gain - min_gain_shift;
+    output->cat_threshold.clear();
+    if (use_onehot) output->cat_threshold.push_back(static_cast<uint32_t>(best_threshold));
+    else {
+      for (int i = 0; i <= best_threshold; ++i)
+        output->cat_threshold.push_back(static_cast<uint32_t>(best_dir == 1 ? sorted_idx[i] : sorted_idx[used_bin - 1 - i]));
+    }
+    output->threshold = 0;
+  }
+}
+
+inline std::vector<uint32_t> ConstructBitset(const std::vector<int>& vals) {
+  std::vector<uint32_t> ret;
+  for (int v : vals) {
+    size_t i1 = static_cast<size_t>(v) / 32, i2 = static_cast<size_t>(v) % 32;
+    if (ret.size() < i1 + 1) ret.resize(i1 + 1, 0);
+    ret[i1] |= (1u << i2);
+  }
+  return ret;
+}
+inline bool FindInBitset(const uint32_t* bits, int n, int pos) {
+  int i1 = pos / 32;
+  if (pos < 0 || i1 >= n) return false;
+  return (bits[i1] >> (pos % 32)) & 1;
+}
+
 // ------------------------------------------------------------------ tree [UPSTREAM io/tree.cpp]
 inline double MaybeRoundToZero(double x) { return std::fabs(x) > kZeroThreshold ? x : 0.0; }
 inline double AvoidInf(double x) {
@@ -887,6 +1078,9 @@ inline double AvoidInf(double x) {
 }
 struct Tree {
   int num_leaves = 1;
+  int num_cat = 0;
+  std::vector<int> cat_boundaries{0}, cat_boundaries_inner{0};
+  std::vector<uint32_t> cat_threshold, cat_threshold_inner;
   double shrinkage = 1.0;
   std::vector<int> left_child, right_child, split_feature_inner, split_feature, leaf_parent, leaf_count, internal_count, leaf_depth;
   std::vector<uint32_t> threshold_in_bin;
@@ -935,6 +1129,21 @@ struct Tree {
     ++num_leaves;
     return num_leaves - 1;
   }
+  int SplitCategorical(int leaf, int feature, int real_feature, const std::vector<uint32_t>& bits_inner, const std::vector<uint32_t>& bits,
+                       double left_value, double right_value, int left_cnt, int right_cnt, double left_weight, double right_weight, float gain,
+                       int missing_type) {
+    int new_leaf = Split(leaf, feature, real_feature, 0, 0.0, left_value, right_value, left_cnt, right_cnt, left_weight, right_weight, gain, missing_type, false);
+    int node = num_leaves - 2;
+    decision_type[node] = static_cast<int8_t>(1 | (missing_type << 2));
+    threshold_in_bin[node] = num_cat;
+    threshold[node] = num_cat;
+    ++num_cat;
+    cat_boundaries.push_back(cat_boundaries.back() + static_cast<int>(bits.size()));
+    cat_threshold.insert(cat_threshold.end(), bits.begin(), bits.end());
+    cat_boundaries_inner.push_back(cat_boundaries_inner.back() + static_cast<int>(bits_inner.size()));
+    cat_threshold_inner.insert(cat_threshold_inner.end(), bits_inner.begin(), bits_inner.end());
+    return new_leaf;
+  }
   void Shrinkage(double rate) {
     for (int i = 0; i < num_leaves - 1; ++i) { leaf_value[i] = MaybeRoundToZero(leaf_value[i] * rate); internal_value[i] = MaybeRoundToZero(internal_value[i] * rate); }
     leaf_value[num_leaves - 1] = MaybeRoundToZero(leaf_value[num_leaves - 1] * rate);
@@ -952,6 +1161,18 @@ struct Tree {
     while (node >= 0) {
       double fval = row[split_feature[node]];
       int mt = (decision_type[node] >> 2) & 3;
+      if (decision_type[node] & 1) {     // CategoricalDecision
+        bool left = false;
+        if (!(std::isnan(fval) && mt == kMissNaN)) {
+          int iv = std::isnan(fval) ? 0 : static_cast<int>(fval);
+          if (iv >= 0) {
+            int ci = static_cast<int>(threshold[node]);
+            left = FindInBitset(cat_threshold.data() + cat_boundaries[ci], cat_boundaries[ci + 1] - cat_boundaries[ci], iv);
+          }
+        }
+        node = left ? left_child[node] : right_child[node];
+        continue;
+      }
       if (std::isnan(fval) && mt != kMissNaN) fval = 0.0;
       bool go_left;
       if ((mt == kMissZero && std::fabs(fval) <= kZeroThreshold) || (mt == kMissNaN && std::isnan(fval))) go_left = decision_type[node] & 2;
@@ -976,7 +1197,7 @@ struct Tree {
     std::ostringstream s;
     int nl = num_leaves;
     s << "num_leaves=" << nl << '\n';
-    s << "num_cat=0\n";
+    s << "num_cat=" << num_cat << '\n';
     s << "split_feature=" << Arr(split_feature, nl - 1, "%d") << '\n';
     s << "split_gain=" << Arr(split_gain, nl - 1, "%g") << '\n';
     s << "threshold=" << Arr(threshold, nl - 1, "%.17g") << '\n';
@@ -989,6 +1210,12 @@ struct Tree {
     s << "internal_value=" << Arr(internal_value, nl - 1, "%g") << '\n';
     s << "internal_weight=" << Arr(internal_weight, nl - 1, "%g") << '\n';
     s << "internal_count=" << Arr(internal_count, nl - 1, "%d") << '\n';
+    if (num_cat > 0) {
+      s << "cat_boundaries=" << Arr(cat_boundaries, num_cat + 1, "%d") << '\n';
+      std::string ct;
+      for (size_t i = 0; i < cat_threshold.size(); ++i) ct += (i ? " " : "") + std::to_string(cat_threshold[i]);
+      s << "cat_threshold=" << ct << '\n';
+    }
     s << "is_linear=0\n";
     char buf[64];
     snprintf(buf, sizeof(buf), "%g", shrinkage);
@@ -1036,6 +1263,8 @@ struct TreeLearner {
     ds = d; cfg = c; parallel = par;
     nf = static_cast<int>(d->used.size());
     sc = {c.lambda_l1, c.lambda_l2, c.max_delta_step, c.min_gain_to_split, c.min_sum_hessian_in_leaf, c.min_data_in_leaf};
+    sc.max_cat_threshold = c.max_cat_threshold; sc.max_cat_to_onehot = c.max_cat_to_onehot; sc.min_data_per_group = c.min_data_per_group;
+    sc.cat_l2 = c.cat_l2; sc.cat_smooth = c.cat_smooth;
     idx.resize(d->n); tmp_left.resize(d->n); tmp_right.resize(d->n); og.resize(d->n); oh.resize(d->n);
     int L = c.num_leaves;
     leaf_begin.assign(L, 0); leaf_cnt.assign(L, 0); global_cnt.assign(L, 0);
@@ -1098,7 +1327,8 @@ struct TreeLearner {
       const BinMapper& bm = ds->mappers[ds->used[u]];
       ScanMeta m{bm.num_bin, bm.missing_type, static_cast<int>(bm.default_bin), bm.most_freq_bin == 0 ? 1 : 0};
       bool ok = false;
-      FindBestThresholdNumerical(&hist[static_cast<size_t>(u) * 512], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
+      if (bm.is_categorical) FindBestThresholdCategorical(&hist[static_cast<size_t>(u) * 512], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
+      else FindBestThresholdNumerical(&hist[static_cast<size_t>(u) * 512], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
       cand[u].feature = ds->used[u];
       flag[u] = ok ? 1 : 0;
     }
@@ -1173,11 +1403,14 @@ struct TreeLearner {
       const uint8_t* col = &ds->bins[static_cast<size_t>(inner) * n];
       int b0 = leaf_begin[best_leaf], c0 = leaf_cnt[best_leaf];
       int nl = 0, nr = 0;
+      std::vector<uint32_t> bits_inner;
+      if (bm.is_categorical) { std::vector<int> v(bs.cat_threshold.begin(), bs.cat_threshold.end()); bits_inner = ConstructBitset(v); }
       for (int i = 0; i < c0; ++i) {
         int r = idx[b0 + i];
         uint32_t bin = col[r];
         bool left;
-        if (bm.missing_type == kMissNaN && bin == static_cast<uint32_t>(bm.num_bin - 1)) left = bs.default_left;
+        if (bm.is_categorical) left = FindInBitset(bits_inner.data(), static_cast<int>(bits_inner.size()), static_cast<int>(bin));
+        else if (bm.missing_type == kMissNaN && bin == static_cast<uint32_t>(bm.num_bin - 1)) left = bs.default_left;
         else if (bm.missing_type == kMissZero && bin == bm.default_bin) left = bs.default_left;
         else left = bin <= bs.threshold;
         if (left) tmp_left[nl++] = r; else tmp_right[nr++] = r;
@@ -1193,6 +1426,13 @@ struct TreeLearner {
                    bs.right_output, smaller_rows, 0};
         trace->push_back(r);
       }
+      if (bm.is_categorical) {
+        std::vector<int> cats;
+        for (uint32_t b : bs.cat_threshold) cats.push_back(bm.bin_2_cat[b]);
+        tree->SplitCategorical(best_leaf, inner, bs.feature, bits_inner, ConstructBitset(cats), bs.left_output, bs.right_output, bs.left_count,
+                               bs.right_count, bs.left_sum_hessian, bs.right_sum_hessian, static_cast<float>(bs.gain + cfg.min_gain_to_split),
+                               bm.missing_type);
+      } else
       tree->Split(best_leaf, inner, bs.feature, bs.threshold, bm.upper[bs.threshold], bs.left_output, bs.right_output, bs.left_count,
                   bs.right_count, bs.left_sum_hessian, bs.right_sum_hessian, static_cast<float>(bs.gain + cfg.min_gain_to_split),
                   bm.missing_type, bs.default_left);

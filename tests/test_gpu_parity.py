@@ -378,3 +378,57 @@ def test_batched_gpu_prediction_bit_exact_with_host_predictor(built):
     big = np.tile(X32, (20, 1))
     out, ms = b.predict_device(big, capi.PREDICT_RAW_SCORE, return_ms=True)
     print("GPU batch predict: %d rows x %d feats x 20 trees in %.2f ms (incl. H2D/D2H) = %.1f Mrows/s" % (big.shape[0], F, ms, big.shape[0] / ms / 1e3))
+
+
+def _categorical_matrix(rng, n):
+    c12 = rng.integers(0, 12, n).astype(np.float64)                               # many-vs-many
+    c3 = rng.integers(0, 3, n).astype(np.float64)                                 # one-hot (num_bin <= 4)
+    c3[rng.random(n) < 0.05] = np.nan
+    zipf = np.minimum(rng.zipf(1.5, n), 400).astype(np.float64) * 3 - 2           # ~150 categories, long tail, a negative value
+    x = rng.standard_normal((n, 3))
+    eff12 = np.array([0.5, -1, 2, 0.1, -0.3, 1.5, -2, 0, 0.7, -0.9, 1.1, -1.4])
+    s = eff12[c12.astype(int)] + np.where(np.nan_to_num(c3) == 1, 1.0, 0.0) + 0.8 * np.sin(zipf) + x[:, 0] + 0.3 * rng.standard_normal(n)
+    X = np.column_stack([c12, x[:, 0], c3, x[:, 1], zipf, x[:, 2]])
+    return X, s
+
+
+@pytest.mark.parametrize("objective", ["regression", "binary"])
+def test_categorical_features(built, objective):
+    """categoricalSlotIndexes -> categorical_feature=... (LightGBMBase.scala:168-199, 265-272; 'num_cat=' check VerifyLightGBMClassifier.scala:463-495):
+    categorical bin finder, one-hot and many-vs-many split search, bitset splits in partition / model text / predictors."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(81)
+    n = 40000
+    X, s = _categorical_matrix(rng, n)
+    y = (s > 0.3).astype(np.float32) if objective == "binary" else s.astype(np.float32)
+    dsp = DS_PARAMS + " categorical_feature=0,2,4"
+    ds, ods = _make(X, y, ds_params=dsp)
+    for f in range(X.shape[1]):
+        assert ds.feature_info(f) == ods.feature_info(f)
+    assert np.array_equal(ds.get_bins(), ods.bins())
+    params = _classifier_params(objective, "categorical_feature=0,2,4" + (" is_unbalance=false" if objective == "binary" else ""), leaves=15)
+    b, ob, m, om = _train_both(ds, ods, params, 15)
+    compare_models(m, om)
+    assert sum(t.get("num_cat", 0) for t in m["trees"]) > 5 and "num_cat=" in b.save_model_to_string()
+    dts = np.concatenate([t["decision_type"] for t in m["trees"]])
+    assert (dts & 1).any() and ((dts & 1) == 0).any()
+    # predictors agree: host single/batch, device batch, oracle, and the training scores
+    raw_host = b.predict_for_mat(X[:3000], capi.PREDICT_RAW_SCORE)[:, 0]
+    np.testing.assert_array_equal(b.predict_device(X[:3000], capi.PREDICT_RAW_SCORE)[:, 0], raw_host)
+    np.testing.assert_allclose(raw_host, ob.predict_raw(X[:3000])[:, 0], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(raw_host, b.get_scores()[:3000], rtol=1e-9, atol=1e-9)
+    b2 = capi.Booster(model_str=b.save_model_to_string())              # model text round trip keeps cat_boundaries / cat_threshold
+    np.testing.assert_array_equal(b2.predict_for_mat(X[:3000], capi.PREDICT_RAW_SCORE)[:, 0], raw_host)
+    unseen = X[:5].copy(); unseen[:, 0] = 999; unseen[:, 4] = -7        # unseen / negative categories go right
+    np.testing.assert_allclose(b.predict_for_mat(unseen, capi.PREDICT_RAW_SCORE), ob.predict_raw(unseen), rtol=1e-6, atol=1e-6)
+
+
+def test_categorical_too_many_bins_fails_loudly(built):
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(0)
+    X = np.column_stack([rng.integers(0, 5000, 100000).astype(np.float64), rng.standard_normal(100000)])
+    with pytest.raises(capi.LightGBMError) as e:
+        capi.Dataset.from_mat(X, DS_PARAMS + " categorical_feature=0")
+    assert "uint8" in str(e.value)
