@@ -465,7 +465,7 @@ void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   k_absmax<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, ctrl.p);
   k_set_scale<<<1, 1, 0, stream>>>(ctrl.p, 0, 1.0);
-  k_quantize<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, q.p, ctrl.p, 0);
+  k_quantize<<<sms * 4, 256, 0, stream>>>(g.p, h.p, n, q.p, ctrl.p, 0, nullptr, 0);
   HistWork w{0, cnt, idx ? 1 : 0, 0};
   B200_CUDA(cudaMemcpyAsync(&ctrl.p->hist_work, &w, sizeof(w), cudaMemcpyHostToDevice, stream));
   k4_hist_build_ws<4><<<sms, kWsThreads, kWsSmemBytes, stream>>>(bins.p, rows_stride, num_tiles, q.p, didx.p, didx.p, &ctrl.p->hist_work,
@@ -604,7 +604,9 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   EnsureDevice();
   device_ = CurrentDevice();
   cfg.Parse(params);
-  if (cfg.boosting != "gbdt") Fatal("boosting_type=" + cfg.boosting + " is not implemented by this build yet (gbdt only)");
+  if (cfg.boosting != "gbdt" && cfg.boosting != "rf" && cfg.boosting != "goss")
+    Fatal("boosting_type=" + cfg.boosting + " is not implemented by this build (gbdt, rf and goss are)");
+  is_rf_ = cfg.boosting == "rf"; is_goss_ = cfg.boosting == "goss";
   {
     static const char* kRegVar[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
     for (int k = 1; k <= 5; ++k) if (cfg.objective == kRegVar[k]) regvar_kind_ = k;
@@ -613,8 +615,19 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
     Fatal("objective=" + cfg.objective + " needs leaf-output renewal (weighted percentiles), which this build does not implement yet");
   if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_)
     Fatal("Unknown/unsupported objective type name: " + cfg.objective);
-  if (cfg.bagging_freq > 0 && (cfg.bagging_fraction < 1.0 || cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
-    Fatal("bagging is not implemented by this build yet");
+  if (cfg.bagging_freq > 0 && (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
+    Fatal("balanced bagging (pos_/neg_bagging_fraction) is not implemented by this build");
+  bagging_ = cfg.bagging_freq > 0 && cfg.bagging_fraction < 1.0;
+  if (bagging_ && !(cfg.bagging_fraction > 0.0)) Fatal("bagging_fraction should be in (0, 1]");
+  if (is_goss_) {      // [LightGBM goss.hpp ResetGoss]
+    if (!(cfg.top_rate + cfg.other_rate <= 1.0)) Fatal("Check failed: (config_->top_rate + config_->other_rate) <= (1.0f)");
+    if (!(cfg.top_rate > 0.0 && cfg.other_rate > 0.0)) Fatal("Check failed: config_->top_rate > 0.0f && config_->other_rate > 0.0f");
+    if (bagging_) Fatal("Cannot use bagging in GOSS");
+  }
+  if (is_rf_) {        // [LightGBM rf.hpp RF::Init]
+    const bool ff = cfg.feature_fraction < 1.0 && cfg.feature_fraction > 0.0;
+    if (!(bagging_ || ff)) Fatal("Check failed: (config->bagging_freq > 0 && config->bagging_fraction < 1.0f && config->bagging_fraction > 0.0f) || (config->feature_fraction < 1.0f && config->feature_fraction > 0.0f)");
+  }
   if (cfg.num_leaves < 2) Fatal("num_leaves should be >= 2");
   if (train->label.empty()) Fatal("label should not be empty for training");
   if (cfg.objective == "multiclass" && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
@@ -622,7 +635,8 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   K = cfg.objective == "multiclass" ? cfg.num_class : 1;
   parallel_ = Net().active && Net().world > 1;
   cfg.num_machines = parallel_ ? Net().world : 1;
-  shrinkage_ = cfg.learning_rate;
+  shrinkage_ = is_rf_ ? 1.0 : cfg.learning_rate;      // "no shrinkage rate for the RF"
+  model.average_output = is_rf_;
   model.num_class = cfg.objective == "multiclass" ? cfg.num_class : 1;
   model.num_tree_per_iteration = K;
   model.label_index = 0;
@@ -716,7 +730,7 @@ void Booster::InitTraining() {
   class_need_train_.assign(K, true);
   const_hessian_ = false;
   if (cfg.objective == "regression") {
-    const_hessian_ = train->weight.empty();
+    const_hessian_ = train->weight.empty() && !is_goss_;      // GOSS amplifies hessians [LightGBM goss.hpp GetIsConstHessian -> false]
   } else if (regvar_kind_) {
     if (regvar_kind_ >= 3) for (int i = 0; i < n; ++i) if (train->label[i] < 0) Fatal("[" + cfg.objective + "]: at least one target label is negative");
   } else if (cfg.objective == "binary") {
@@ -789,7 +803,58 @@ void Booster::InitTraining() {
   feature_used_.Alloc(train->nf_pad);
   feature_used_.Upload(feature_used_host_.data(), train->nf_pad, stream_);
   ResetFeaturesByTree();
+  if (bagging_ || is_goss_) {
+    bag_blocks_ = (n + kBagBlock - 1) / kBagBlock;
+    std::vector<unsigned> st(bag_blocks_);
+    for (int i = 0; i < bag_blocks_; ++i) st[i] = static_cast<unsigned>(cfg.bagging_seed + i);     // bagging_rands_[i] = Random(bagging_seed + i)
+    bag_lcg_.Alloc(bag_blocks_); bag_lcg_.Upload(st.data(), st.size(), stream_);
+    std::unique_ptr<LcgJump> jt(new LcgJump());
+    unsigned a = 1, c = 0;
+    for (int j = 0; j < kBagBlock; ++j) { a = a * 214013u; c = c * 214013u + 2531011u; jt->mul[j] = a; jt->add[j] = c; }
+    bag_jump_.Alloc(1); bag_jump_.Upload(jt.get(), 1, stream_);
+    in_bag_.Alloc(n); bag_block_cnt_.Alloc(bag_blocks_); bag_idx_.Alloc(n); bag_total_.Alloc(1);
+    need_re_bagging_ = bagging_;
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  }
+  if (is_rf_) {        // [LightGBM rf.hpp RF::Boosting] gradients are taken once, at the constant init score
+    if (!train->init_score.empty()) Fatal("Check failed: train_data->metadata().init_score() == nullptr");
+    rf_init_scores_.assign(K, 0.0);
+    DevBuf<double> tmp;
+    tmp.Alloc(static_cast<size_t>(K) * n); tmp.Zero(stream_);
+    for (int k = 0; k < K; ++k) {
+      double init = (cfg.boost_from_average && !has_init_score_) ? ObjectiveInitScore(k) : 0.0;
+      if (!(std::fabs(init) > kEps)) init = 0.0;
+      rf_init_scores_[k] = init;
+      if (init != 0.0) k_add_const<<<num_sms_ * 4, 256, 0, stream_>>>(tmp.p + static_cast<size_t>(k) * n, n, init);
+    }
+    ComputeGradientsAt(tmp.p);
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  }
   B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// [LightGBM gbdt.cpp GBDT::Bagging / goss.hpp GOSS::Bagging] draws the in-bag flags on the device, compacts the in-bag rows
+// (ascending) into bag_idx_; the tree's root leaf is that list.  One small D2H (the bag size) per re-bagging.
+void Booster::Bagging(int it) {
+  const int n = train->num_data;
+  cudaStream_t s = stream_;
+  if (is_goss_) {
+    use_bag_ = false;
+    if (it < static_cast<int>(1.0f / cfg.learning_rate)) return;
+    k_goss_draw<<<bag_blocks_, 256, 0, s>>>(bag_lcg_.p, n, K, cfg.top_rate, cfg.other_rate, grad_.p, hess_.p, in_bag_.p, bag_block_cnt_.p);
+  } else {
+    if (!bagging_) return;
+    if (!((use_bag_ && it % cfg.bagging_freq == 0) || need_re_bagging_)) return;
+    need_re_bagging_ = false;
+    k_bag_draw<<<bag_blocks_, 256, 0, s>>>(bag_lcg_.p, bag_jump_.p, n, cfg.bagging_fraction, in_bag_.p, bag_block_cnt_.p);
+  }
+  k_bag_scan<<<1, 1024, 0, s>>>(bag_block_cnt_.p, bag_blocks_, bag_total_.p);
+  k_bag_compact<<<bag_blocks_, 256, 0, s>>>(in_bag_.p, bag_block_cnt_.p, n, bag_idx_.p);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(&bag_count_, bag_total_.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  timing.launches += 3;
+  use_bag_ = true;
 }
 
 // Peer-memory set-up for the fused reduce+scan (k_scan_dp / k_pick_dp): every rank publishes its scratch histogram, mailbox and
@@ -912,25 +977,26 @@ double Booster::BoostFromAverage(int k) {
   return 0.0;
 }
 
-void Booster::ComputeGradients() {
+void Booster::ComputeGradients() { ComputeGradientsAt(score_.p); }
+void Booster::ComputeGradientsAt(const double* score_p) {
   const int n = train->num_data;
   const int grid = num_sms_ * 8;
   const float* w = train->weight.empty() ? nullptr : train->d_weight.p;
   if (cfg.objective == "regression") {
-    k_grad_l2<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n);
+    k_grad_l2<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n);
   } else if (regvar_kind_) {
-    k_grad_regvar<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, regvar_kind_, cfg.alpha, cfg.fair_c,
+    k_grad_regvar<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, regvar_kind_, cfg.alpha, cfg.fair_c,
                                              cfg.poisson_max_delta_step, cfg.tweedie_variance_power);
   } else if (cfg.objective == "binary") {
     if (binary_need_train_)
-      k_grad_binary<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, cfg.sigmoid, binary_w_[0], binary_w_[1]);
+      k_grad_binary<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, cfg.sigmoid, binary_w_[0], binary_w_[1]);
   } else if (cfg.objective == "multiclass") {
-    k_grad_softmax<<<grid, 256, 0, stream_>>>(score_.p, train->d_label.p, w, grad_.p, hess_.p, n, K, static_cast<double>(K) / (K - 1.0));
+    k_grad_softmax<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, K, static_cast<double>(K) / (K - 1.0));
   } else if (cfg.objective == "lambdarank") {
     const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
     size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4), 1024);
     k_grad_lambdarank<<<std::min(nq, num_sms_ * 8), 256, smem, stream_>>>(
-        score_.p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
+        score_p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
         lr_max_in_, lr_idx_factor_, cfg.sigmoid, cfg.lambdarank_truncation_level, cfg.lambdarank_norm ? 1 : 0, grad_.p, hess_.p, lr_max_q_);
   }
   B200_CUDA(cudaGetLastError());
@@ -952,10 +1018,12 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   k_absmax<<<egrid, 256, 0, s>>>(g, h, n, ctrl);
   if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->absmax_bits[0], &ctrl->absmax_bits[0], 2, ncclUint32, ncclMax, Net().comm, s));
   k_set_scale<<<1, 1, 0, s>>>(ctrl, const_hessian_ ? 1 : 0, 1.0);
-  k_quantize<<<egrid, 256, 0, s>>>(g, h, n, qgh_.p, ctrl, const_hessian_ ? 1 : 0);
+  k_quantize<<<egrid, 256, 0, s>>>(g, h, n, qgh_.p, ctrl, const_hessian_ ? 1 : 0, use_bag_ ? in_bag_.p : nullptr, bag_count_);
   if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->root_q[0], &ctrl->root_q[0], 3, ncclInt64, ncclSum, Net().comm, s));
   ResetFeaturesByTree();
-  k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, n, feature_used_.p);
+  if (use_bag_)      // the root leaf is the ascending in-bag row list (SetBaggingData); partitions then ping-pong idx0/idx1 as usual
+    B200_CUDA(cudaMemcpyAsync(idx0_.p, bag_idx_.p, static_cast<size_t>(bag_count_) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, use_bag_ ? bag_count_ : n, feature_used_.p, use_bag_ ? 1 : 0);
   timing.launches += 4;
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, num_sms_ * 8));
   const dim3 sgrid((d.nf + 7) / 8, 2);
@@ -988,10 +1056,16 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     timing.launches += 7; timing.hist_launches += 1;
   }
   k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 1);
-  k_add_score<<<egrid, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, idx0_.p, idx1_.p, score_.p + static_cast<size_t>(k) * n, shrinkage_);
+  // rf keeps scores as the running average of (tree + init score) over the iterations [LightGBM rf.hpp MultiplyScore / UpdateScore]
+  const double bias = is_rf_ ? rf_init_scores_[k] : 0.0, pre = is_rf_ ? static_cast<double>(iter + num_init_iteration) : 1.0;
+  const double post = is_rf_ ? 1.0 / (iter + num_init_iteration + 1) : 1.0;
+  if (use_bag_ || is_rf_)      // out-of-bag rows are scored by walking the tree on the binned data, so walk it for every row
+    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, d.meta.p, d.bins.p, d.rows_stride, n, score_.p + static_cast<size_t>(k) * n, shrinkage_, bias, pre, post);
+  else
+    k_add_score<<<egrid, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, idx0_.p, idx1_.p, score_.p + static_cast<size_t>(k) * n, shrinkage_);
   for (auto* v : valids_)
     k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, v->ds->meta.p, v->ds->bins.p, v->ds->rows_stride, v->ds->num_data,
-                                            v->score.p + static_cast<size_t>(k) * v->ds->num_data, shrinkage_);
+                                            v->score.p + static_cast<size_t>(k) * v->ds->num_data, shrinkage_, bias, pre, post);
   timing.launches += 2 + static_cast<long long>(valids_.size());
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(tree_host_, tree_blob_.p, tree_blob_bytes_, cudaMemcpyDeviceToHost, s));
@@ -1057,7 +1131,10 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
   B200_CUDA(cudaEventRecord(ev_a_, s));
   std::vector<double> init_scores(K, 0.0);
   bool saved_const = const_hessian_;
-  if (!custom_g) {
+  if (is_rf_) {
+    if (custom_g) Fatal("RF mode do not support custom objective function, please use built-in objectives.");
+    init_scores = rf_init_scores_;
+  } else if (!custom_g) {
     for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
     ComputeGradients();
   } else {
@@ -1065,7 +1142,8 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
     hess_.Upload(custom_h, static_cast<size_t>(K) * n, s);
     const_hessian_ = false;
   }
-  bool should_continue = false;
+  Bagging(iter);
+  bool should_continue = is_rf_;        // a random forest never stops early
   for (int k = 0; k < K; ++k) {
     std::unique_ptr<HostTree> t(new HostTree());
     t->Resize(1);
@@ -1078,8 +1156,9 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
     } else if (static_cast<int>(model.trees.size()) < K) {
       double output = class_need_train_[k] ? init_scores[k] : ObjectiveInitScore(k);
       t->MakeConstant(output);
-      k_add_const<<<num_sms_ * 4, 256, 0, s>>>(score_.p + static_cast<size_t>(k) * n, n, output);
-      for (auto* v : valids_) k_add_const<<<num_sms_ * 4, 256, 0, s>>>(v->score.p + static_cast<size_t>(k) * v->ds->num_data, v->ds->num_data, output);
+      const double pre = is_rf_ ? static_cast<double>(iter + num_init_iteration) : 1.0, post = is_rf_ ? 1.0 / (iter + num_init_iteration + 1) : 1.0;
+      k_scale_add<<<num_sms_ * 4, 256, 0, s>>>(score_.p + static_cast<size_t>(k) * n, n, pre, output, post);
+      for (auto* v : valids_) k_scale_add<<<num_sms_ * 4, 256, 0, s>>>(v->score.p + static_cast<size_t>(k) * v->ds->num_data, v->ds->num_data, pre, output, post);
     } else {
       t->MakeConstant(0.0);
     }
@@ -1109,7 +1188,7 @@ void Booster::ResetParameter(const char* params) {
   int keep_machines = cfg.num_machines;
   cfg.Refresh();
   cfg.num_machines = keep_machines;
-  shrinkage_ = cfg.learning_rate;
+  shrinkage_ = is_rf_ ? 1.0 : cfg.learning_rate;
   sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step; sp_.min_gain_to_split = cfg.min_gain_to_split;
   sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf; sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth;
 }
@@ -1433,9 +1512,11 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
   cudaEventElapsedTime(&ms, e0, e1);
   last_predict_ms = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const bool avg = model.average_output && t1 > t0 && predict_type != 2;      // rf: raw score = mean over the iterations
+  if (avg && predict_type == 1)
+    for (int64_t i = 0; i < nrow * Kc; ++i) out[i] /= ((t1 - t0) / Kc);
   if (predict_type == 0) {          // objective transform on the host, identical to the single-row predictor
     std::vector<double> r(Kc), o(Kc);
-    const bool avg = model.average_output && t1 > t0;
     for (int64_t i = 0; i < nrow; ++i) {
       double* p = out + i * Kc;
       if (avg) for (int k = 0; k < Kc; ++k) p[k] /= ((t1 - t0) / Kc);

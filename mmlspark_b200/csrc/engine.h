@@ -184,6 +184,16 @@ class Booster {
   std::vector<uint8_t> feature_used_host_;
   DevBuf<uint8_t> feature_used_;
   void ResetFeaturesByTree();
+  // row subsampling: bagging / GOSS / random forest
+  bool is_rf_ = false, is_goss_ = false, bagging_ = false, use_bag_ = false, need_re_bagging_ = false;
+  int bag_count_ = 0, bag_blocks_ = 0;
+  DevBuf<unsigned> bag_lcg_;            // one LCG state per 1024-row block
+  DevBuf<LcgJump> bag_jump_;
+  DevBuf<uint8_t> in_bag_;
+  DevBuf<int> bag_block_cnt_, bag_idx_, bag_total_;
+  std::vector<double> rf_init_scores_;
+  void Bagging(int it);
+  void ComputeGradientsAt(const double* score);
   SplitParams sp_{};
   // device state
   DevBuf<double> score_;        // [K][n]

@@ -308,7 +308,8 @@ __global__ void k_set_scale(TreeCtrl* ctrl, int const_hessian, double hess_const
   ctrl->root_q[0] = 0; ctrl->root_q[1] = 0; ctrl->root_q[2] = 0; ctrl->root_q[3] = 0;
 }
 __global__ void __launch_bounds__(256)
-k_quantize(const float* __restrict__ g, const float* __restrict__ h, int n, int4* __restrict__ qgh, TreeCtrl* ctrl, int const_hessian) {
+k_quantize(const float* __restrict__ g, const float* __restrict__ h, int n, int4* __restrict__ qgh, TreeCtrl* ctrl, int const_hessian,
+           const uint8_t* __restrict__ in_bag, int bag_count) {
   const int eg = ctrl->exp_g, eh = ctrl->exp_h;
   long long sg = 0, sh = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -319,7 +320,7 @@ k_quantize(const float* __restrict__ g, const float* __restrict__ h, int n, int4
     if (const_hessian) { qh = 1; q.z = 1; q.w = 0; }
     else { qh = __double2ll_rn(ldexp(static_cast<double>(h[i]), eh)); q.z = static_cast<int>(qh >> kLoBits); q.w = static_cast<int>(qh & ((1LL << kLoBits) - 1)); }
     qgh[i] = q;
-    sg += qg; sh += qh;
+    if (!in_bag || in_bag[i]) { sg += qg; sh += qh; }       // root sums run over the in-bag rows only
   }
   for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sh += __shfl_xor_sync(0xffffffffu, sh, o); }
   __shared__ long long s_g[8], s_h[8];
@@ -331,13 +332,14 @@ k_quantize(const float* __restrict__ g, const float* __restrict__ h, int n, int4
     for (int w = 0; w < 8; ++w) { a += s_g[w]; b += s_h[w]; }
     atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[0]), static_cast<unsigned long long>(a));
     atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[1]), static_cast<unsigned long long>(b));
-    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[2]), static_cast<unsigned long long>(n));
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->root_q[2]), static_cast<unsigned long long>(in_bag ? bag_count : n));
   }
 }
 
 // ---------------------------------------------------------------- tree init / round controller
 __global__ void __launch_bounds__(256)
-k_tree_init(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, SplitParams p, int n_local, const uint8_t* feature_used) {
+k_tree_init(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, SplitParams p, int n_local, const uint8_t* feature_used,
+            int root_is_bag) {
   for (int u = threadIdx.x; u < p.nf_pad; u += blockDim.x) flags[u] = (u < p.nf && (!feature_used || feature_used[u])) ? 1 : 0;
   for (int l = threadIdx.x; l < p.num_leaves; l += blockDim.x) {
     leaves[l].best.gain = kNegInf; leaves[l].best.feature = -1;
@@ -345,7 +347,7 @@ k_tree_init(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, Spl
   }
   if (threadIdx.x == 0) {
     LeafState& r = leaves[0];
-    r.begin = 0; r.count = n_local; r.buf = 0; r.depth = 0; r.identity = 1; r.hist_slot = 0; r.parent_node = -1;
+    r.begin = 0; r.count = n_local; r.buf = 0; r.depth = 0; r.identity = root_is_bag ? 0 : 1; r.hist_slot = 0; r.parent_node = -1;
     r.global_count = static_cast<int>(ctrl->root_q[2]);
     r.sum_g = static_cast<double>(ctrl->root_q[0]) * ctrl->inv_g;
     r.sum_h = static_cast<double>(ctrl->root_q[1]) * ctrl->inv_h;
@@ -1165,7 +1167,7 @@ __global__ void k_add_const(double* __restrict__ score, int n, double v) {
 // score of a (validation) dataset += shrinkage * tree(row), traversing by bin thresholds
 __global__ void __launch_bounds__(256)
 k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t* __restrict__ bins, size_t rows_stride, int n,
-                  double* __restrict__ score, double shrinkage) {
+                  double* __restrict__ score, double shrinkage, double bias = 0.0, double pre_mul = 1.0, double post_mul = 1.0) {
   const int nl = *tree.num_leaves;
   if (nl <= 1) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1182,7 +1184,156 @@ k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t
     }
     double v = tree.leaf_value[~node] * shrinkage;
     if (!(fabs(v) > 1e-35)) v = 0.0;
-    score[i] += v;
+    score[i] = (score[i] * pre_mul + (v + bias)) * post_mul;      // rf: running average of (tree + init score); gbdt: pre = post = 1, bias = 0
+  }
+}
+__global__ void k_scale_add(double* __restrict__ score, int n, double pre_mul, double add, double post_mul) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) score[i] = (score[i] * pre_mul + add) * post_mul;
+}
+
+// ---------------------------------------------------------------- row subsampling: bagging / GOSS  
+// [LightGBM src/boosting/gbdt.cpp GBDT::BaggingHelper, goss.hpp GOSS::BaggingHelper] Rows are drawn per 1024-row block, every block
+// owning an LCG (x <- 214013 x + 2531011, float = ((x >> 16) & 0x7fff) / 32768) seeded bagging_seed + block. One CUDA block per
+// 1024-row block. The draw of row j of a block is the (j+1)-th LCG output, which the jump table gives directly:
+// x_{j+1} = mulA[j] * x0 + addC[j], so plain bagging is embarrassingly parallel and still bit-identical to the sequential draw.
+constexpr int kBagBlock = 1024;
+struct LcgJump { unsigned mul[kBagBlock]; unsigned add[kBagBlock]; };
+__device__ __forceinline__ float d_lcg_float(unsigned x) { return static_cast<float>((x >> 16) & 0x7FFFu) / 32768.0f; }
+
+__global__ void __launch_bounds__(256)
+k_bag_draw(unsigned* __restrict__ lcg_state, const LcgJump* __restrict__ jump, int n, double fraction, uint8_t* __restrict__ in_bag,
+           int* __restrict__ block_count) {
+  const int b = blockIdx.x, base = b * kBagBlock, cnt = min(kBagBlock, n - base);
+  const unsigned x0 = lcg_state[b];
+  int mine = 0;
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const unsigned x = jump->mul[j] * x0 + jump->add[j];
+    const int take = static_cast<double>(d_lcg_float(x)) < fraction;
+    in_bag[base + j] = static_cast<uint8_t>(take);
+    mine += take;
+  }
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) { block_count[b] = s_cnt; lcg_state[b] = jump->mul[cnt - 1] * x0 + jump->add[cnt - 1]; }
+}
+
+// GOSS: keep the top_rate share of rows by sum_k |g*h| and sample other_rate of the rest, amplifying the sampled gradients by
+// (cnt - top_k) / other_k.  The running probability depends on how many rows were sampled so far, so the draw is sequential inside
+// a 1024-row chunk (thread 0); threshold selection (bitonic sort) and the gradient scaling are parallel.
+__global__ void __launch_bounds__(256)
+k_goss_draw(unsigned* __restrict__ lcg_state, int n, int K, double top_rate, double other_rate, float* __restrict__ grad,
+            float* __restrict__ hess, uint8_t* __restrict__ in_bag, int* __restrict__ block_count) {
+  __shared__ float s_tg[kBagBlock];
+  __shared__ float s_sorted[kBagBlock];
+  __shared__ uint8_t s_flag[kBagBlock];      // 0 out, 1 top, 2 sampled (amplified)
+  __shared__ int s_left;
+  const int b = blockIdx.x, base = b * kBagBlock, cnt = min(kBagBlock, n - base);
+  for (int j = threadIdx.x; j < kBagBlock; j += blockDim.x) {
+    float t = -1.0f;        // padding sorts last (real values are >= 0)
+    if (j < cnt) {
+      t = 0.0f;
+      for (int k = 0; k < K; ++k) { const size_t id = static_cast<size_t>(k) * n + base + j; t = __fadd_rn(t, fabsf(__fmul_rn(grad[id], hess[id]))); }
+    }
+    s_tg[j] = t; s_sorted[j] = t;
+  }
+  __syncthreads();
+  for (int k = 2; k <= kBagBlock; k <<= 1)            // bitonic sort, descending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < kBagBlock; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = s_sorted[i], c = s_sorted[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < c) : (a > c)) { s_sorted[i] = c; s_sorted[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const int top_k = max(1, static_cast<int>(cnt * top_rate));
+  const int other_k = static_cast<int>(cnt * other_rate);
+  const float multiply = static_cast<float>(cnt - top_k) / other_k;
+  if (threadIdx.x == 0) {
+    const float threshold = s_sorted[top_k - 1];
+    unsigned x = lcg_state[b];
+    int left = 0, big = 0;
+    for (int i = 0; i < cnt; ++i) {
+      uint8_t f = 0;
+      if (s_tg[i] >= threshold) { f = 1; ++left; ++big; }
+      else {
+        const int rest_need = other_k - (left - big), rest_all = (cnt - i) - (top_k - big);
+        const double prob = rest_need / static_cast<double>(rest_all);
+        x = 214013u * x + 2531011u;
+        if (static_cast<double>(d_lcg_float(x)) < prob) { f = 2; ++left; }
+      }
+      s_flag[i] = f;
+    }
+    lcg_state[b] = x;
+    s_left = left;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const uint8_t f = s_flag[j];
+    in_bag[base + j] = f ? 1 : 0;
+    if (f == 2)
+      for (int k = 0; k < K; ++k) { const size_t id = static_cast<size_t>(k) * n + base + j; grad[id] = __fmul_rn(grad[id], multiply); hess[id] = __fmul_rn(hess[id], multiply); }
+  }
+  if (threadIdx.x == 0) block_count[b] = s_left;
+}
+
+// exclusive scan of the per-block in-bag counts (single CTA), total -> *bag_total
+__global__ void __launch_bounds__(1024)
+k_bag_scan(int* __restrict__ block_count, int nblocks, int* __restrict__ bag_total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? block_count[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = s_warp[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += t; }
+      s_warp[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+    const int carry = s_carry;
+    if (i < nblocks) block_count[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *bag_total = s_carry;
+}
+// ordered compaction: bag_idx[offset(block) + rank-in-block] = row
+__global__ void __launch_bounds__(256)
+k_bag_compact(const uint8_t* __restrict__ in_bag, const int* __restrict__ block_offset, int n, int* __restrict__ bag_idx) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x, base = b * kBagBlock, cnt = min(kBagBlock, n - base);
+  if (threadIdx.x == 0) s_base = block_offset[b];
+  __syncthreads();
+  for (int j0 = 0; j0 < cnt; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const int take = (j < cnt) ? in_bag[base + j] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (take) bag_idx[off + __popc(m & ((1u << lane) - 1u))] = base + j;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
+    __syncthreads();
   }
 }
 

@@ -77,6 +77,8 @@ struct Config {
   double alpha = 0.9, fair_c = 1.0, poisson_max_delta_step = 0.7, tweedie_variance_power = 1.5;
   int max_cat_threshold = 32, max_cat_to_onehot = 4, min_data_per_group = 100;
   double cat_l2 = 10.0, cat_smooth = 10.0;
+  double bagging_fraction = 1.0, top_rate = 0.2, other_rate = 0.1;
+  int bagging_freq = 0, bagging_seed = 3;
   std::string tree_learner = "serial";
   int verbosity = 1;
   std::map<std::string, std::string> raw;
@@ -144,6 +146,10 @@ struct Config {
     getd("tweedie_variance_power", tweedie_variance_power);
     geti("max_cat_threshold", max_cat_threshold); geti("max_cat_to_onehot", max_cat_to_onehot); geti("min_data_per_group", min_data_per_group);
     getd("cat_l2", cat_l2); getd("cat_smooth", cat_smooth);
+    getd("bagging_fraction", bagging_fraction); geti("bagging_freq", bagging_freq); geti("bagging_seed", bagging_seed);
+    getd("top_rate", top_rate); getd("other_rate", other_rate);
+    if (boosting == "random_forest") boosting = "rf";
+    if (boosting == "gbrt") boosting = "gbdt";
     auto split_list = [&](const char* k, auto& out, auto conv) {
       auto it = raw.find(k);
       if (it == raw.end() || it->second.empty()) return;
@@ -1144,6 +1150,25 @@ struct Tree {
     cat_threshold_inner.insert(cat_threshold_inner.end(), bits_inner.begin(), bits_inner.end());
     return new_leaf;
   }
+  // traversal on BINNED data (how LightGBM ScoreUpdater::AddScore(tree, cur_tree_id) scores out-of-bag rows): numerical bin <= threshold_in_bin, NaN bin by default_left,
+  // categorical by the inner (bin) bitset
+  template <typename GetBin>
+  int LeafByBins(GetBin bin_of, const std::vector<int>& nan_bin_of_inner) const {
+    if (num_leaves <= 1) return 0;
+    int node = 0;
+    while (node >= 0) {
+      const int f = split_feature_inner[node];
+      const uint32_t bin = bin_of(f);
+      bool left;
+      if (decision_type[node] & 1) {
+        int ci = static_cast<int>(threshold_in_bin[node]);
+        left = FindInBitset(cat_threshold_inner.data() + cat_boundaries_inner[ci], cat_boundaries_inner[ci + 1] - cat_boundaries_inner[ci], static_cast<int>(bin));
+      } else if (((decision_type[node] >> 2) & 3) == kMissNaN && static_cast<int>(bin) == nan_bin_of_inner[f]) left = decision_type[node] & 2;
+      else left = bin <= threshold_in_bin[node];
+      node = left ? left_child[node] : right_child[node];
+    }
+    return ~node;
+  }
   void Shrinkage(double rate) {
     for (int i = 0; i < num_leaves - 1; ++i) { leaf_value[i] = MaybeRoundToZero(leaf_value[i] * rate); internal_value[i] = MaybeRoundToZero(internal_value[i] * rate); }
     leaf_value[num_leaves - 1] = MaybeRoundToZero(leaf_value[num_leaves - 1] * rate);
@@ -1295,7 +1320,7 @@ struct TreeLearner {
     out.assign(static_cast<size_t>(nf) * 512, 0.0);
     const int b = leaf_begin[leaf], cnt = leaf_cnt[leaf];
     const int* rows = idx.data() + b;
-    const bool root = (cnt == ds->n);
+    const bool root = (cnt == ds->n) && rows[0] == 0 && rows[cnt - 1] == cnt - 1;
     if (!root) {
 #pragma omp parallel for schedule(static)
       for (int i = 0; i < cnt; ++i) { og[i] = g[rows[i]]; oh[i] = h[rows[i]]; }
@@ -1336,16 +1361,18 @@ struct TreeLearner {
     for (int u = 0; u < nf; ++u) if (cand[u].feature >= 0 && cand[u].better_than(b)) b = cand[u];
     best[leaf] = b;
   }
-  Tree* Train(const float* g, const float* h) {
+  Tree* Train(const float* g, const float* h, const std::vector<int>* bag = nullptr) {
     const int n = ds->n;
     const int L = cfg.num_leaves;
     Tree* tree = new Tree(L);
-    std::iota(idx.begin(), idx.end(), 0);
-    leaf_begin[0] = 0; leaf_cnt[0] = n; global_cnt[0] = n;
+    int nroot = n;
+    if (bag) { nroot = static_cast<int>(bag->size()); std::copy(bag->begin(), bag->end(), idx.begin()); }   // SetBaggingData: the root holds the in-bag rows
+    else std::iota(idx.begin(), idx.end(), 0);
+    leaf_begin[0] = 0; leaf_cnt[0] = nroot; global_cnt[0] = nroot;
     for (int i = 0; i < L; ++i) best[i] = SplitInfo();
     double sg = 0, sh = 0;
 #pragma omp parallel for schedule(static) reduction(+ : sg, sh)
-    for (int i = 0; i < n; ++i) { sg += g[i]; sh += h[i]; }
+    for (int i = 0; i < nroot; ++i) { sg += g[idx[i]]; sh += h[idx[i]]; }
     leaf_sum_g[0] = sg; leaf_sum_h[0] = sh;
     ResetByTree();
     splittable[0].assign(feature_used.begin(), feature_used.end());
@@ -1464,6 +1491,13 @@ struct Booster {
   bool has_init_score = false;
   double shrinkage_rate = 0.1;
   std::string model_str;
+  // bagging / GOSS / RF  [LightGBM src/boosting/gbdt.cpp Bagging/BaggingHelper, goss.hpp, rf.hpp]
+  std::vector<Random> bagging_rands;        // one LCG per 1024-row block of every rank's shard
+  std::vector<int> block_of_row_base;       // per rank: first block index
+  std::vector<int> bag_idx;
+  bool use_bag = false, need_re_bagging = false, is_rf = false, is_goss = false, average_output = false;
+  std::vector<double> rf_init_scores;
+  std::vector<int> nan_bin_of_inner;
 
   void Init(Dataset* d, const char* params) {
     ds = d;
@@ -1484,6 +1518,107 @@ struct Booster {
     grad.resize(score.size()); hess.resize(score.size());
     class_need_train.assign(K, true);
     for (int k = 0; k < K; ++k) class_need_train[k] = obj->ClassNeedTrain(k);
+    for (int f : d->used) nan_bin_of_inner.push_back(d->mappers[f].missing_type == kMissNaN && !d->mappers[f].is_categorical ? d->mappers[f].num_bin - 1 : -1);
+    is_rf = cfg.boosting == "rf"; is_goss = cfg.boosting == "goss";
+    const bool bagging = cfg.bagging_fraction < 1.0 && cfg.bagging_freq > 0;
+    if (bagging || is_goss) {
+      int blocks = 0;
+      for (int r = 0; r < num_ranks; ++r) {
+        block_of_row_base.push_back(blocks);
+        int nb = (d->rank_rows[r] + 1023) / 1024;
+        for (int i = 0; i < nb; ++i) bagging_rands.emplace_back(cfg.bagging_seed + i);     // every rank seeds its own blocks from bagging_seed
+        blocks += nb;
+      }
+      need_re_bagging = bagging;
+    }
+    if (is_rf) {
+      average_output = true;
+      shrinkage_rate = 1.0;
+      rf_init_scores.assign(K, 0.0);
+      for (int k = 0; k < K; ++k) rf_init_scores[k] = InitScoreValue(k);
+      std::vector<double> tmp(score.size());
+      for (int k = 0; k < K; ++k) std::fill(tmp.begin() + static_cast<size_t>(k) * d->n, tmp.begin() + static_cast<size_t>(k + 1) * d->n, rf_init_scores[k]);
+      obj->GetGradients(tmp.data(), grad.data(), hess.data());      // "only boosting one time"
+    }
+  }
+  double InitScoreValue(int k) {       // BoostFromAverage(k, update_scorer = false)
+    if (models.empty() && !has_init_score && cfg.boost_from_average) {
+      double init;
+      if (num_ranks == 1 || obj->GlobalInitScore()) init = obj->BoostFromScore(k, 0, ds->n);
+      else { double s = 0; int off = 0; for (int r = 0; r < num_ranks; ++r) { s += obj->BoostFromScore(k, off, off + ds->rank_rows[r]); off += ds->rank_rows[r]; } init = s / num_ranks; }
+      if (std::fabs(init) > kEpsilon) return init;
+    }
+    return 0.0;
+  }
+  void Bagging(int it) {
+    const int n = ds->n;
+    if (is_goss) {
+      use_bag = false;
+      if (it < static_cast<int>(1.0f / cfg.learning_rate)) return;      // no subsampling for the first 1/lr iterations
+      bag_idx.clear();
+      int off = 0;
+      for (int r = 0; r < num_ranks; ++r) {
+        const int ln = ds->rank_rows[r];
+        for (int c0 = 0; c0 < ln; c0 += 1024) {          // one chunk per 1024-row block (LightGBM chunks by thread count; this equals it when num_threads >= n/1024)
+          const int cnt = std::min(1024, ln - c0);
+          Random& rnd = bagging_rands[block_of_row_base[r] + c0 / 1024];
+          std::vector<float> tg(cnt, 0.0f);
+          for (int i = 0; i < cnt; ++i)
+            for (int k = 0; k < K; ++k) { size_t id = static_cast<size_t>(k) * n + off + c0 + i; tg[i] += std::fabs(grad[id] * hess[id]); }
+          int top_k = std::max(1, static_cast<int>(cnt * cfg.top_rate));
+          int other_k = static_cast<int>(cnt * cfg.other_rate);
+          std::vector<float> sorted(tg);
+          std::nth_element(sorted.begin(), sorted.begin() + top_k - 1, sorted.end(), std::greater<float>());
+          const float threshold = sorted[top_k - 1];
+          const float multiply = static_cast<float>(cnt - top_k) / other_k;
+          int left = 0, big = 0;
+          for (int i = 0; i < cnt; ++i) {
+            if (tg[i] >= threshold) { bag_idx.push_back(off + c0 + i); ++left; ++big; }
+            else {
+              int sampled = left - big, rest_need = other_k - sampled, rest_all = (cnt - i) - (top_k - big);
+              double prob = rest_need / static_cast<double>(rest_all);
+              if (rnd.NextFloat() < prob) {
+                bag_idx.push_back(off + c0 + i); ++left;
+                for (int k = 0; k < K; ++k) { size_t id = static_cast<size_t>(k) * n + off + c0 + i; grad[id] *= multiply; hess[id] *= multiply; }
+              }
+            }
+          }
+        }
+        off += ln;
+      }
+      use_bag = true;
+      return;
+    }
+    const bool bagging = cfg.bagging_fraction < 1.0 && cfg.bagging_freq > 0;
+    if (!bagging) return;
+    if ((use_bag && it % cfg.bagging_freq == 0) || need_re_bagging) {
+      need_re_bagging = false;
+      bag_idx.clear();
+      int off = 0;
+      for (int r = 0; r < num_ranks; ++r) {
+        for (int i = 0; i < ds->rank_rows[r]; ++i)
+          if (bagging_rands[block_of_row_base[r] + i / 1024].NextFloat() < cfg.bagging_fraction) bag_idx.push_back(off + i);
+        off += ds->rank_rows[r];
+      }
+      use_bag = true;
+    }
+  }
+  void AddTreeToScores(const Tree& t, int k) {        // UpdateScore: in-bag via the partition, out-of-bag by binned traversal == tree(row) for all rows
+    const int n = ds->n;
+    double* sp = &score[static_cast<size_t>(k) * n];
+    if (!use_bag) {
+      for (int l = 0; l < t.num_leaves; ++l) {
+        double v = t.leaf_value[l];
+        int b = learner.leaf_begin[l], c = learner.leaf_cnt[l];
+        for (int i = 0; i < c; ++i) sp[learner.idx[b + i]] += v;
+      }
+      return;
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int leaf = t.LeafByBins([&](int f) { return static_cast<uint32_t>(ds->bins[static_cast<size_t>(f) * n + i]); }, nan_bin_of_inner);
+      sp[i] += t.leaf_value[leaf];
+    }
   }
   double BoostFromAverage(int k) {
     if (models.empty() && !has_init_score && cfg.boost_from_average) {
@@ -1503,35 +1638,51 @@ struct Booster {
     return 0.0;
   }
   bool TrainOneIter() {
-    std::vector<double> init_scores(K, 0.0);
-    for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
-    obj->GetGradients(score.data(), grad.data(), hess.data());
-    bool should_continue = false;
     const int n = ds->n;
+    std::vector<double> init_scores(K, 0.0);
+    if (is_rf) {
+      init_scores = rf_init_scores;
+    } else {
+      for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
+      obj->GetGradients(score.data(), grad.data(), hess.data());
+    }
+    Bagging(iter);
+    bool should_continue = false;
     for (int k = 0; k < K; ++k) {
       std::unique_ptr<Tree> t(new Tree(2));
       if (class_need_train[k] && !ds->used.empty()) {
         learner.cur_tree = static_cast<int>(models.size());
-        t.reset(learner.Train(&grad[static_cast<size_t>(k) * n], &hess[static_cast<size_t>(k) * n]));
+        t.reset(learner.Train(&grad[static_cast<size_t>(k) * n], &hess[static_cast<size_t>(k) * n], use_bag ? &bag_idx : nullptr));
+      }
+      double* sp = &score[static_cast<size_t>(k) * n];
+      if (is_rf) {
+        const double m0 = static_cast<double>(iter), m1 = 1.0 / (iter + 1);
+        if (t->num_leaves > 1) {
+          if (std::fabs(init_scores[k]) > kEpsilon) t->AddBias(init_scores[k]);
+          for (int i = 0; i < n; ++i) sp[i] *= m0;
+          AddTreeToScores(*t, k);
+          for (int i = 0; i < n; ++i) sp[i] *= m1;
+        } else if (models.size() < static_cast<size_t>(K)) {
+          double output = class_need_train[k] ? init_scores[k] : obj->BoostFromScore(k, 0, n);
+          t->AsConstantTree(output);
+          for (int i = 0; i < n; ++i) sp[i] = (sp[i] * m0 + output) * m1;
+        }
+        models.push_back(std::move(t));
+        continue;
       }
       if (t->num_leaves > 1) {
         should_continue = true;
         t->Shrinkage(shrinkage_rate);
-        double* sp = &score[static_cast<size_t>(k) * n];
-        for (int l = 0; l < t->num_leaves; ++l) {
-          double v = t->leaf_value[l];
-          int b = learner.leaf_begin[l], c = learner.leaf_cnt[l];
-          for (int i = 0; i < c; ++i) sp[learner.idx[b + i]] += v;
-        }
+        AddTreeToScores(*t, k);
         if (std::fabs(init_scores[k]) > kEpsilon) t->AddBias(init_scores[k]);
       } else if (models.size() < static_cast<size_t>(K)) {
         double output = class_need_train[k] ? init_scores[k] : obj->BoostFromScore(k, 0, n);
         t->AsConstantTree(output);
-        double* sp = &score[static_cast<size_t>(k) * n];
         for (int i = 0; i < n; ++i) sp[i] += output;
       }
       models.push_back(std::move(t));
     }
+    if (is_rf) { ++iter; return false; }
     if (!should_continue) {
       if (models.size() > static_cast<size_t>(K)) for (int k = 0; k < K; ++k) models.pop_back();
       return true;
@@ -1547,6 +1698,7 @@ struct Booster {
     ss << "label_index=0\n";
     ss << "max_feature_idx=" << ds->F - 1 << '\n';
     ss << "objective=" << obj->ToString() << '\n';
+    if (average_output) ss << "average_output\n";
     ss << "feature_names=";
     for (int f = 0; f < ds->F; ++f) ss << (f ? " " : "") << ds->feature_names[f];
     ss << '\n' << "feature_infos=";
@@ -1665,6 +1817,7 @@ void orc_booster_predict_raw(void* h, const double* X, int nrow, int F, double* 
   for (int i = 0; i < nrow; ++i) {
     for (int k = 0; k < K; ++k) out[static_cast<size_t>(i) * K + k] = 0;
     for (size_t t = 0; t < b->models.size(); ++t) out[static_cast<size_t>(i) * K + (t % K)] += b->models[t]->Predict(X + static_cast<size_t>(i) * F);
+    if (b->average_output && !b->models.empty()) for (int k = 0; k < K; ++k) out[static_cast<size_t>(i) * K + k] /= (b->models.size() / K);
   }
 }
 void orc_booster_hist_stats(void* h, double* seconds, long long* cells) {

@@ -121,3 +121,33 @@ def test_rank_with_single_class_does_not_hang(built):
     res = run_ranks(X, y, [n0, n - n0], _params("binary", 2, "is_unbalance=false"), 5, 23700)
     m = parse_model(res[0]["model"])
     assert len(m["trees"]) == 5 and m["trees"][0]["num_leaves"] > 1
+
+
+@pytest.mark.parametrize("mode", ["bagging", "goss"])
+def test_data_parallel_row_sampling(built, mode, monkeypatch):
+    """Every rank bags its own shard with its own per-block LCGs (seeded bagging_seed + local block); root counts and sums are
+    all-reduced over the in-bag rows only."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("B200GBM_FUSED_REDUCE", "0")
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(321)
+    n, F = 50000, 16
+    X = rng.standard_normal((n, F))
+    s = 1.5 * X[:, 0] + np.sin(2 * X[:, 1]) + X[:, 2] * X[:, 3] + 0.3 * rng.standard_normal(n)
+    y = (s > 0).astype(np.float32)
+    rank_rows = [n // 2 + 333, n - n // 2 - 333]
+    params = _params("binary", 2, "is_unbalance=false")
+    if mode == "bagging":
+        params = params.replace("bagging_fraction=1.0 bagging_freq=0", "bagging_fraction=0.5 bagging_freq=2")
+    else:
+        params = params.replace("boosting_type=gbdt", "boosting_type=goss").replace("learning_rate=0.1", "learning_rate=0.3")
+    res = run_ranks(X, y, rank_rows, params, 8, 23900 + (0 if mode == "bagging" else 11))
+    ods = O.OracleDataset(X, DS_PARAMS, rank_rows=rank_rows).set_field("label", y)
+    ob = O.OracleBooster(ods, params)
+    ob.train(8)
+    assert res[1]["model"] == res[0]["model"]
+    compare_models(parse_model(res[0]["model"]), parse_model(ob.model_string()))
+    got_scores = np.concatenate([res[r]["scores"] for r in range(2)])
+    np.testing.assert_allclose(got_scores, ob.scores(), rtol=1e-6, atol=1e-6)

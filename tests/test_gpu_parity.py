@@ -432,3 +432,95 @@ def test_categorical_too_many_bins_fails_loudly(built):
     with pytest.raises(capi.LightGBMError) as e:
         capi.Dataset.from_mat(X, DS_PARAMS + " categorical_feature=0")
     assert "uint8" in str(e.value)
+
+
+def _sampling_case(rng, n=30000, F=12):
+    X = rng.standard_normal((n, F))
+    X[:, 3] = np.where(rng.random(n) < 0.1, np.nan, X[:, 3])
+    s = 1.2 * X[:, 0] + np.sin(2 * X[:, 1]) + X[:, 2] * np.nan_to_num(X[:, 3]) + 0.4 * rng.standard_normal(n)
+    return X, s
+
+
+@pytest.mark.parametrize("objective,extra", [
+    ("regression", "bagging_fraction=0.6 bagging_freq=2"),
+    ("binary", "bagging_fraction=0.35 bagging_freq=1 bagging_seed=11 is_unbalance=false"),
+    ("multiclass", "num_class=3 bagging_fraction=0.8 bagging_freq=3"),
+])
+def test_bagging(built, objective, extra):
+    """Row bagging: per-1024-row-block LCG draws, the in-bag list is the tree's root, out-of-bag rows are scored
+    by the binned tree walk.  n is not a multiple of 1024 so the last block is partial."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(81)
+    X, s = _sampling_case(rng)
+    y = {"regression": s, "binary": s > 0, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params(objective, "", leaves=15).replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 bagging_seed=3", "") + " " + extra
+    b, ob, m, om = _train_both(ds, ods, params, 9)
+    compare_models(m, om)
+    assert len(m["trees"]) == 9 * (3 if objective == "multiclass" else 1)
+    np.testing.assert_allclose(b.get_scores(0).ravel(), ob.scores().ravel(), rtol=0, atol=1e-9)
+    root_counts = [int(t["internal_count"][0]) for t in m["trees"]]
+    assert max(root_counts) < 0.95 * len(y)        # trees really saw a subsample
+
+
+@pytest.mark.parametrize("objective,extra", [
+    ("binary", "bagging_fraction=0.7 bagging_freq=1 is_unbalance=false"),
+    ("regression", "feature_fraction=0.5"),                       # rf without row bagging: column sampling only
+    ("multiclass", "num_class=3 bagging_fraction=0.5 bagging_freq=1 feature_fraction=0.8"),
+])
+def test_random_forest(built, objective, extra):
+    """boosting_type=rf: gradients fixed at the init score, no shrinkage, average_output model, running-average scores."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(83)
+    X, s = _sampling_case(rng, n=20000)
+    y = {"regression": s + 3.0, "binary": s > 0.5, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params(objective, "", leaves=15).replace("boosting_type=gbdt", "boosting_type=rf")
+    for k in ("bagging_fraction=1.0 ", "bagging_freq=0 ", "feature_fraction=1.0 "):
+        params = params.replace(k, "")
+    params += " " + extra
+    b, ob, m, om = _train_both(ds, ods, params, 8)
+    compare_models(m, om)
+    text = b.save_model_to_string()
+    assert "\naverage_output\n" in text
+    np.testing.assert_allclose(b.get_scores(0).ravel(), ob.scores().ravel(), rtol=0, atol=1e-9)
+    # the model's prediction is the average over the iterations == the training score
+    Xs = X[:2000]
+    raw = b.predict_for_mat(Xs, predict_type=1).reshape(len(Xs), -1)
+    K = raw.shape[1]
+    np.testing.assert_allclose(raw, b.get_scores(0).reshape(K, -1)[:, :2000].T, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(b.predict_device(Xs, predict_type=1).reshape(len(Xs), -1), raw, rtol=0, atol=0)
+
+
+def test_random_forest_needs_subsampling(built):
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((2000, 4))
+    ds, _ = _make(X, X[:, 0].astype(np.float32))
+    with pytest.raises(capi.LightGBMError, match="bagging_freq"):
+        capi.Booster(ds, "objective=regression boosting_type=rf verbosity=-1")
+
+
+@pytest.mark.parametrize("objective,extra", [
+    ("binary", "learning_rate=0.25 is_unbalance=false"),
+    ("multiclass", "num_class=3 learning_rate=0.5 top_rate=0.3 other_rate=0.2"),
+    ("regression", "learning_rate=0.34 top_rate=0.1 other_rate=0.05"),
+])
+def test_goss(built, objective, extra):
+    """boosting_type=goss: full data for the first 1/learning_rate iterations, then top_rate by |g*h| + other_rate sampled with
+    amplified gradients, per 1024-row chunk."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(85)
+    X, s = _sampling_case(rng, n=25000)
+    # no NaN column here: in a leaf whose subsample holds no NaN row the two scan directions have mathematically EQUAL gains, and
+    # with float-amplified gradients the winner (default_left) is decided by summation-order rounding noise (DESIGN.md, ties)
+    X[:, 3] = np.nan_to_num(X[:, 3])
+    y = {"regression": s, "binary": s > 0, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params(objective, "", leaves=15).replace("boosting_type=gbdt", "boosting_type=goss").replace("learning_rate=0.1 ", "") + " " + extra
+    b, ob, m, om = _train_both(ds, ods, params, 9)
+    compare_models(m, om)
+    np.testing.assert_allclose(b.get_scores(0).ravel(), ob.scores().ravel(), rtol=0, atol=1e-9)
+    K = 3 if objective == "multiclass" else 1
+    root_counts = [int(t["internal_count"][0]) for t in m["trees"]]
+    assert root_counts[0] == len(y) and root_counts[-1] < 0.6 * len(y)       # warm-up on all rows, then the GOSS subsample
