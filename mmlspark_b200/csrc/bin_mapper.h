@@ -49,11 +49,11 @@ class LcgRandom {
     }
     return out;
   }
+  float NextFloat() { return static_cast<float>((Step() >> 16) & 0x7FFF) / 32768.0f; }
 
  private:
   unsigned Step() { x_ = 214013u * x_ + 2531011u; return x_; }
   unsigned Next31() { return Step() & 0x7FFFFFFFu; }
-  float NextFloat() { return static_cast<float>((Step() >> 16) & 0x7FFF) / 32768.0f; }
   unsigned x_;
 };
 

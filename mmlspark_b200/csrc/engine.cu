@@ -604,9 +604,10 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   EnsureDevice();
   device_ = CurrentDevice();
   cfg.Parse(params);
-  if (cfg.boosting != "gbdt" && cfg.boosting != "rf" && cfg.boosting != "goss")
-    Fatal("boosting_type=" + cfg.boosting + " is not implemented by this build (gbdt, rf and goss are)");
-  is_rf_ = cfg.boosting == "rf"; is_goss_ = cfg.boosting == "goss";
+  if (cfg.boosting != "gbdt" && cfg.boosting != "rf" && cfg.boosting != "goss" && cfg.boosting != "dart")
+    Fatal("Unknown boosting type " + cfg.boosting);
+  is_rf_ = cfg.boosting == "rf"; is_goss_ = cfg.boosting == "goss"; is_dart_ = cfg.boosting == "dart";
+  drop_rand_ = LcgRandom(cfg.drop_seed);
   {
     static const char* kRegVar[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
     for (int k = 1; k <= 5; ++k) if (cfg.objective == kRegVar[k]) regvar_kind_ = k;
@@ -831,6 +832,97 @@ void Booster::InitTraining() {
     B200_CUDA(cudaStreamSynchronize(stream_));
   }
   B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---- DART [LightGBM src/boosting/dart.hpp]
+TreeDev Booster::RebasedTree(unsigned char* base) const {
+  TreeDev t = tree_dev_;
+  auto mv = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(base + (reinterpret_cast<unsigned char*>(p) - tree_blob_.p)); };
+  mv(t.left_child); mv(t.right_child); mv(t.split_feature_inner); mv(t.threshold_bin); mv(t.decision_type); mv(t.split_gain);
+  mv(t.leaf_value); mv(t.leaf_weight); mv(t.leaf_count); mv(t.internal_value); mv(t.internal_weight); mv(t.internal_count);
+  mv(t.leaf_parent); mv(t.leaf_depth); mv(t.num_leaves); mv(t.cat_bits);
+  return t;
+}
+// ScoreUpdater::AddScore(models_[tree], class): the tree's CURRENT host leaf values (after the Shrinkage calls) are pushed into
+// its stored device blob and every row walks the tree on its bins.
+void Booster::AddStoredTree(int iter_index, int k, bool to_train, bool to_valid) {
+  const size_t ti = static_cast<size_t>(num_init_iteration + iter_index) * K + k;
+  const HostTree& ht = *model.trees[ti];
+  cudaStream_t s = stream_;
+  const int n = train->num_data;
+  if (ht.num_leaves <= 1) {
+    const double v = ht.leaf_value[0];
+    if (v != 0.0) {
+      if (to_train) k_add_const<<<num_sms_ * 4, 256, 0, s>>>(score_.p + static_cast<size_t>(k) * n, n, v);
+      if (to_valid) for (auto* vs : valids_) k_add_const<<<num_sms_ * 4, 256, 0, s>>>(vs->score.p + static_cast<size_t>(k) * vs->ds->num_data, vs->ds->num_data, v);
+    }
+    return;
+  }
+  DevBuf<unsigned char>& blob = *tree_store_.at(static_cast<size_t>(iter_index) * K + k);
+  TreeDev td = RebasedTree(blob.p);
+  B200_CUDA(cudaMemcpyAsync(td.leaf_value, ht.leaf_value.data(), sizeof(double) * ht.num_leaves, cudaMemcpyHostToDevice, s));
+  const int egrid = num_sms_ * 8;
+  if (to_train) k_add_tree_binned<<<egrid, 256, 0, s>>>(td, train->meta.p, train->bins.p, train->rows_stride, n, score_.p + static_cast<size_t>(k) * n, 1.0);
+  if (to_valid)
+    for (auto* vs : valids_)
+      k_add_tree_binned<<<egrid, 256, 0, s>>>(td, vs->ds->meta.p, vs->ds->bins.p, vs->ds->rows_stride, vs->ds->num_data,
+                                              vs->score.p + static_cast<size_t>(k) * vs->ds->num_data, 1.0);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaStreamSynchronize(s));        // the pageable host leaf values must stay put until the copy is done
+  timing.launches += (to_train ? 1 : 0) + (to_valid ? static_cast<long long>(valids_.size()) : 0);
+}
+void Booster::DroppingTrees() {
+  drop_index_.clear();
+  const bool is_skip = drop_rand_.NextFloat() < cfg.skip_drop;
+  if (!is_skip) {
+    double drop_rate = cfg.drop_rate;
+    if (!cfg.uniform_drop) {
+      const double inv_average_weight = static_cast<double>(tree_weight_.size()) / sum_weight_;
+      if (cfg.max_drop > 0) drop_rate = std::min(drop_rate, cfg.max_drop * inv_average_weight / sum_weight_);
+      for (int i = 0; i < iter; ++i)
+        if (drop_rand_.NextFloat() < drop_rate * tree_weight_[i] * inv_average_weight) {
+          drop_index_.push_back(i);
+          if (drop_index_.size() >= static_cast<size_t>(cfg.max_drop)) break;
+        }
+    } else {
+      if (cfg.max_drop > 0) drop_rate = std::min(drop_rate, cfg.max_drop / static_cast<double>(iter));
+      for (int i = 0; i < iter; ++i)
+        if (drop_rand_.NextFloat() < drop_rate) {
+          drop_index_.push_back(i);
+          if (drop_index_.size() >= static_cast<size_t>(cfg.max_drop)) break;
+        }
+    }
+  }
+  for (int i : drop_index_)
+    for (int k = 0; k < K; ++k) {
+      model.trees[static_cast<size_t>(num_init_iteration + i) * K + k]->Shrink(-1.0);
+      AddStoredTree(i, k, true, false);
+    }
+  if (!cfg.xgboost_dart_mode) shrinkage_ = cfg.learning_rate / (1.0f + static_cast<double>(drop_index_.size()));
+  else if (drop_index_.empty()) shrinkage_ = cfg.learning_rate;
+  else shrinkage_ = cfg.learning_rate / (cfg.learning_rate + static_cast<double>(drop_index_.size()));
+  if (!drop_index_.empty()) forest_.reset();
+  dart_dropped_this_iter_ = true;
+}
+void Booster::DartNormalize() {
+  const double k = static_cast<double>(drop_index_.size());
+  for (int i : drop_index_) {
+    for (int c = 0; c < K; ++c) {
+      HostTree& t = *model.trees[static_cast<size_t>(num_init_iteration + i) * K + c];
+      if (!cfg.xgboost_dart_mode) {
+        t.Shrink(1.0f / (k + 1.0f)); AddStoredTree(i, c, false, true);
+        t.Shrink(-k); AddStoredTree(i, c, true, false);
+      } else {
+        t.Shrink(shrinkage_); AddStoredTree(i, c, false, true);
+        t.Shrink(-k / cfg.learning_rate); AddStoredTree(i, c, true, false);
+      }
+    }
+    if (!cfg.uniform_drop) {
+      if (!cfg.xgboost_dart_mode) { sum_weight_ -= tree_weight_[i] * (1.0f / (k + 1.0f)); tree_weight_[i] *= (k / (k + 1.0f)); }
+      else { sum_weight_ -= tree_weight_[i] * (1.0f / (k + cfg.learning_rate)); tree_weight_[i] *= (k / (k + cfg.learning_rate)); }
+    }
+  }
+  if (!drop_index_.empty()) forest_.reset();        // leaf values of earlier trees changed: the device forest for predict is stale
 }
 
 // [LightGBM gbdt.cpp GBDT::Bagging / goss.hpp GOSS::Bagging] draws the in-bag flags on the device, compacts the in-bag rows
@@ -1136,6 +1228,7 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
     init_scores = rf_init_scores_;
   } else if (!custom_g) {
     for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
+    if (is_dart_ && !dart_dropped_this_iter_) DroppingTrees();      // GetTrainingScore() in GBDT::Boosting: "only drop one time in one iteration"
     ComputeGradients();
   } else {
     grad_.Upload(custom_g, static_cast<size_t>(K) * n, s);
@@ -1163,6 +1256,11 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
       t->MakeConstant(0.0);
     }
     model.trees.push_back(std::move(t));
+    if (is_dart_) {       // keep the device form of the tree (bin thresholds, inner bitsets) for later drops
+      tree_store_.emplace_back(new DevBuf<unsigned char>());
+      tree_store_.back()->Alloc(tree_blob_bytes_);
+      B200_CUDA(cudaMemcpyAsync(tree_store_.back()->p, tree_blob_.p, tree_blob_bytes_, cudaMemcpyDeviceToDevice, s));
+    }
   }
   const_hessian_ = saved_const;
   B200_CUDA(cudaEventRecord(ev_b_, s));
@@ -1170,11 +1268,16 @@ bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
   float ms = 0;
   B200_CUDA(cudaEventElapsedTime(&ms, ev_a_, ev_b_));
   timing.total_ms += ms;
+  dart_dropped_this_iter_ = false;
   if (!should_continue) {
-    if (static_cast<int>(model.trees.size()) > K) for (int k = 0; k < K; ++k) model.trees.pop_back();
+    if (static_cast<int>(model.trees.size()) > K) for (int k = 0; k < K; ++k) { model.trees.pop_back(); if (is_dart_) tree_store_.pop_back(); }
     return true;
   }
   ++iter;
+  if (is_dart_) {
+    DartNormalize();
+    if (!cfg.uniform_drop) { tree_weight_.push_back(shrinkage_); sum_weight_ += shrinkage_; }
+  }
   return false;
 }
 
@@ -1189,6 +1292,7 @@ void Booster::ResetParameter(const char* params) {
   cfg.Refresh();
   cfg.num_machines = keep_machines;
   shrinkage_ = is_rf_ ? 1.0 : cfg.learning_rate;
+  if (is_dart_) { drop_rand_ = LcgRandom(cfg.drop_seed); sum_weight_ = 0.0; }      // [LightGBM dart.hpp DART::ResetConfig]
   sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step; sp_.min_gain_to_split = cfg.min_gain_to_split;
   sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf; sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth;
 }
@@ -1281,6 +1385,7 @@ int64_t Booster::NumPredict(int data_idx) const {
 }
 void Booster::GetPredict(int data_idx, int64_t* out_len, double* out) {
   EnsureDevice();
+  if (is_dart_ && data_idx == 0 && !dart_dropped_this_iter_) DroppingTrees();      // DART::GetTrainingScore
   const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
   const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
   const int n = ds->num_data;

@@ -194,6 +194,17 @@ class Booster {
   std::vector<double> rf_init_scores_;
   void Bagging(int it);
   void ComputeGradientsAt(const double* score);
+  // DART: every trained tree keeps its device blob so dropped trees can be re-applied to the binned data
+  bool is_dart_ = false, dart_dropped_this_iter_ = false;
+  LcgRandom drop_rand_{4};
+  std::vector<int> drop_index_;
+  std::vector<double> tree_weight_;
+  double sum_weight_ = 0.0;
+  std::vector<std::unique_ptr<DevBuf<unsigned char>>> tree_store_;     // [iteration * K + class]
+  void DroppingTrees();
+  void DartNormalize();
+  void AddStoredTree(int iter_index, int class_id, bool to_train, bool to_valid);
+  TreeDev RebasedTree(unsigned char* base) const;
   SplitParams sp_{};
   // device state
   DevBuf<double> score_;        // [K][n]

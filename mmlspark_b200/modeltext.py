@@ -67,4 +67,6 @@ def compare_models(a, b, value_tol=1e-5, gain_tol=1e-5, check_counts=True):
             np.testing.assert_allclose(ta["split_gain"], tb["split_gain"], rtol=max(gain_tol, 2e-6), atol=1e-12, err_msg="tree %d split_gain" % ti)
             np.testing.assert_allclose(ta["leaf_weight"], tb["leaf_weight"], rtol=value_tol, atol=1e-9, err_msg="tree %d leaf_weight" % ti)
         np.testing.assert_allclose(ta["leaf_value"], tb["leaf_value"], rtol=value_tol, atol=1e-9, err_msg="tree %d leaf_value" % ti)
+        if "shrinkage" in ta and "shrinkage" in tb:
+            np.testing.assert_allclose(float(ta["shrinkage"]), float(tb["shrinkage"]), rtol=1e-9, err_msg="tree %d shrinkage" % ti)
     return True

@@ -79,6 +79,9 @@ struct Config {
   double cat_l2 = 10.0, cat_smooth = 10.0;
   double bagging_fraction = 1.0, top_rate = 0.2, other_rate = 0.1;
   int bagging_freq = 0, bagging_seed = 3;
+  double drop_rate = 0.1, skip_drop = 0.5;
+  int max_drop = 50, drop_seed = 4;
+  bool uniform_drop = false, xgboost_dart_mode = false;
   std::string tree_learner = "serial";
   int verbosity = 1;
   std::map<std::string, std::string> raw;
@@ -148,6 +151,8 @@ struct Config {
     getd("cat_l2", cat_l2); getd("cat_smooth", cat_smooth);
     getd("bagging_fraction", bagging_fraction); geti("bagging_freq", bagging_freq); geti("bagging_seed", bagging_seed);
     getd("top_rate", top_rate); getd("other_rate", other_rate);
+    getd("drop_rate", drop_rate); getd("skip_drop", skip_drop); geti("max_drop", max_drop); geti("drop_seed", drop_seed);
+    getb("uniform_drop", uniform_drop); getb("xgboost_dart_mode", xgboost_dart_mode);
     if (boosting == "random_forest") boosting = "rf";
     if (boosting == "gbrt") boosting = "gbdt";
     auto split_list = [&](const char* k, auto& out, auto conv) {
@@ -1498,6 +1503,12 @@ struct Booster {
   bool use_bag = false, need_re_bagging = false, is_rf = false, is_goss = false, average_output = false;
   std::vector<double> rf_init_scores;
   std::vector<int> nan_bin_of_inner;
+  // DART [LightGBM src/boosting/dart.hpp]
+  bool is_dart = false;
+  Random random_for_drop{4};
+  std::vector<int> drop_index;
+  std::vector<double> tree_weight;
+  double sum_weight = 0.0;
 
   void Init(Dataset* d, const char* params) {
     ds = d;
@@ -1519,7 +1530,8 @@ struct Booster {
     class_need_train.assign(K, true);
     for (int k = 0; k < K; ++k) class_need_train[k] = obj->ClassNeedTrain(k);
     for (int f : d->used) nan_bin_of_inner.push_back(d->mappers[f].missing_type == kMissNaN && !d->mappers[f].is_categorical ? d->mappers[f].num_bin - 1 : -1);
-    is_rf = cfg.boosting == "rf"; is_goss = cfg.boosting == "goss";
+    is_rf = cfg.boosting == "rf"; is_goss = cfg.boosting == "goss"; is_dart = cfg.boosting == "dart";
+    random_for_drop = Random(cfg.drop_seed);
     const bool bagging = cfg.bagging_fraction < 1.0 && cfg.bagging_freq > 0;
     if (bagging || is_goss) {
       int blocks = 0;
@@ -1603,6 +1615,60 @@ struct Booster {
       use_bag = true;
     }
   }
+  // ScoreUpdater::AddScore(tree, cur_tree_id) for an arbitrary stored tree: every row walks the tree on its bins
+  void AddStoredTree(const Tree& t, int k) {
+    const int n = ds->n;
+    double* sp = &score[static_cast<size_t>(k) * n];
+    if (t.num_leaves <= 1) { if (t.leaf_value[0] != 0.0) for (int i = 0; i < n; ++i) sp[i] += t.leaf_value[0]; return; }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int leaf = t.LeafByBins([&](int f) { return static_cast<uint32_t>(ds->bins[static_cast<size_t>(f) * n + i]); }, nan_bin_of_inner);
+      sp[i] += t.leaf_value[leaf];
+    }
+  }
+  void DroppingTrees() {       // DART::DroppingTrees
+    drop_index.clear();
+    bool is_skip = random_for_drop.NextFloat() < cfg.skip_drop;
+    if (!is_skip) {
+      double drop_rate = cfg.drop_rate;
+      if (!cfg.uniform_drop) {
+        double inv_average_weight = static_cast<double>(tree_weight.size()) / sum_weight;
+        if (cfg.max_drop > 0) drop_rate = std::min(drop_rate, cfg.max_drop * inv_average_weight / sum_weight);
+        for (int i = 0; i < iter; ++i)
+          if (random_for_drop.NextFloat() < drop_rate * tree_weight[i] * inv_average_weight) {
+            drop_index.push_back(i);
+            if (drop_index.size() >= static_cast<size_t>(cfg.max_drop)) break;
+          }
+      } else {
+        if (cfg.max_drop > 0) drop_rate = std::min(drop_rate, cfg.max_drop / static_cast<double>(iter));
+        for (int i = 0; i < iter; ++i)
+          if (random_for_drop.NextFloat() < drop_rate) {
+            drop_index.push_back(i);
+            if (drop_index.size() >= static_cast<size_t>(cfg.max_drop)) break;
+          }
+      }
+    }
+    for (int i : drop_index)
+      for (int k = 0; k < K; ++k) { Tree& t = *models[static_cast<size_t>(i) * K + k]; t.Shrinkage(-1.0); AddStoredTree(t, k); }
+    if (!cfg.xgboost_dart_mode) shrinkage_rate = cfg.learning_rate / (1.0f + static_cast<double>(drop_index.size()));
+    else if (drop_index.empty()) shrinkage_rate = cfg.learning_rate;
+    else shrinkage_rate = cfg.learning_rate / (cfg.learning_rate + static_cast<double>(drop_index.size()));
+  }
+  void Normalize() {           // DART::Normalize (train scores only; the oracle holds no validation sets)
+    const double k = static_cast<double>(drop_index.size());
+    for (int i : drop_index) {
+      for (int c = 0; c < K; ++c) {
+        Tree& t = *models[static_cast<size_t>(i) * K + c];
+        if (!cfg.xgboost_dart_mode) { t.Shrinkage(1.0f / (k + 1.0f)); t.Shrinkage(-k); }
+        else { t.Shrinkage(shrinkage_rate); t.Shrinkage(-k / cfg.learning_rate); }
+        AddStoredTree(t, c);
+      }
+      if (!cfg.uniform_drop) {
+        if (!cfg.xgboost_dart_mode) { sum_weight -= tree_weight[i] * (1.0f / (k + 1.0f)); tree_weight[i] *= (k / (k + 1.0f)); }
+        else { sum_weight -= tree_weight[i] * (1.0f / (k + cfg.learning_rate)); tree_weight[i] *= (k / (k + cfg.learning_rate)); }
+      }
+    }
+  }
   void AddTreeToScores(const Tree& t, int k) {        // UpdateScore: in-bag via the partition, out-of-bag by binned traversal == tree(row) for all rows
     const int n = ds->n;
     double* sp = &score[static_cast<size_t>(k) * n];
@@ -1644,6 +1710,7 @@ struct Booster {
       init_scores = rf_init_scores;
     } else {
       for (int k = 0; k < K; ++k) init_scores[k] = BoostFromAverage(k);
+      if (is_dart) DroppingTrees();        // GetTrainingScore() inside Boosting(): drop before the gradients are taken
       obj->GetGradients(score.data(), grad.data(), hess.data());
     }
     Bagging(iter);
@@ -1688,6 +1755,10 @@ struct Booster {
       return true;
     }
     ++iter;
+    if (is_dart) {
+      Normalize();
+      if (!cfg.uniform_drop) { tree_weight.push_back(shrinkage_rate); sum_weight += shrinkage_rate; }
+    }
     return false;
   }
   std::string ModelToString() const {
@@ -1780,7 +1851,12 @@ void* orc_booster_create(void* ds, const char* params) {
 }
 void orc_booster_free(void* h) { delete static_cast<Booster*>(h); }
 int orc_booster_update(void* h) { return static_cast<Booster*>(h)->TrainOneIter() ? 1 : 0; }
-void orc_booster_reset_learning_rate(void* h, double lr) { static_cast<Booster*>(h)->shrinkage_rate = lr; }
+void orc_booster_reset_learning_rate(void* h, double lr) {      // GBDT::ResetConfig (+ DART::ResetConfig: drop RNG and sum_weight_ restart)
+  Booster* b = static_cast<Booster*>(h);
+  b->cfg.learning_rate = lr;
+  if (!b->is_rf) b->shrinkage_rate = lr;
+  if (b->is_dart) { b->random_for_drop = Random(b->cfg.drop_seed); b->sum_weight = 0.0; }
+}
 int orc_booster_num_trees(void* h) { return static_cast<int>(static_cast<Booster*>(h)->models.size()); }
 const char* orc_booster_model_string(void* h) {
   Booster* b = static_cast<Booster*>(h);

@@ -41,8 +41,16 @@ def main():
         ("binary", "objective=binary num_leaves=7 learning_rate=0.1 min_data_in_leaf=20 verbosity=-1 is_unbalance=false", (s > 0).astype(np.float32)),
         ("multiclass", "objective=multiclass num_class=3 num_leaves=5 learning_rate=0.1 min_data_in_leaf=20 verbosity=-1",
          np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)),
+        # row-sampling modes and categorical splits (name prefix = label kind; optional dataset parameters after '|')
+        ("regression_bagging", "objective=regression num_leaves=7 min_data_in_leaf=20 verbosity=-1 bagging_fraction=0.6 bagging_freq=2", s.astype(np.float32)),
+        ("binary_rf", "objective=binary boosting_type=rf num_leaves=7 min_data_in_leaf=20 verbosity=-1 bagging_fraction=0.7 bagging_freq=1 feature_fraction=0.8",
+         (s > 0).astype(np.float32)),
+        ("binary_goss", "objective=binary boosting_type=goss learning_rate=0.5 num_leaves=7 min_data_in_leaf=20 verbosity=-1", (s > 0).astype(np.float32)),
+        ("binary_dart", "objective=binary boosting_type=dart drop_rate=0.5 skip_drop=0.0 num_leaves=7 min_data_in_leaf=20 verbosity=-1", (s > 0).astype(np.float32)),
+        ("regression_categorical|categorical_feature=4", "objective=regression num_leaves=7 min_data_in_leaf=20 verbosity=-1 min_data_per_group=50 cat_smooth=5",
+         s.astype(np.float32)),
     ]:
-        d = O.OracleDataset(X, DS_PARAMS).set_field("label", y)
+        d = O.OracleDataset(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", y)
         b = O.OracleBooster(d, params)
         b.train(5)
         models[name] = {"params": params, "model": b.model_string(), "raw_pred_first8": b.predict_raw(X[:8]).tolist()}

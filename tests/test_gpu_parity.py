@@ -524,3 +524,61 @@ def test_goss(built, objective, extra):
     K = 3 if objective == "multiclass" else 1
     root_counts = [int(t["internal_count"][0]) for t in m["trees"]]
     assert root_counts[0] == len(y) and root_counts[-1] < 0.6 * len(y)       # warm-up on all rows, then the GOSS subsample
+
+
+def test_cuda_path_reproduces_committed_golden_models(built):
+    """The committed fixtures (tests/golden/oracle_golden.json, generated by make_golden.py) are reproduced by the CUDA path
+    without running the oracle: regression / binary / multiclass / bagging / rf / goss / categorical, 5 iterations each."""
+    import importlib.util
+    import json
+    import os
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_data", os.path.join(here, "golden", "make_golden.py"))
+    golden = json.load(open(os.path.join(here, "golden", "oracle_golden.json")))["models"]
+    # make_golden imports the oracle at module level only to GENERATE; here just its seeded dataset() is used
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    X, s = mg.dataset(123, 2000, 10)
+    labels = {"regression": s.astype(np.float32), "binary": (s > 0).astype(np.float32), "multiclass": np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)}
+    assert len(golden) >= 7
+    for name, g in golden.items():
+        ds = capi.Dataset.from_mat(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else ""))
+        ds.set_field("label", labels[name.split("_")[0].split("|")[0]])
+        b = capi.Booster(ds, g["params"])
+        for _ in range(5):
+            b.update_one_iter()
+        compare_models(parse_model(b.save_model_to_string()), parse_model(g["model"]))
+        raw = b.predict_for_mat(X[:8], predict_type=1).reshape(8, -1)
+        np.testing.assert_allclose(raw, np.array(g["raw_pred_first8"]).reshape(8, -1), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("objective,extra", [
+    ("regression", ""),                                                              # native defaults: drop_rate 0.1, skip_drop 0.5, max_drop 50
+    ("binary", "uniform_drop=true drop_rate=0.3 skip_drop=0.2 is_unbalance=false"),
+    ("binary", "xgboost_dart_mode=true drop_rate=0.5 skip_drop=0.0 max_drop=3 is_unbalance=false"),
+    ("multiclass", "num_class=3 drop_rate=0.4 skip_drop=0.1 bagging_fraction=0.7 bagging_freq=1"),
+])
+def test_dart(built, objective, extra):
+    """boosting_type=dart: dropped trees are negated and re-applied to the binned training rows before the gradients are taken,
+    the new tree is shrunk by lr/(1+k), then the dropped trees are re-normalised (their stored leaf values change in the model)."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(87)
+    X, s = _sampling_case(rng, n=20000)
+    y = {"regression": s, "binary": s > 0, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
+    ds, ods = _make(X, y)
+    params = _classifier_params(objective, "", leaves=15).replace("boosting_type=gbdt", "boosting_type=dart")
+    if "bagging_fraction" in extra:
+        params = params.replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 ", "")
+    params += " " + extra
+    b, ob, m, om = _train_both(ds, ods, params, 25)
+    compare_models(m, om)
+    np.testing.assert_allclose(b.get_scores(0).ravel(), ob.scores().ravel(), rtol=0, atol=1e-8)
+    shr = np.array([float(t["shrinkage"]) for t in m["trees"]])
+    assert len(np.unique(np.round(shr, 12))) > 2        # trees were dropped and re-normalised
+    # model prediction == training score (drops are fully accounted for), host and device predictors
+    Xs = X[:3000]
+    raw = b.predict_for_mat(Xs, predict_type=1).reshape(len(Xs), -1)
+    K = raw.shape[1]
+    np.testing.assert_allclose(raw, b.get_scores(0).reshape(K, -1)[:, :3000].T, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(b.predict_device(Xs, predict_type=1).reshape(len(Xs), -1), raw, rtol=0, atol=0)

@@ -211,7 +211,7 @@ def test_golden_models(O):
     labels = {"regression": s.astype(np.float32), "binary": (s > 0).astype(np.float32), "multiclass": np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)}
     from mmlspark_b200.modeltext import parse_model, compare_models
     for name, g in GOLDEN["models"].items():
-        d = O.OracleDataset(X, DS_PARAMS).set_field("label", labels[name])
+        d = O.OracleDataset(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", labels[name.split("_")[0].split("|")[0]])
         b = O.OracleBooster(d, g["params"])
         b.train(5)
         compare_models(parse_model(b.model_string()), parse_model(g["model"]), value_tol=1e-12, gain_tol=1e-6)
