@@ -166,17 +166,30 @@ class Params:
     def isSet(self, name):
         return name in self._values
 
+    def _param_of_accessor(self, suffix):
+        # setNumLeaves -> numLeaves; acronym setters like setXGBoostDartMode -> xgboostDartMode (LightGBMParams.scala:176-180)
+        name = suffix[0].lower() + suffix[1:]
+        if name in self._defaults:
+            return name
+        low = suffix.lower()
+        for k in self._defaults:
+            if k.lower() == low:
+                return k
+        return None
+
     def __getattr__(self, item):
+        if item.startswith("_"):
+            raise AttributeError(item)
         if item.startswith("set") and len(item) > 3:
-            name = item[3].lower() + item[4:]
-            if name in self._defaults:
+            name = self._param_of_accessor(item[3:])
+            if name is not None:
                 def setter(value, _n=name):
                     self._values[_n] = value
                     return self
                 return setter
         if item.startswith("get") and len(item) > 3:
-            name = item[3].lower() + item[4:]
-            if name in self._defaults:
+            name = self._param_of_accessor(item[3:])
+            if name is not None:
                 return lambda _n=name: self.get(_n)
         raise AttributeError(item)
 

@@ -223,3 +223,70 @@ def test_two_tasks_two_gpus(built):
     a2 = _auc(df["label"], m2.transform(df)["probability"][:, 1])
     a1 = _auc(df["label"], m1.transform(df)["probability"][:, 1])
     assert abs(a1 - a2) < 0.01 and a2 > 0.85
+
+
+BOOSTING_TYPES = ["gbdt", "rf", "dart", "goss"]          # VerifyLightGBMClassifier.scala:135
+
+
+def _with_boosting(est, boosting_type):
+    est.setBoostingType(boosting_type)
+    if boosting_type == "rf":                             # VerifyLightGBMClassifier.scala:655-658
+        est.setBaggingFraction(0.9)
+        est.setBaggingFreq(1)
+    return est
+
+
+def test_classifier_all_boosting_types(built):
+    """'can be trained and scored on <file>' sweeps boostingTypes (VerifyLightGBMClassifier.scala:644-668): probabilities are
+    well-formed, importances have one entry per feature, the model is better than chance."""
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(3)
+    aucs = {}
+    for bt in BOOSTING_TYPES:
+        model = _with_boosting(LightGBMClassifier(numIterations=25, numLeaves=15, numTasks=1), bt).fit(df)
+        out = model.transform(df)
+        np.testing.assert_allclose(out["probability"].sum(axis=1), 1.0, atol=1e-12)
+        assert len(model.getFeatureImportances("split")) == 12 and len(model.getFeatureImportances("gain")) == 12
+        aucs[bt] = _auc(df["label"], out["probability"][:, 1])
+        assert ("boosting: %s]" % bt) in model.getNativeModel()
+    assert all(a > 0.8 for a in aucs.values()), aucs
+    assert "average_output" in _with_boosting(LightGBMClassifier(numIterations=3, numTasks=1), "rf").fit(df).getNativeModel()
+
+
+def test_multiclass_and_regressor_all_boosting_types(built):
+    """VerifyLightGBMClassifier.scala:676-705 (multiclass sweep) and VerifyLightGBMRegressor.scala:188-207 (regression sweep)."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier, LightGBMRegressor
+    rng = np.random.default_rng(12)
+    n, F = 15000, 8
+    X = rng.standard_normal((n, F))
+    s = 2 * X[:, 0] + X[:, 1] * X[:, 2] + 0.4 * rng.standard_normal(n)
+    ycls = np.digitize(s, [-1.0, 1.0]).astype(np.float64)
+    dfc, dfr = Frame({"features": X, "label": ycls}), Frame({"features": X, "label": s})
+    for bt in BOOSTING_TYPES:
+        mc = _with_boosting(LightGBMClassifier(objective="multiclass", numIterations=15, numLeaves=15, numTasks=1), bt).fit(dfc)
+        out = mc.transform(dfc)
+        assert out["probability"].shape == (n, 3)
+        np.testing.assert_allclose(out["probability"].sum(axis=1), 1.0, atol=1e-12)
+        assert float(np.mean(out["prediction"] == ycls)) > 0.7, bt
+        mr = _with_boosting(LightGBMRegressor(numIterations=30, numLeaves=15, numTasks=1), bt).fit(dfr)
+        rmse = float(np.sqrt(np.mean((mr.transform(dfr)["prediction"] - s) ** 2)))
+        assert rmse < 0.75 * float(np.std(s)), (bt, rmse)
+        assert len(mr.getFeatureImportances("split")) == F
+
+
+def test_dart_mode_parameters(built):
+    """'Verify LightGBM Classifier with dart mode parameters' (VerifyLightGBMClassifier.scala:352-368): the dart knobs are accepted,
+    reach the engine (parameter block) and change the model."""
+    from mmlspark_b200.lightgbm import LightGBMClassifier
+    df = _binary_frame(4)
+    m1 = LightGBMClassifier(numIterations=40, numLeaves=15, numTasks=1).setBoostingType("dart").setSkipDrop(1.0).fit(df)
+    m2 = (LightGBMClassifier(numIterations=40, numLeaves=15, numTasks=1).setBoostingType("dart").setXGBoostDartMode(True).setDropRate(0.6)
+          .setMaxDrop(60).setSkipDrop(0.4).setUniformDrop(True).fit(df))
+    s1, s2 = m1.getNativeModel(), m2.getNativeModel()
+    assert "[skip_drop: 1]" in s1 and "[xgboost_dart_mode: 1]" in s2 and "[drop_rate: 0.6]" in s2 and "[max_drop: 60]" in s2 and "[uniform_drop: 1]" in s2
+    p1, p2 = m1.transform(df)["probability"][:, 1], m2.transform(df)["probability"][:, 1]
+    assert _auc(df["label"], p1) > 0.85 and _auc(df["label"], p2) > 0.85
+    assert np.abs(p1 - p2).max() > 1e-3
+    # skip_drop = 1 never drops => identical to plain gbdt
+    m0 = LightGBMClassifier(numIterations=40, numLeaves=15, numTasks=1).fit(df)
+    np.testing.assert_allclose(m0.transform(df)["probability"], m1.transform(df)["probability"], rtol=0, atol=1e-12)
