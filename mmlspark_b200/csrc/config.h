@@ -103,6 +103,8 @@ struct Config {
       return "regression";
     if (o == "softmax") return "multiclass";
     if (o == "rank" ) return "lambdarank";
+    if (o == "l1" || o == "mean_absolute_error" || o == "mae") return "regression_l1";
+    if (o == "mean_absolute_percentage_error") return "mape";
     return o;
   }
   static std::string CanonMetric(const std::string& m) {
@@ -115,6 +117,7 @@ struct Config {
       return "multi_logloss";
     if (m == "ndcg" || m == "lambdarank" || m == "rank_xendcg" || m == "xendcg") return "ndcg";
     if (m == "map" || m == "mean_average_precision") return "map";
+    if (m == "mean_absolute_percentage_error") return "mape";
     return m;
   }
   void Set(const std::map<std::string, std::string>& kv) {

@@ -1,6 +1,7 @@
 // b200gbm engine implementation: network bootstrap, dataset ingestion/binning, GBDT driver and the
 // device-resident leaf-wise tree learner.  See engine.h / kernels.cuh / hist_kernel.cuh.
 #include "engine.h"
+#include "renew_kernel.cuh"
 
 #include <arpa/inet.h>
 #include <netdb.h>
@@ -589,6 +590,37 @@ void Dataset::SetFeatureNames(const char** names, int n) {
   }
 }
 
+// ---- host percentiles for the init score of regression_l1 / quantile / mape
+// [LightGBM regression_objective.hpp PercentileFun / WeightedPercentileFun, T = label_t]: the alpha percentile counted from the
+// top of the descending order, position (cnt-1)(1-alpha), linear interpolation; weighted: upper_bound on the running weight sum.
+static float LabelPercentile(const float* y, int cnt, double alpha) {
+  if (cnt <= 1) return y[0];
+  const double float_pos = static_cast<double>(cnt - 1) * (1.0 - alpha);
+  const int pos = static_cast<int>(float_pos);
+  if (pos < 1) return *std::max_element(y, y + cnt);
+  if (pos >= cnt) return *std::min_element(y, y + cnt);
+  std::vector<float> v(y, y + cnt);
+  std::nth_element(v.begin(), v.begin() + pos, v.end(), std::greater<float>());
+  const float v2 = v[pos], v1 = *std::min_element(v.begin(), v.begin() + pos);
+  return static_cast<float>(v1 - (v1 - v2) * (float_pos - pos));
+}
+static float LabelWeightedPercentile(const float* y, const float* w, int cnt, double alpha) {
+  if (cnt <= 1) return y[0];
+  std::vector<int> order(cnt);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return y[a] < y[b]; });
+  std::vector<double> cdf(cnt);
+  cdf[0] = w[order[0]];
+  for (int i = 1; i < cnt; ++i) cdf[i] = cdf[i - 1] + w[order[i]];
+  const double threshold = cdf[cnt - 1] * alpha;
+  size_t pos = std::upper_bound(cdf.begin(), cdf.end(), threshold) - cdf.begin();
+  pos = std::min(pos, static_cast<size_t>(cnt - 1));
+  if (pos == 0 || pos == static_cast<size_t>(cnt - 1)) return y[order[pos]];
+  const float v1 = y[order[pos - 1]], v2 = y[order[pos]];
+  if (cdf[pos + 1] - cdf[pos] >= 1.0f) return static_cast<float>((threshold - cdf[pos]) / (cdf[pos + 1] - cdf[pos]) * (v2 - v1) + v1);
+  return v2;
+}
+
 // =============================================================================== booster
 static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 constexpr int kScanSmem = 8 * (768 + 32) * 8;     // k_scan: per-warp scratch of the categorical split search
@@ -612,9 +644,12 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
     static const char* kRegVar[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
     for (int k = 1; k <= 5; ++k) if (cfg.objective == kRegVar[k]) regvar_kind_ = k;
   }
-  if (cfg.objective == "regression_l1" || cfg.objective == "l1" || cfg.objective == "quantile" || cfg.objective == "mape")
-    Fatal("objective=" + cfg.objective + " needs leaf-output renewal (weighted percentiles), which this build does not implement yet");
-  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_)
+  if (cfg.objective == "regression_l1") renew_kind_ = 1;
+  else if (cfg.objective == "quantile") renew_kind_ = 2;
+  else if (cfg.objective == "mape") renew_kind_ = 3;
+  if (renew_kind_ == 2 && !(cfg.alpha > 0.0 && cfg.alpha < 1.0)) Fatal("Check failed: alpha_ > 0 && alpha_ < 1");
+  renew_alpha_ = renew_kind_ == 2 ? static_cast<double>(static_cast<float>(cfg.alpha)) : 0.5;     // quantile keeps alpha as score_t
+  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_ && !renew_kind_)
     Fatal("Unknown/unsupported objective type name: " + cfg.objective);
   if (cfg.bagging_freq > 0 && (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
     Fatal("balanced bagging (pos_/neg_bagging_fraction) is not implemented by this build");
@@ -734,6 +769,25 @@ void Booster::InitTraining() {
     const_hessian_ = train->weight.empty() && !is_goss_;      // GOSS amplifies hessians [LightGBM goss.hpp GetIsConstHessian -> false]
   } else if (regvar_kind_) {
     if (regvar_kind_ >= 3) for (int i = 0; i < n; ++i) if (train->label[i] < 0) Fatal("[" + cfg.objective + "]: at least one target label is negative");
+  } else if (renew_kind_) {
+    const_hessian_ = train->weight.empty() && !is_goss_;
+    if (renew_kind_ == 3) {       // [LightGBM RegressionMAPELOSS::Init] label_weight = 1 / max(1, |label|) (* weight)
+      label_weight_host_.resize(n);
+      for (int i = 0; i < n; ++i) {
+        label_weight_host_[i] = 1.0f / std::max(1.0f, std::fabs(train->label[i]));
+        if (!train->weight.empty()) label_weight_host_[i] *= train->weight[i];
+      }
+      label_weight_.Alloc(n); label_weight_.Upload(label_weight_host_.data(), n, stream_);
+    }
+    // sort buffers of the renewal pass (renew_kernel.cuh)
+    rn_keys_a_.Alloc(n); rn_keys_b_.Alloc(n); rn_pos_a_.Alloc(n); rn_pos_b_.Alloc(n); rn_leaf_of_pos_.Alloc(n); rn_leaf_a_.Alloc(n); rn_leaf_b_.Alloc(n);
+    rn_res_.Alloc(n); rn_row_.Alloc(n); rn_seg_.Alloc(L + 1); rn_out_.Alloc(2 * static_cast<size_t>(L));
+    if (renew_kind_ == 3 || !train->weight.empty()) rn_cdf_.Alloc(n);
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, rn_keys_a_.p, rn_keys_b_.p, rn_pos_a_.p, rn_pos_b_.p, n, 0, 64, stream_);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, rn_leaf_a_.p, rn_leaf_b_.p, rn_pos_b_.p, rn_pos_a_.p, n, 0, 32, stream_);
+    rn_tmp_bytes_ = std::max(t1, t2);
+    rn_tmp_.Alloc(rn_tmp_bytes_ + 16);
   } else if (cfg.objective == "binary") {
     double cnt[2] = {0, 0};
     for (int i = 0; i < n; ++i) cnt[train->label[i] > 0 ? 1 : 0] += 1;
@@ -1041,6 +1095,15 @@ double Booster::ObjectiveInitScore(int k) {
     if (parallel_) { AllReduceHost(&v, 1, ncclSum, stream_); v /= Net().world; }   // GlobalSyncUpByMean (R11)
     return v;
   }
+  if (renew_kind_) {
+    const float* y = train->label.data();
+    double v;
+    if (renew_kind_ == 3) v = LabelWeightedPercentile(y, label_weight_host_.data(), n, 0.5);
+    else if (train->weight.empty()) v = LabelPercentile(y, n, renew_alpha_);
+    else v = LabelWeightedPercentile(y, train->weight.data(), n, renew_alpha_);
+    if (parallel_) { AllReduceHost(&v, 1, ncclSum, stream_); v /= Net().world; }   // GlobalSyncUpByMean
+    return v;
+  }
   if (cfg.objective == "binary") {
     double s[2] = {0, 0};
     if (!train->weight.empty()) for (int i = 0; i < n; ++i) { s[0] += (train->label[i] > 0) * static_cast<double>(train->weight[i]); s[1] += train->weight[i]; }
@@ -1076,6 +1139,9 @@ void Booster::ComputeGradientsAt(const double* score_p) {
   const float* w = train->weight.empty() ? nullptr : train->d_weight.p;
   if (cfg.objective == "regression") {
     k_grad_l2<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n);
+  } else if (renew_kind_) {
+    k_grad_percentile<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, renew_kind_ == 3 ? label_weight_.p : nullptr, grad_.p, hess_.p, n, renew_kind_,
+                                                 static_cast<float>(cfg.alpha));
   } else if (regvar_kind_) {
     k_grad_regvar<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, regvar_kind_, cfg.alpha, cfg.fair_c,
                                              cfg.poisson_max_delta_step, cfg.tweedie_variance_power);
@@ -1093,6 +1159,41 @@ void Booster::ComputeGradientsAt(const double* score_p) {
   }
   B200_CUDA(cudaGetLastError());
   timing.launches += 1;
+}
+
+// [LightGBM SerialTreeLearner::RenewTreeOutput] device pass described in renew_kernel.cuh; patches tree_dev_.leaf_value in place
+void Booster::RenewTreeOutput(int k, double rf_pred) {
+  const int n = train->num_data;
+  const int total = use_bag_ ? bag_count_ : n;
+  const int L = cfg.num_leaves;
+  cudaStream_t s = stream_;
+  TreeCtrl* ctrl = ctrl_.p;
+  const int egrid = num_sms_ * 8;
+  const bool weighted = renew_kind_ == 3 || !train->weight.empty();
+  const float* wptr = renew_kind_ == 3 ? label_weight_.p : (train->weight.empty() ? nullptr : train->d_weight.p);
+  k_renew_gather<<<egrid, 256, 0, s>>>(ctrl, leaves_.p, idx0_.p, idx1_.p, train->d_label.p, is_rf_ ? nullptr : score_.p + static_cast<size_t>(k) * n, rf_pred,
+                                       rn_keys_a_.p, rn_pos_a_.p, rn_res_.p, rn_leaf_of_pos_.p, rn_row_.p);
+  size_t tb = rn_tmp_bytes_;
+  B200_CUDA(cub::DeviceRadixSort::SortPairs(rn_tmp_.p, tb, rn_keys_a_.p, rn_keys_b_.p, rn_pos_a_.p, rn_pos_b_.p, total, 0, 64, s));
+  k_renew_leaf_keys<<<egrid, 256, 0, s>>>(rn_pos_b_.p, rn_leaf_of_pos_.p, total, rn_leaf_a_.p);
+  int leaf_bits = 1;
+  while ((1 << leaf_bits) < L) ++leaf_bits;
+  tb = rn_tmp_bytes_;
+  B200_CUDA(cub::DeviceRadixSort::SortPairs(rn_tmp_.p, tb, rn_leaf_a_.p, rn_leaf_b_.p, rn_pos_b_.p, rn_pos_a_.p, total, 0, leaf_bits, s));
+  k_renew_offsets<<<1, 32, 0, s>>>(ctrl, leaves_.p, rn_seg_.p);
+  double* out = rn_out_.p;
+  double* has = rn_out_.p + L;
+  const int lgrid = (L + 127) / 128;
+  if (!weighted) {
+    k_renew_unweighted<<<lgrid, 128, 0, s>>>(ctrl, rn_seg_.p, rn_pos_a_.p, rn_res_.p, renew_alpha_, out, has);
+  } else {
+    k_renew_cdf<<<L, 1024, 0, s>>>(ctrl, rn_seg_.p, rn_pos_a_.p, rn_row_.p, wptr, rn_cdf_.p);
+    k_renew_weighted<<<lgrid, 128, 0, s>>>(ctrl, rn_seg_.p, rn_pos_a_.p, rn_res_.p, rn_cdf_.p, renew_kind_ == 3 ? 0.5 : renew_alpha_, out, has);
+  }
+  if (parallel_) B200_NCCL(ncclAllReduce(out, out, 2 * static_cast<size_t>(L), ncclDouble, ncclSum, Net().comm, s));
+  k_renew_apply<<<lgrid, 128, 0, s>>>(ctrl, tree_dev_, out, has, parallel_ ? 1 : 0);
+  B200_CUDA(cudaGetLastError());
+  timing.launches += weighted ? 7 : 6;
 }
 
 // One tree: the whole leaf-wise growth is enqueued without a host sync; leaf choice, smaller/larger
@@ -1148,6 +1249,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     timing.launches += 7; timing.hist_launches += 1;
   }
   k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 1);
+  if (renew_kind_) RenewTreeOutput(k, is_rf_ ? rf_init_scores_[k] : 0.0);
   // rf keeps scores as the running average of (tree + init score) over the iterations [LightGBM rf.hpp MultiplyScore / UpdateScore]
   const double bias = is_rf_ ? rf_init_scores_[k] : 0.0, pre = is_rf_ ? static_cast<double>(iter + num_init_iteration) : 1.0;
   const double post = is_rf_ ? 1.0 / (iter + num_init_iteration + 1) : 1.0;
@@ -1455,6 +1557,17 @@ std::vector<double> Booster::GetEval(int data_idx) {
           else if (m == "gamma") { double theta = -1.0 / sc, b = -(-theta > 0 ? std::log(-theta) : -INFINITY); double cc = (lab > 0 ? std::log(lab) : -INFINITY) - (lab > 0 ? std::log(lab) : -INFINITY); l = -((lab * theta - b) + cc); }
           else { sc = std::max(sc, 1e-10); l = -lab * std::exp((1 - rho) * std::log(sc)) / (1 - rho) + std::exp((2 - rho) * std::log(sc)) / (2 - rho); }
         }
+        loss += l * wi; sw += wi;
+      }
+      out.push_back(avg(loss, sw));
+    } else if (m == "quantile" || m == "mape") {      // [LightGBM regression_metric.hpp QuantileMetric / MAPEMetric]
+      double loss = 0, sw = 0;
+      const double a = cfg.alpha;
+      for (int i = 0; i < n; ++i) {
+        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
+        double l;
+        if (m == "quantile") { const double delta = lab - raw[i]; l = delta < 0 ? (a - 1.0) * delta : a * delta; }
+        else l = std::fabs(lab - raw[i]) / std::max(1.0, std::fabs(lab));
         loss += l * wi; sw += wi;
       }
       out.push_back(avg(loss, sw));

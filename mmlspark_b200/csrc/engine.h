@@ -194,6 +194,18 @@ class Booster {
   std::vector<double> rf_init_scores_;
   void Bagging(int it);
   void ComputeGradientsAt(const double* score);
+  // percentile objectives: regression_l1 / quantile / mape renew the leaf outputs after the tree is grown (renew_kernel.cuh)
+  int renew_kind_ = 0;                  // 0 none, 1 l1, 2 quantile, 3 mape
+  double renew_alpha_ = 0.5;
+  std::vector<float> label_weight_host_;    // mape: 1 / max(1, |label|) (* weight)
+  DevBuf<float> label_weight_;
+  DevBuf<unsigned long long> rn_keys_a_, rn_keys_b_;
+  DevBuf<unsigned> rn_pos_a_, rn_pos_b_, rn_leaf_of_pos_, rn_leaf_a_, rn_leaf_b_;
+  DevBuf<double> rn_res_, rn_cdf_, rn_out_;      // rn_out_: [2][num_leaves] outputs, has-rows flags
+  DevBuf<int> rn_row_, rn_seg_;
+  DevBuf<unsigned char> rn_tmp_;
+  size_t rn_tmp_bytes_ = 0;
+  void RenewTreeOutput(int class_id, double rf_pred);
   // DART: every trained tree keeps its device blob so dropped trees can be re-applied to the binned data
   bool is_dart_ = false, dart_dropped_this_iter_ = false;
   LcgRandom drop_rand_{4};

@@ -171,6 +171,23 @@ __global__ void k_grad_regvar(const double* __restrict__ score, const float* __r
     g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
   }
 }
+// [LightGBM RegressionL1loss / RegressionQuantileloss / RegressionMAPELOSS ::GetGradients]; kind 1 l1, 2 quantile, 3 mape
+__global__ void k_grad_percentile(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
+                                  const float* __restrict__ label_weight, float* __restrict__ g, float* __restrict__ h, int n, int kind, float alpha) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (kind == 2) {
+      const float delta = static_cast<float>(score[i] - label[i]);
+      const float gg = delta >= 0 ? (1.0f - alpha) : -alpha;
+      g[i] = weight ? __fmul_rn(gg, weight[i]) : gg;
+    } else {
+      const double diff = score[i] - label[i];
+      const int sgn = (diff > 0.0) - (diff < 0.0);
+      if (kind == 1) g[i] = weight ? static_cast<float>(sgn * static_cast<double>(weight[i])) : static_cast<float>(sgn);
+      else g[i] = static_cast<float>(sgn * static_cast<double>(label_weight[i]));
+    }
+    h[i] = weight ? weight[i] : 1.0f;
+  }
+}
 // [UPSTREAM BinaryLogloss::GetGradients]
 __global__ void k_grad_binary(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
                               float* __restrict__ g, float* __restrict__ h, int n, double sigmoid, double w_neg, double w_pos) {

@@ -31,6 +31,7 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <functional>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -115,6 +116,8 @@ struct Config {
         o == "l2_root" || o == "root_mean_squared_error" || o == "rmse")
       return "regression";
     if (o == "softmax") return "multiclass";
+    if (o == "l1" || o == "mean_absolute_error" || o == "mae") return "regression_l1";
+    if (o == "mean_absolute_percentage_error") return "mape";
     return o;
   }
   void parse(const char* s) {
@@ -538,7 +541,45 @@ struct Objective {
   virtual bool ClassNeedTrain(int) const { return true; }
   virtual std::string ToString() const = 0;
   virtual bool GlobalInitScore() const { return false; }   // true: BoostFromScore already syncs sums across ranks
+  // objectives whose leaf outputs are re-fitted after the tree is grown (L1 / quantile / MAPE)  [LightGBM IsRenewTreeOutput]
+  virtual bool IsRenewTreeOutput() const { return false; }
+  // rows = the leaf's (in-bag) rows of ONE rank, in partition order; residual(i) = label[i] - score[i]
+  virtual double RenewTreeOutput(const std::vector<int>&, const std::function<double(int)>&) const { return 0.0; }
 };
+
+// [LightGBM src/objective/regression_objective.hpp PercentileFun / WeightedPercentileFun]
+// percentile at `alpha` counted from the TOP of the descending order: position (cnt-1)(1-alpha), linear interpolation
+template <typename T, typename Reader>
+static T PercentileOf(Reader data_reader, int cnt, double alpha) {
+  if (cnt <= 1) return data_reader(0);
+  std::vector<T> ref(cnt);
+  for (int i = 0; i < cnt; ++i) ref[i] = data_reader(i);
+  const double float_pos = static_cast<double>(cnt - 1) * (1.0 - alpha);
+  const int pos = static_cast<int>(float_pos);
+  if (pos < 1) return *std::max_element(ref.begin(), ref.end());
+  if (pos >= cnt) return *std::min_element(ref.begin(), ref.end());
+  const double bias = float_pos - pos;
+  std::sort(ref.begin(), ref.end(), std::greater<T>());
+  const T v1 = ref[pos - 1], v2 = ref[pos];
+  return static_cast<T>(v1 - (v1 - v2) * bias);
+}
+template <typename T, typename Reader, typename WReader>
+static T WeightedPercentileOf(Reader data_reader, WReader weight_reader, int cnt, double alpha) {
+  if (cnt <= 1) return data_reader(0);
+  std::vector<int> sorted_idx(cnt);
+  std::iota(sorted_idx.begin(), sorted_idx.end(), 0);
+  std::stable_sort(sorted_idx.begin(), sorted_idx.end(), [&](int a, int b) { return data_reader(a) < data_reader(b); });
+  std::vector<double> cdf(cnt);
+  cdf[0] = weight_reader(sorted_idx[0]);
+  for (int i = 1; i < cnt; ++i) cdf[i] = cdf[i - 1] + weight_reader(sorted_idx[i]);
+  const double threshold = cdf[cnt - 1] * alpha;
+  size_t pos = std::upper_bound(cdf.begin(), cdf.end(), threshold) - cdf.begin();
+  pos = std::min(pos, static_cast<size_t>(cnt - 1));
+  if (pos == 0 || pos == static_cast<size_t>(cnt - 1)) return data_reader(sorted_idx[pos]);
+  const T v1 = data_reader(sorted_idx[pos - 1]), v2 = data_reader(sorted_idx[pos]);
+  if (cdf[pos + 1] - cdf[pos] >= 1.0f) return static_cast<T>((threshold - cdf[pos]) / (cdf[pos + 1] - cdf[pos]) * (v2 - v1) + v1);
+  return static_cast<T>(v2);
+}
 
 struct RegressionL2 : Objective {
   void GetGradients(const double* score, float* g, float* h) const override {
@@ -595,6 +636,62 @@ struct RegressionVariant : RegressionL2 {
     static const char* names[] = {"", "huber", "fair", "poisson", "gamma", "tweedie"};
     return names[kind];
   }
+};
+
+// [LightGBM regression_objective.hpp RegressionL1loss / RegressionQuantileloss / RegressionMAPELOSS]
+struct RegressionPercentile : RegressionL2 {
+  int kind;                 // 0 l1, 1 quantile, 2 mape
+  float alpha_f = 0.5f;     // quantile keeps alpha as score_t
+  std::vector<float> label_weight;      // mape: 1 / max(1, |label|) (* weight)
+  explicit RegressionPercentile(int k) : kind(k) {}
+  void Init(const Dataset* d, const Config& c) override {
+    Objective::Init(d, c);
+    alpha_f = static_cast<float>(c.alpha);
+    if (kind == 2) {
+      label_weight.resize(d->n);
+      for (int i = 0; i < d->n; ++i) {
+        label_weight[i] = 1.0f / std::max(1.0f, std::fabs(d->label[i]));
+        if (!d->weight.empty()) label_weight[i] *= d->weight[i];
+      }
+    }
+  }
+  double Alpha() const { return kind == 1 ? static_cast<double>(alpha_f) : 0.5; }
+  void GetGradients(const double* score, float* g, float* h) const override {
+    const int n = ds->n;
+    const float* y = ds->label.data();
+    const float* w = ds->weight.empty() ? nullptr : ds->weight.data();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      if (kind == 1) {
+        const float delta = static_cast<float>(score[i] - y[i]);
+        const float gg = delta >= 0 ? (1.0f - alpha_f) : -alpha_f;
+        g[i] = w ? static_cast<float>(gg * w[i]) : gg;
+        h[i] = w ? w[i] : 1.0f;
+      } else {
+        const double diff = score[i] - y[i];
+        const int sgn = (diff > 0.0) - (diff < 0.0);
+        if (kind == 0) { g[i] = w ? static_cast<float>(sgn * w[i]) : static_cast<float>(sgn); h[i] = w ? w[i] : 1.0f; }
+        else { g[i] = static_cast<float>(sgn * label_weight[i]); h[i] = w ? w[i] : 1.0f; }
+      }
+    }
+  }
+  double BoostFromScore(int, int r0, int r1) const override {
+    const float* y = ds->label.data();
+    const int cnt = r1 - r0;
+    if (kind == 2) return WeightedPercentileOf<float>([&](int i) { return y[r0 + i]; }, [&](int i) { return label_weight[r0 + i]; }, cnt, 0.5);
+    if (ds->weight.empty()) return PercentileOf<float>([&](int i) { return y[r0 + i]; }, cnt, Alpha());
+    return WeightedPercentileOf<float>([&](int i) { return y[r0 + i]; }, [&](int i) { return ds->weight[r0 + i]; }, cnt, Alpha());
+  }
+  bool IsRenewTreeOutput() const override { return true; }
+  double RenewTreeOutput(const std::vector<int>& rows, const std::function<double(int)>& residual) const override {
+    const int cnt = static_cast<int>(rows.size());
+    auto dr = [&](int i) { return residual(rows[i]); };
+    if (kind == 2) return WeightedPercentileOf<double>(dr, [&](int i) { return label_weight[rows[i]]; }, cnt, 0.5);
+    if (ds->weight.empty()) return PercentileOf<double>(dr, cnt, Alpha());
+    return WeightedPercentileOf<double>(dr, [&](int i) { return ds->weight[rows[i]]; }, cnt, Alpha());
+  }
+  bool IsConstantHessian() const override { return ds->weight.empty(); }
+  std::string ToString() const override { return kind == 0 ? "regression_l1" : kind == 1 ? "quantile" : "mape"; }
 };
 
 struct BinaryLogloss : Objective {
@@ -807,6 +904,9 @@ static Objective* CreateObjective(const Config& c) {
   if (c.objective == "poisson") return new RegressionVariant(3);
   if (c.objective == "gamma") return new RegressionVariant(4);
   if (c.objective == "tweedie") return new RegressionVariant(5);
+  if (c.objective == "regression_l1") return new RegressionPercentile(0);
+  if (c.objective == "quantile") return new RegressionPercentile(1);
+  if (c.objective == "mape") return new RegressionPercentile(2);
   if (c.objective == "binary") return new BinaryLogloss();
   if (c.objective == "multiclass") return new MulticlassSoftmax();
   if (c.objective == "lambdarank") return new LambdarankNDCG();
@@ -1669,6 +1769,24 @@ struct Booster {
       }
     }
   }
+  // SerialTreeLearner::RenewTreeOutput: every leaf's output is re-fitted on the residuals of its (in-bag) rows; with several
+  // ranks each fits its own shard's rows and the outputs are averaged over the ranks that hold rows of the leaf
+  void RenewTreeOutput(Tree* t, const std::function<double(int)>& residual) {
+    if (!obj->IsRenewTreeOutput()) return;
+    std::vector<int> rank_end;
+    { int off = 0; for (int r = 0; r < num_ranks; ++r) { off += ds->rank_rows[r]; rank_end.push_back(off); } }
+    for (int l = 0; l < t->num_leaves; ++l) {
+      const int b = learner.leaf_begin[l], c = learner.leaf_cnt[l];
+      double sum = 0.0; int workers = 0;
+      int i = 0;
+      for (int r = 0; r < num_ranks; ++r) {
+        std::vector<int> rows;
+        while (i < c && learner.idx[b + i] < rank_end[r]) rows.push_back(learner.idx[b + i++]);
+        if (!rows.empty()) { sum += obj->RenewTreeOutput(rows, residual); ++workers; }
+      }
+      t->leaf_value[l] = num_ranks > 1 ? sum / workers : sum;
+    }
+  }
   void AddTreeToScores(const Tree& t, int k) {        // UpdateScore: in-bag via the partition, out-of-bag by binned traversal == tree(row) for all rows
     const int n = ds->n;
     double* sp = &score[static_cast<size_t>(k) * n];
@@ -1725,6 +1843,7 @@ struct Booster {
       if (is_rf) {
         const double m0 = static_cast<double>(iter), m1 = 1.0 / (iter + 1);
         if (t->num_leaves > 1) {
+          { const double pred = init_scores[k]; const float* y = ds->label.data(); RenewTreeOutput(t.get(), [=](int i) { return static_cast<double>(y[i]) - pred; }); }
           if (std::fabs(init_scores[k]) > kEpsilon) t->AddBias(init_scores[k]);
           for (int i = 0; i < n; ++i) sp[i] *= m0;
           AddTreeToScores(*t, k);
@@ -1739,6 +1858,7 @@ struct Booster {
       }
       if (t->num_leaves > 1) {
         should_continue = true;
+        { const float* y = ds->label.data(); RenewTreeOutput(t.get(), [=](int i) { return static_cast<double>(y[i]) - sp[i]; }); }
         t->Shrinkage(shrinkage_rate);
         AddTreeToScores(*t, k);
         if (std::fabs(init_scores[k]) > kEpsilon) t->AddBias(init_scores[k]);

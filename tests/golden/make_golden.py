@@ -47,6 +47,7 @@ def main():
          (s > 0).astype(np.float32)),
         ("binary_goss", "objective=binary boosting_type=goss learning_rate=0.5 num_leaves=7 min_data_in_leaf=20 verbosity=-1", (s > 0).astype(np.float32)),
         ("binary_dart", "objective=binary boosting_type=dart drop_rate=0.5 skip_drop=0.0 num_leaves=7 min_data_in_leaf=20 verbosity=-1", (s > 0).astype(np.float32)),
+        ("regression_quantile", "objective=quantile alpha=0.7 num_leaves=7 min_data_in_leaf=20 verbosity=-1 learning_rate=0.3", s.astype(np.float32)),
         ("regression_categorical|categorical_feature=4", "objective=regression num_leaves=7 min_data_in_leaf=20 verbosity=-1 min_data_per_group=50 cat_smooth=5",
          s.astype(np.float32)),
     ]:

@@ -324,11 +324,12 @@ def test_unsupported_objective_fails_loudly(built):
     rng = np.random.default_rng(0)
     X = rng.standard_normal((500, 3)); y = rng.standard_normal(500).astype(np.float32)
     ds, _ = _make(X, y)
-    for obj in ("regression_l1", "quantile", "not_an_objective"):
+    for obj in ("cross_entropy", "rank_xendcg", "multiclassova", "not_an_objective"):
         with pytest.raises(capi.LightGBMError):
             capi.Booster(ds, "objective=%s" % obj)
-    with pytest.raises(capi.LightGBMError):
-        capi.Booster(ds, "objective=regression boosting_type=dart")
+    for bad in ("boosting_type=not_a_booster", "bagging_fraction=0.5 bagging_freq=1 pos_bagging_fraction=0.5", "boosting_type=goss bagging_fraction=0.5 bagging_freq=1"):
+        with pytest.raises(capi.LightGBMError):
+            capi.Booster(ds, "objective=regression " + bad)
 
 
 def test_feature_fraction_column_sampling(built):
@@ -582,3 +583,40 @@ def test_dart(built, objective, extra):
     K = raw.shape[1]
     np.testing.assert_allclose(raw, b.get_scores(0).reshape(K, -1)[:, :3000].T, rtol=0, atol=1e-8)
     np.testing.assert_allclose(b.predict_device(Xs, predict_type=1).reshape(len(Xs), -1), raw, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("objective,extra,weighted", [
+    ("regression_l1", "", False),
+    ("quantile", "alpha=0.8", False),
+    ("quantile", "alpha=0.2", True),
+    ("mape", "", False),
+    ("regression_l1", "bagging_fraction=0.7 bagging_freq=1", True),
+])
+def test_percentile_objectives_renew_leaf_outputs(built, objective, extra, weighted):
+    """regression_l1 / quantile / mape: sign-type gradients, init score = (weighted) percentile of the labels and, after every
+    tree, leaf outputs re-fitted as the percentile of the leaf's residuals (SURVEY §8 a9 RenewTreeOutput) — device sort path."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(91)
+    n, F = 30000, 8
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] + 0.5 * X[:, 1] + (1 + 0.5 * np.abs(X[:, 2])) * rng.standard_normal(n)).astype(np.float32)
+    if objective == "mape":
+        y = (y + 6).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32) if weighted else None
+    ds, ods = _make(X, y, weight=w)
+    params = _classifier_params(objective, "", leaves=15).replace("learning_rate=0.1", "learning_rate=0.2")
+    if "bagging" in extra:
+        params = params.replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 ", "")
+    params += " " + extra
+    b, ob, m, om = _train_both(ds, ods, params, 12)
+    compare_models(m, om)
+    assert m["header"]["objective"] == objective
+    np.testing.assert_allclose(b.get_scores(0).ravel(), ob.scores().ravel(), rtol=0, atol=1e-9)
+    p = b.predict_for_mat(X, predict_type=1).ravel()
+    if objective == "quantile":
+        a = float(extra.split("=")[1])
+        ww = w if w is not None else np.ones(n)
+        assert abs(float(np.sum(ww * (y < p)) / np.sum(ww)) - a) < 0.03          # calibrated quantile
+    names = b.eval_names()
+    assert names == [{"regression_l1": "l1"}.get(objective, objective)]
+    assert np.isfinite(b.get_eval(0)[0])
