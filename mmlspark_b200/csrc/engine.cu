@@ -651,9 +651,8 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   renew_alpha_ = renew_kind_ == 2 ? static_cast<double>(static_cast<float>(cfg.alpha)) : 0.5;     // quantile keeps alpha as score_t
   if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_ && !renew_kind_)
     Fatal("Unknown/unsupported objective type name: " + cfg.objective);
-  if (cfg.bagging_freq > 0 && (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0))
-    Fatal("balanced bagging (pos_/neg_bagging_fraction) is not implemented by this build");
-  bagging_ = cfg.bagging_freq > 0 && cfg.bagging_fraction < 1.0;
+  balanced_bagging_ = cfg.bagging_freq > 0 && (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0) && cfg.objective == "binary";
+  bagging_ = cfg.bagging_freq > 0 && (cfg.bagging_fraction < 1.0 || balanced_bagging_);
   if (bagging_ && !(cfg.bagging_fraction > 0.0)) Fatal("bagging_fraction should be in (0, 1]");
   if (is_goss_) {      // [LightGBM goss.hpp ResetGoss]
     if (!(cfg.top_rate + cfg.other_rate <= 1.0)) Fatal("Check failed: (config_->top_rate + config_->other_rate) <= (1.0f)");
@@ -671,6 +670,16 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   K = cfg.objective == "multiclass" ? cfg.num_class : 1;
   parallel_ = Net().active && Net().world > 1;
   cfg.num_machines = parallel_ ? Net().world : 1;
+  if (balanced_bagging_) {      // [LightGBM GBDT::ResetBaggingConfig] needs (globally) at least one positive row
+    double npos = static_cast<double>(std::count_if(train->label.begin(), train->label.end(), [](float v) { return v > 0; }));
+    if (parallel_) {
+      cudaStream_t ts;
+      B200_CUDA(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
+      AllReduceHost(&npos, 1, ncclSum, ts);
+      B200_CUDA(cudaStreamDestroy(ts));
+    }
+    if (!(npos > 0)) { balanced_bagging_ = false; bagging_ = cfg.bagging_freq > 0 && cfg.bagging_fraction < 1.0; }
+  }
   shrinkage_ = is_rf_ ? 1.0 : cfg.learning_rate;      // "no shrinkage rate for the RF"
   model.average_output = is_rf_;
   model.num_class = cfg.objective == "multiclass" ? cfg.num_class : 1;
@@ -992,7 +1001,8 @@ void Booster::Bagging(int it) {
     if (!bagging_) return;
     if (!((use_bag_ && it % cfg.bagging_freq == 0) || need_re_bagging_)) return;
     need_re_bagging_ = false;
-    k_bag_draw<<<bag_blocks_, 256, 0, s>>>(bag_lcg_.p, bag_jump_.p, n, cfg.bagging_fraction, in_bag_.p, bag_block_cnt_.p);
+    k_bag_draw<<<bag_blocks_, 256, 0, s>>>(bag_lcg_.p, bag_jump_.p, n, cfg.bagging_fraction, in_bag_.p, bag_block_cnt_.p,
+                                           balanced_bagging_ ? train->d_label.p : nullptr, cfg.pos_bagging_fraction, cfg.neg_bagging_fraction);
   }
   k_bag_scan<<<1, 1024, 0, s>>>(bag_block_cnt_.p, bag_blocks_, bag_total_.p);
   k_bag_compact<<<bag_blocks_, 256, 0, s>>>(in_bag_.p, bag_block_cnt_.p, n, bag_idx_.p);

@@ -185,7 +185,7 @@ class Booster {
   DevBuf<uint8_t> feature_used_;
   void ResetFeaturesByTree();
   // row subsampling: bagging / GOSS / random forest
-  bool is_rf_ = false, is_goss_ = false, bagging_ = false, use_bag_ = false, need_re_bagging_ = false;
+  bool is_rf_ = false, is_goss_ = false, bagging_ = false, balanced_bagging_ = false, use_bag_ = false, need_re_bagging_ = false;
   int bag_count_ = 0, bag_blocks_ = 0;
   DevBuf<unsigned> bag_lcg_;            // one LCG state per 1024-row block
   DevBuf<LcgJump> bag_jump_;

@@ -25,9 +25,13 @@
 // run to run and across ranks (the NCCL reduction is an int64 sum).
 //
 // Bank mapping: the sub-histogram planes are laid out [bin][feature-of-tile], so feature f lives in
-// bank f.  A warp step covers 4 rows x 32 features; in each of its 4 sub-steps the 32 lanes handle 32
-// DIFFERENT features (a rotation by the lane's row selector), so every ATOMS instruction is
-// conflict-free by construction regardless of the bin distribution (ncu: 1.0 wavefront per ATOMS).
+// bank f.  Every ATOMS instruction of a warp addresses 32 DIFFERENT features, so it is conflict-free by
+// construction regardless of the bin distribution (ncu: 1.0 wavefront per ATOMS).
+//   k4_hist_build    (v2): warp step = 4 rows x 32 features, lane = (row selector, bin word), bytes rotated by the row selector.
+//   k4_hist_build_ws (v3, the engine's kernel): warp step = 32 rows x 4 features, lane = row for 8 steps; the lane's (g,h)
+//     quadruple stays in registers (one 16-byte LDS per 32 cells instead of one per 4), bin word and byte rotated by the lane id.
+// The LSU data pipe is the binding unit (ncu: ~94 % busy): an ATOMS wavefront costs ~0.93 cycles, so the v3 loop spends
+// 16 x 0.93 (atomics) + 1 (bin word) + 0.5 (q) cycles per 128 cells.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,6 +42,9 @@ constexpr int kTileFeat = 32;                      // features per tile == lanes
 constexpr int kBins = 256;                         // uint8 bin ids
 constexpr int kLoBits = 18;                        // low fixed-point field
 constexpr int kFlushRows = 1 << (32 - kLoBits);    // rows a sub-histogram may absorb (16384)
+#ifndef B200GBM_K4_EXPERIMENT
+#define B200GBM_K4_EXPERIMENT 0
+#endif
 #ifndef B200GBM_STAGE_ROWS
 #define B200GBM_STAGE_ROWS 512
 #endif
@@ -360,7 +367,14 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
     cp_async_wait<0>();
   } else {
     // ------------------------------------------------------------------ consumer warps
-    const int rsel = lane >> 3, wsel = lane & 7;
+    // Warp step = 32 rows x 4 features: lane owns ROW g*32+lane for 8 steps and keeps its (g,h) quadruple in registers, so the
+    // 16-byte q load (4 LSU wavefronts for a warp) is paid once per 1024 cells instead of once per 128.  At step k the lane reads
+    // bin word w = ((lane>>2)+k)&7 of its row: bank = 8*(lane&3)+w, all 32 distinct.  Inside the word the byte order is rotated
+    // by lane&3, so the 32 atomics of one instruction hit features 4w+kk = 32 distinct banks (plane index = bin*32 + feature).
+#if B200GBM_K4_EXPERIMENT != 0
+    unsigned exp_sink = 0;
+#endif
+    const int sub = lane >> 2, rot = lane & 3;
     int acc_rows = 0;                                             // rows absorbed by the sub-histogram since the last flush
     for (int item = i0; item < i1; ++item) {
       const int tile = item / chunks, chunk = item - tile * chunks;
@@ -373,25 +387,38 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
         const int rows = min(kWsStageRows, nrows - s * kWsStageRows);
         const unsigned* sw = reinterpret_cast<const unsigned*>(stage_bins + slot * kWsStageRows * 32);
         const int4* sq = stage_q + slot * kWsStageRows;
-        const int groups = (rows + 3) >> 2;
-#pragma unroll 2
+        const int groups = (rows + 31) >> 5;
         for (int g = warp; g < groups; g += kWsConsumerWarps) {
-          const int r = g * 4 + rsel;
+          const int r = g * 32 + lane;
           if (r < rows) {
-            const unsigned word = sw[r * 8 + wsel];
             const int4 q = sq[r];
+            const unsigned* rw = sw + r * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int kk = (k + rsel) & 3;
-              const unsigned b = (word >> (8 * kk)) & 0xFFu;
-              const unsigned a = b * 32u + static_cast<unsigned>(wsel * 4 + kk);
-              atomicAdd(&plane[a], static_cast<unsigned>(q.x));
-              atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
-              atomicAdd(&plane[2 * kPlaneWords + a], static_cast<unsigned>(q.z));
-              if (NATOM == 4) atomicAdd(&plane[3 * kPlaneWords + a], static_cast<unsigned>(q.w));
+            for (int k = 0; k < 8; ++k) {
+              const int w8 = (sub + k) & 7;
+              const unsigned word = rw[w8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int kk = (j + rot) & 3;
+                const unsigned b = (word >> (8 * kk)) & 0xFFu;
+                const unsigned a = b * 32u + static_cast<unsigned>(w8 * 4 + kk);
+#if B200GBM_K4_EXPERIMENT == 0
+                atomicAdd(&plane[a], static_cast<unsigned>(q.x));
+                atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
+                atomicAdd(&plane[2 * kPlaneWords + a], static_cast<unsigned>(q.z));
+                if (NATOM == 4) atomicAdd(&plane[3 * kPlaneWords + a], static_cast<unsigned>(q.w));
+#else   // tools/ubench_hist.cu only: cost model of the loop with 0 / 1 / 2 atomics per cell
+                if (B200GBM_K4_EXPERIMENT >= 2) atomicAdd(&plane[a], static_cast<unsigned>(q.x));
+                if (B200GBM_K4_EXPERIMENT >= 3) atomicAdd(&plane[kPlaneWords + a], static_cast<unsigned>(q.y));
+                if (B200GBM_K4_EXPERIMENT == 1) exp_sink ^= a + static_cast<unsigned>(q.x ^ q.y ^ q.z ^ q.w);
+#endif
+              }
             }
           }
         }
+#if B200GBM_K4_EXPERIMENT != 0
+        if (exp_sink == 0x12345679u) plane[lane] = exp_sink;
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);
       }

@@ -1219,13 +1219,15 @@ __device__ __forceinline__ float d_lcg_float(unsigned x) { return static_cast<fl
 
 __global__ void __launch_bounds__(256)
 k_bag_draw(unsigned* __restrict__ lcg_state, const LcgJump* __restrict__ jump, int n, double fraction, uint8_t* __restrict__ in_bag,
-           int* __restrict__ block_count) {
+           int* __restrict__ block_count, const float* __restrict__ label = nullptr, double pos_fraction = 1.0, double neg_fraction = 1.0) {
   const int b = blockIdx.x, base = b * kBagBlock, cnt = min(kBagBlock, n - base);
   const unsigned x0 = lcg_state[b];
   int mine = 0;
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
     const unsigned x = jump->mul[j] * x0 + jump->add[j];
-    const int take = static_cast<double>(d_lcg_float(x)) < fraction;
+    // balanced bagging (label given): positives and negatives are kept with their own fractions [LightGBM BalancedBaggingHelper]
+    const double frac = label ? (label[base + j] > 0 ? pos_fraction : neg_fraction) : fraction;
+    const int take = static_cast<double>(d_lcg_float(x)) < frac;
     in_bag[base + j] = static_cast<uint8_t>(take);
     mine += take;
   }

@@ -78,7 +78,7 @@ struct Config {
   double alpha = 0.9, fair_c = 1.0, poisson_max_delta_step = 0.7, tweedie_variance_power = 1.5;
   int max_cat_threshold = 32, max_cat_to_onehot = 4, min_data_per_group = 100;
   double cat_l2 = 10.0, cat_smooth = 10.0;
-  double bagging_fraction = 1.0, top_rate = 0.2, other_rate = 0.1;
+  double bagging_fraction = 1.0, pos_bagging_fraction = 1.0, neg_bagging_fraction = 1.0, top_rate = 0.2, other_rate = 0.1;
   int bagging_freq = 0, bagging_seed = 3;
   double drop_rate = 0.1, skip_drop = 0.5;
   int max_drop = 50, drop_seed = 4;
@@ -152,6 +152,7 @@ struct Config {
     getd("tweedie_variance_power", tweedie_variance_power);
     geti("max_cat_threshold", max_cat_threshold); geti("max_cat_to_onehot", max_cat_to_onehot); geti("min_data_per_group", min_data_per_group);
     getd("cat_l2", cat_l2); getd("cat_smooth", cat_smooth);
+    getd("pos_bagging_fraction", pos_bagging_fraction); getd("neg_bagging_fraction", neg_bagging_fraction);
     getd("bagging_fraction", bagging_fraction); geti("bagging_freq", bagging_freq); geti("bagging_seed", bagging_seed);
     getd("top_rate", top_rate); getd("other_rate", other_rate);
     getd("drop_rate", drop_rate); getd("skip_drop", skip_drop); geti("max_drop", max_drop); geti("drop_seed", drop_seed);
@@ -1600,7 +1601,7 @@ struct Booster {
   std::vector<Random> bagging_rands;        // one LCG per 1024-row block of every rank's shard
   std::vector<int> block_of_row_base;       // per rank: first block index
   std::vector<int> bag_idx;
-  bool use_bag = false, need_re_bagging = false, is_rf = false, is_goss = false, average_output = false;
+  bool balanced_bagging = false, use_bag = false, need_re_bagging = false, is_rf = false, is_goss = false, average_output = false;
   std::vector<double> rf_init_scores;
   std::vector<int> nan_bin_of_inner;
   // DART [LightGBM src/boosting/dart.hpp]
@@ -1632,7 +1633,10 @@ struct Booster {
     for (int f : d->used) nan_bin_of_inner.push_back(d->mappers[f].missing_type == kMissNaN && !d->mappers[f].is_categorical ? d->mappers[f].num_bin - 1 : -1);
     is_rf = cfg.boosting == "rf"; is_goss = cfg.boosting == "goss"; is_dart = cfg.boosting == "dart";
     random_for_drop = Random(cfg.drop_seed);
-    const bool bagging = cfg.bagging_fraction < 1.0 && cfg.bagging_freq > 0;
+    // [LightGBM GBDT::ResetBaggingConfig] balanced bagging needs positive rows, i.e. the binary objective
+    balanced_bagging = (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0) && cfg.objective == "binary" && cfg.bagging_freq > 0 &&
+                       std::any_of(d->label.begin(), d->label.end(), [](float v) { return v > 0; });
+    const bool bagging = (cfg.bagging_fraction < 1.0 || balanced_bagging) && cfg.bagging_freq > 0;
     if (bagging || is_goss) {
       int blocks = 0;
       for (int r = 0; r < num_ranks; ++r) {
@@ -1701,7 +1705,7 @@ struct Booster {
       use_bag = true;
       return;
     }
-    const bool bagging = cfg.bagging_fraction < 1.0 && cfg.bagging_freq > 0;
+    const bool bagging = (cfg.bagging_fraction < 1.0 || balanced_bagging) && cfg.bagging_freq > 0;
     if (!bagging) return;
     if ((use_bag && it % cfg.bagging_freq == 0) || need_re_bagging) {
       need_re_bagging = false;
@@ -1709,7 +1713,9 @@ struct Booster {
       int off = 0;
       for (int r = 0; r < num_ranks; ++r) {
         for (int i = 0; i < ds->rank_rows[r]; ++i)
-          if (bagging_rands[block_of_row_base[r] + i / 1024].NextFloat() < cfg.bagging_fraction) bag_idx.push_back(off + i);
+          if (bagging_rands[block_of_row_base[r] + i / 1024].NextFloat() <
+              (balanced_bagging ? (ds->label[off + i] > 0 ? cfg.pos_bagging_fraction : cfg.neg_bagging_fraction) : cfg.bagging_fraction))
+            bag_idx.push_back(off + i);
         off += ds->rank_rows[r];
       }
       use_bag = true;

@@ -18,6 +18,11 @@ def _classifier_params(objective="binary", extra="", iters=100, leaves=31, machi
             "min_gain_to_split=0.0 max_delta_step=0.0 min_data_in_leaf=20 objective=%s num_threads=0 %s" % (iters, leaves, machines, objective, extra))
 
 
+def _without(params, *keys):
+    """drops whole key=value tokens (so that 'bagging_fraction' does not also hit 'pos_bagging_fraction')"""
+    return " ".join(t for t in params.split(" ") if t.split("=")[0] not in keys)
+
+
 def _make(X, y, ds_params=DS_PARAMS, weight=None, group=None, init_score=None):
     from mmlspark_b200 import capi
     from oracle import oracle as O
@@ -327,7 +332,7 @@ def test_unsupported_objective_fails_loudly(built):
     for obj in ("cross_entropy", "rank_xendcg", "multiclassova", "not_an_objective"):
         with pytest.raises(capi.LightGBMError):
             capi.Booster(ds, "objective=%s" % obj)
-    for bad in ("boosting_type=not_a_booster", "bagging_fraction=0.5 bagging_freq=1 pos_bagging_fraction=0.5", "boosting_type=goss bagging_fraction=0.5 bagging_freq=1"):
+    for bad in ("boosting_type=not_a_booster", "boosting_type=goss bagging_fraction=0.5 bagging_freq=1"):
         with pytest.raises(capi.LightGBMError):
             capi.Booster(ds, "objective=regression " + bad)
 
@@ -446,6 +451,7 @@ def _sampling_case(rng, n=30000, F=12):
     ("regression", "bagging_fraction=0.6 bagging_freq=2"),
     ("binary", "bagging_fraction=0.35 bagging_freq=1 bagging_seed=11 is_unbalance=false"),
     ("multiclass", "num_class=3 bagging_fraction=0.8 bagging_freq=3"),
+    ("binary", "pos_bagging_fraction=0.9 neg_bagging_fraction=0.3 bagging_freq=1 is_unbalance=false"),       # balanced bagging
 ])
 def test_bagging(built, objective, extra):
     """Row bagging: per-1024-row-block LCG draws, the in-bag list is the tree's root, out-of-bag rows are scored
@@ -455,7 +461,8 @@ def test_bagging(built, objective, extra):
     X, s = _sampling_case(rng)
     y = {"regression": s, "binary": s > 0, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
     ds, ods = _make(X, y)
-    params = _classifier_params(objective, "", leaves=15).replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 bagging_seed=3", "") + " " + extra
+    params = _without(_classifier_params(objective, "", leaves=15), "bagging_fraction", "pos_bagging_fraction", "neg_bagging_fraction", "bagging_freq", "bagging_seed")
+    params += " " + extra
     b, ob, m, om = _train_both(ds, ods, params, 9)
     compare_models(m, om)
     assert len(m["trees"]) == 9 * (3 if objective == "multiclass" else 1)
@@ -477,9 +484,7 @@ def test_random_forest(built, objective, extra):
     y = {"regression": s + 3.0, "binary": s > 0.5, "multiclass": np.digitize(s, [-0.8, 0.8])}[objective].astype(np.float32)
     ds, ods = _make(X, y)
     params = _classifier_params(objective, "", leaves=15).replace("boosting_type=gbdt", "boosting_type=rf")
-    for k in ("bagging_fraction=1.0 ", "bagging_freq=0 ", "feature_fraction=1.0 "):
-        params = params.replace(k, "")
-    params += " " + extra
+    params = _without(params, "bagging_fraction", "bagging_freq", "feature_fraction") + " " + extra
     b, ob, m, om = _train_both(ds, ods, params, 8)
     compare_models(m, om)
     text = b.save_model_to_string()
@@ -570,7 +575,7 @@ def test_dart(built, objective, extra):
     ds, ods = _make(X, y)
     params = _classifier_params(objective, "", leaves=15).replace("boosting_type=gbdt", "boosting_type=dart")
     if "bagging_fraction" in extra:
-        params = params.replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 ", "")
+        params = _without(params, "bagging_fraction", "bagging_freq")
     params += " " + extra
     b, ob, m, om = _train_both(ds, ods, params, 25)
     compare_models(m, om)
@@ -606,7 +611,7 @@ def test_percentile_objectives_renew_leaf_outputs(built, objective, extra, weigh
     ds, ods = _make(X, y, weight=w)
     params = _classifier_params(objective, "", leaves=15).replace("learning_rate=0.1", "learning_rate=0.2")
     if "bagging" in extra:
-        params = params.replace("bagging_fraction=1.0 ", "").replace("bagging_freq=0 ", "")
+        params = _without(params, "bagging_fraction", "bagging_freq")
     params += " " + extra
     b, ob, m, om = _train_both(ds, ods, params, 12)
     compare_models(m, om)
