@@ -158,6 +158,17 @@ def cpu_reference_run(n_total, F, sample_rows, steps, warmup, use_gpu_generator=
     return ips, ips * sample_rows / n_total, info
 
 
+def k4_traffic(rows, feats, world):
+    """roofline.traffic: DRAM bytes per K4 launch from the committed ncu capture of this shape (profiles/), else null."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_k4_dram_traffic_%dx%d.json" % (rows, feats))
+    if world != 1 or not os.path.exists(path):
+        return None
+    try:
+        return float(json.load(open(path))["bytes_per_launch_avg"])
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,7 +273,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (tm["hist_ms"] / 1000.0) / 1e9 if tm["hist_ms"] > 0 else None
     roofline = {"bound": "hbm", "kernel": "k4_hist_build_ws<4>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "peak_source": peak_src, "traffic": None, "launches": launches, "avg_launch_ms": tm["hist_ms"] / max(launches, 1),
+                "peak_source": peak_src, "traffic": k4_traffic(args.rows, args.features, world), "launches": launches, "avg_launch_ms": tm["hist_ms"] / max(launches, 1),
                 "cells_per_s": rows_rank0 * F / (tm["hist_ms"] / 1000.0) if tm["hist_ms"] > 0 else None,
                 "k4_share_of_step": tm["hist_ms"] / dev_ms if dev_ms > 0 else None,
                 "co_limit": "shared-memory ATOMS issue rate (profiles/r01_ubench_smem_scatter.json): 4 native 32-bit atomics per cell"}

@@ -113,6 +113,12 @@ class Dataset {
   void FindBins(const void* data, bool on_device, int data_type, int is_row_major);
   void FindBinsFromColumns(std::vector<std::vector<double>>* nz, int sample_cnt);
   void BinBlock(const void* data, bool on_device, int data_type, int is_row_major, long long nrow, long long start_row);
+  // persistent H2D staging of the host ingestion path (two device chunks, a copy stream, events); released once every row is in
+  DevBuf<unsigned char> ingest_buf_[2];
+  cudaStream_t ingest_copy_stream_ = nullptr;
+  cudaEvent_t ingest_copied_[2] = {nullptr, nullptr}, ingest_binned_[2] = {nullptr, nullptr};
+  long long ingest_rows_done_ = 0;
+  void ReleaseIngestStaging();
   void UploadMeta();
 };
 
@@ -221,7 +227,7 @@ class Booster {
   // device state
   DevBuf<double> score_;        // [K][n]
   DevBuf<float> grad_, hess_;   // [K][n]
-  DevBuf<int4> qgh_;
+  DevBuf<int4> qgh_, qord_;     // per-row fixed-point (g,h) words; the same in leaf order for the leaf being built
   DevBuf<int> idx0_, idx1_;
   DevBuf<long long> H_;         // scratch histogram of the current smaller leaf
   DevBuf<long long> pool_;      // [num_leaves] leaf histograms

@@ -72,6 +72,20 @@ struct HistWork {
   int buf;        // which of the two index buffers holds the leaf's row list
 };
 
+// (g,h) words of a leaf in partition order: qord[begin + i] = qgh[idx[begin + i]] (no-op for the identity root)
+__global__ void __launch_bounds__(256)
+k_gather_q(const HistWork* __restrict__ work, const int* __restrict__ idx0, const int* __restrict__ idx1, const int4* __restrict__ qgh,
+           int4* __restrict__ qord) {
+  const HistWork w = *work;
+  if (!w.use_idx) return;
+  const int* __restrict__ idx = w.buf ? idx1 : idx0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.count; i += gridDim.x * blockDim.x) {
+    const int p = w.begin + i;
+    qord[p] = qgh[idx[p]];
+  }
+}
+
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   int sz = valid ? 16 : 0;   // src-size 0 => zero fill, nothing is read
@@ -258,6 +272,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -281,8 +298,8 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* b
 template <int NATOM>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tiles, const int4* __restrict__ qgh,
-                 const int* __restrict__ idx0, const int* __restrict__ idx1, const HistWork* __restrict__ work,
-                 unsigned long long* __restrict__ hist) {
+                 const int4* __restrict__ qord, const int* __restrict__ idx0, const int* __restrict__ idx1,
+                 const HistWork* __restrict__ work, unsigned long long* __restrict__ hist) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned* plane = reinterpret_cast<unsigned*>(smem_raw);
   unsigned char* stage_bins = smem_raw + 4 * kPlaneWords * 4;
@@ -346,19 +363,24 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
             mbar_arrive(&full_bar[slot]);
           }
         } else {
+          // leaf = index list: the bin rows are gathered sector by sector with cp.async; the (g,h) words were put into LEAF ORDER
+          // once per leaf by k_gather_q (qord[position]), so every feature tile streams them with one bulk copy instead of
+          // re-gathering 16 B out of a 64 B DRAM atom 16 times (ncu: the per-tile q gather doubled the DRAM traffic of a leaf pass)
           const int* ip = idx + w.begin + p0;
-          int rr[kPerLane];
+          if (ptid == 0) {
+            mbar_expect_tx(&full_bar[slot], static_cast<unsigned>(rows) * 16u);
+            tma_bulk_g2s(dq, qord + static_cast<size_t>(w.begin + p0), static_cast<unsigned>(rows) * 16u, &full_bar[slot]);
+          }
+          // (one 32-byte cp.async.bulk per row was tried instead: the TMA unit retires ~1 such copy per 32 cycles per SM, 4.5x slower)
+          // a lane pair fetches the two 16-byte halves of ONE row sector, so an LDGSTS instruction touches 16 sectors instead of
+          // 32 (ncu: the data return costs one LSU wavefront per distinct sector: 28 per instruction with one half-row per lane)
+          int rr[2 * kPerLane];
 #pragma unroll
-          for (int k = 0; k < kPerLane; ++k) { const int j = ptid + k * kPT; rr[k] = j < rows ? ip[j] : -1; }
+          for (int k = 0; k < 2 * kPerLane; ++k) { const int j = (ptid + k * kPT) >> 1; rr[k] = j < rows ? ip[j] : -1; }
 #pragma unroll
-          for (int k = 0; k < kPerLane; ++k) {
-            const int j = ptid + k * kPT;
-            if (rr[k] >= 0) {
-              const size_t r = static_cast<size_t>(rr[k]);
-              cp_async16(db + j * 32, tbins + r * 32, true);
-              cp_async16(db + j * 32 + 16, tbins + r * 32 + 16, true);
-              cp_async16(dq + j, qgh + r, true);
-            }
+          for (int k = 0; k < 2 * kPerLane; ++k) {
+            const int hh = ptid + k * kPT, j = hh >> 1, half = (hh & 1) * 16;
+            if (rr[k] >= 0) cp_async16(db + j * 32 + half, tbins + static_cast<size_t>(rr[k]) * 32 + half, true);
           }
           cp_async_mbar_arrive_noinc(&full_bar[slot]);
         }

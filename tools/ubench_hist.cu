@@ -160,14 +160,19 @@ int main(int argc, char** argv) {
   }
   printf(" },\n");
 
+  if (const char* e = getenv("B200GBM_L2_FETCH")) {
+    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
+  }
+  { size_t g = 0; cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); printf(" \"l2_fetch_granularity\": %zu,\n", g); }
   // ---- Part B
   const int F = 256, num_tiles = F / 32;
   size_t N = (argc > 1) ? (size_t)atoll(argv[1]) : 10000000;
   size_t rows_stride = (N + 255) / 256 * 256;
-  uint8_t* d_bins; int4* d_q; int* d_idx; unsigned long long* d_hist; HistWork* d_work;
+  uint8_t* d_bins; int4* d_q; int4* d_qord; int* d_idx; unsigned long long* d_hist; HistWork* d_work;
   size_t slot_elems = (size_t)F * 256 * 2;
   CK(cudaMalloc(&d_bins, (size_t)num_tiles * rows_stride * 32));
   CK(cudaMalloc(&d_q, N * sizeof(int4)));
+  CK(cudaMalloc(&d_qord, N * sizeof(int4)));
   CK(cudaMalloc(&d_idx, N * sizeof(int)));
   CK(cudaMalloc(&d_hist, slot_elems * 8 * 2));
   CK(cudaMalloc(&d_work, sizeof(HistWork) * 4));
@@ -188,8 +193,9 @@ int main(int argc, char** argv) {
     gen_idx<<<nsm, 256>>>(d_idx, n_chk / 3, 3);
     CK(cudaMemset(d_hist, 0, slot_elems * 8 * 2));
     if (use_ws) {
-      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
-      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
+      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
+      k_gather_q<<<nsm * 8, 256>>>(d_work + 1, d_idx, d_idx, d_q, d_qord);
+      k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
     } else {
     k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
     k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
@@ -226,9 +232,10 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 2; ++r) {
       CK(cudaMemsetAsync(d_hist, 0, slot_elems * 8));
       CK(cudaEventRecord(e0));
+      if (use_ws && use_idx) k_gather_q<<<nsm * 8, 256>>>(d_work, d_idx, d_idx, d_q, d_qord);     // part of a leaf pass: timed
       if (use_ws) {
-        if (natom == 4) k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
-        else k4_hist_build_ws<3><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
+        if (natom == 4) k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
+        else k4_hist_build_ws<3><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
       } else if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
       else k4_hist_build<3><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
