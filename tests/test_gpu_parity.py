@@ -625,3 +625,64 @@ def test_percentile_objectives_renew_leaf_outputs(built, objective, extra, weigh
     names = b.eval_names()
     assert names == [{"regression_l1": "l1"}.get(objective, objective)]
     assert np.isfinite(b.get_eval(0)[0])
+
+
+@pytest.mark.parametrize("n,F,case", [
+    (45, 3, "tiny"),                 # fewer rows than a warp; min_data_in_leaf=20 leaves room for exactly one split
+    (1000, 1, "one_feature"),
+    (5000, 33, "tile_boundary"),     # 33 used features = 2 tiles, the second holding one feature
+    (5000, 40, "trivial_columns"),   # constant / all-NaN / all-zero columns are dropped by the bin finder (used-feature map)
+    (4000, 6, "duplicates"),         # heavy ties: few distinct values per feature, duplicated rows
+    (1537, 5, "ragged_blocks"),      # not a multiple of 32 / 512 / 1024 / 2048 (stage, bagging block, partition chunk sizes)
+])
+def test_edge_shapes(built, n, F, case):
+    """Ragged and degenerate inputs through the whole path (binning, K4 staging tails, partition chunks, model text)."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(1000 + n)
+    X = rng.standard_normal((n, F))
+    if case == "trivial_columns":
+        X[:, 3] = 7.5; X[:, 10] = np.nan; X[:, 17] = 0.0; X[:, 25] = np.where(rng.random(n) < 0.999, 0.0, 1.0)
+    if case == "duplicates":
+        X = np.round(X[rng.integers(0, 200, n)] * 2) / 2
+    y = (X[:, 0] + (np.nan_to_num(X[:, min(1, F - 1)]) > 0.3) + 0.2 * rng.standard_normal(n)).astype(np.float32)
+    ds, ods = _make(X, y)
+    assert np.array_equal(ds.get_bins(), ods.bins())
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("regression", "", leaves=15), 6)
+    compare_models(m, om)
+    np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=0, atol=1e-9)
+    # bagging on a ragged row count exercises the partial last LCG block
+    b2, ob2, m2, om2 = _train_both(ds, ods, _without(_classifier_params("regression", "", leaves=7), "bagging_fraction", "bagging_freq") + " bagging_fraction=0.7 bagging_freq=1", 4)
+    compare_models(m2, om2)
+
+
+def test_no_usable_feature_gives_constant_model(built):
+    """every column trivial => no tree can be grown: one constant tree holding the label mean, is_finished on the first call."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model
+    X = np.ones((500, 4)); X[:, 1] = np.nan
+    y = np.linspace(0, 1, 500).astype(np.float32)
+    ds, ods = _make(X, y)
+    b = capi.Booster(ds, "objective=regression verbosity=-1")
+    from oracle import oracle as O
+    ob = O.OracleBooster(ods, "objective=regression verbosity=-1")
+    assert b.update_one_iter() == ob.update()
+    m, om = parse_model(b.save_model_to_string()), parse_model(ob.model_string())
+    assert len(m["trees"]) == len(om["trees"])
+    if m["trees"]:
+        np.testing.assert_allclose(m["trees"][0]["leaf_value"], om["trees"][0]["leaf_value"], rtol=1e-12)
+    np.testing.assert_allclose(b.predict_for_mat(X[:3], predict_type=1).ravel(), float(np.mean(y)), rtol=1e-6)
+
+
+def test_zero_and_extreme_weights_and_gradients(built):
+    """weights spanning 12 orders of magnitude and zero-weight rows: the per-tree fixed-point scale follows max|g| and the
+    reconstructed counts follow the hessians, as in the oracle."""
+    from mmlspark_b200.modeltext import compare_models
+    rng = np.random.default_rng(77)
+    n, F = 20000, 6
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] - X[:, 1] + 0.3 * rng.standard_normal(n) > 0).astype(np.float32)
+    w = np.exp(rng.uniform(-6, 6, n)).astype(np.float32)
+    w[rng.random(n) < 0.05] = 0.0
+    ds, ods = _make(X, y, weight=w)
+    b, ob, m, om = _train_both(ds, ods, _classifier_params("binary", "is_unbalance=false min_sum_hessian_in_leaf=1e-3", leaves=15), 8)
+    compare_models(m, om, check_counts=True)
