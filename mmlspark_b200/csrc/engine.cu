@@ -1272,7 +1272,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
     } else {
       if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2 (fallback)
-      k_scan<<<sgrid, 256, kScanSmem, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+      k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);   // the scratch is only touched by categorical features
       k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
     }
     k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);

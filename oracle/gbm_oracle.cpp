@@ -3,8 +3,8 @@
 //
 // CPU restatement (C++17 + OpenMP) of the LightGBM-on-Spark training hot path that MMLSpark
 // reaches through SWIG: bin finding + binning, objectives, per-leaf fp64
-// feature histograms, numerical best-split scan, leaf-wise growth with histogram subtraction,
-// GBDT loop and model-text v3 writer.
+// feature histograms, numerical and categorical best-split scans, leaf-wise growth with histogram
+// subtraction, bagging / GOSS / RF / DART, leaf-output renewal, GBDT loop and model-text v3 writer.
 //
 // PARITY UNPINNED: the arithmetic lives in the un-vendored Maven artifact
 // com.microsoft.ml.lightgbm:lightgbmlib:3.2.110 (/root/reference/build.sbt:222), whose source
@@ -18,6 +18,12 @@
 //   model string       lightgbm/src/main/scala/com/microsoft/ml/spark/lightgbm/booster/LightGBMBooster.scala:269-274
 // The reference's own tests hold no bit-level vectors for this path; its only
 // known-answer tests (countCardinality, VerifyLightGBMRanker.scala:127-137) are checked in tests/.
+// Independent cross-check (tests/test_oracle_vs_sklearn_cpu.py): on data where the bin finders agree by
+// construction this oracle and scikit-learn's HistGradientBoosting (a separate implementation of the same
+// algorithm family) fit the same model to 1e-13 — regression, binary, max_depth, NaN default direction,
+// weights, categorical splits — once LightGBM's is_splittable inheritance rule is accounted for.  That
+// pins the shared algorithm, not LightGBM's remaining idiosyncrasies (bin finder, tie-breaks, DART/GOSS
+// details), which stay unpinned against the real binary.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -83,6 +89,7 @@ struct Config {
   double drop_rate = 0.1, skip_drop = 0.5;
   int max_drop = 50, drop_seed = 4;
   bool uniform_drop = false, xgboost_dart_mode = false;
+  bool oracle_inherit_splittable = true;   // test-only switch: false = children re-examine every feature (what sklearn's HGB does)
   std::string tree_learner = "serial";
   int verbosity = 1;
   std::map<std::string, std::string> raw;
@@ -157,6 +164,7 @@ struct Config {
     getd("top_rate", top_rate); getd("other_rate", other_rate);
     getd("drop_rate", drop_rate); getd("skip_drop", skip_drop); geti("max_drop", max_drop); geti("drop_seed", drop_seed);
     getb("uniform_drop", uniform_drop); getb("xgboost_dart_mode", xgboost_dart_mode);
+    getb("oracle_inherit_splittable", oracle_inherit_splittable);
     if (boosting == "random_forest") boosting = "rf";
     if (boosting == "gbrt") boosting = "gbdt";
     auto split_list = [&](const char* k, auto& out, auto conv) {
@@ -1509,6 +1517,7 @@ struct TreeLearner {
           if (larger != left_leaf) { pool[larger].swap(pool[left_leaf]); }
           // children inherit the parent's per-feature splittable flags
           std::vector<uint8_t> pf = splittable[left_leaf];
+          if (!cfg.oracle_inherit_splittable) pf.assign(feature_used.begin(), feature_used.end());
           splittable[left_leaf] = pf; splittable[right_leaf] = pf;
         }
         smaller_rows = leaf_cnt[smaller];

@@ -686,3 +686,41 @@ def test_zero_and_extreme_weights_and_gradients(built):
     ds, ods = _make(X, y, weight=w)
     b, ob, m, om = _train_both(ds, ods, _classifier_params("binary", "is_unbalance=false min_sum_hessian_in_leaf=1e-3", leaves=15), 8)
     compare_models(m, om, check_counts=True)
+
+
+@pytest.mark.parametrize("case", ["regression_nan", "binary", "categorical_weights"])
+def test_cuda_path_matches_sklearn_hist_gradient_boosting(built, case):
+    """The CUDA path against an INDEPENDENT implementation (scikit-learn's HistGradientBoosting), no oracle involved: on
+    integer-valued features both bin finders put one bin per distinct value, so the fitted models must be the same function
+    (tests/test_oracle_vs_sklearn_cpu.py explains the construction).  Tolerance 1e-6: the north star's leaf-value bar."""
+    sk = pytest.importorskip("sklearn.ensemble")
+    from mmlspark_b200 import capi
+    rng = np.random.default_rng(16)
+    n, F = 20000, 8
+    X = rng.integers(-20, 30, size=(n, F)).astype(np.float64)
+    y = (0.3 * X[:, 0] - 0.02 * X[:, 1] ** 2 + 0.5 * (X[:, 2] > 3) * X[:, 3] + rng.standard_normal(n)).astype(np.float32)
+    base = "num_leaves=31 learning_rate=0.1 min_data_in_leaf=20 min_sum_hessian_in_leaf=0.001 verbosity=-1 "
+    common = dict(learning_rate=0.1, max_iter=15, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255, early_stopping=False)
+    w, ds_params = None, DS_PARAMS
+    if case == "regression_nan":
+        X[rng.random(X.shape) < 0.1] = np.nan
+        h = sk.HistGradientBoostingRegressor(loss="squared_error", **common).fit(X, y.astype(np.float64))
+        params, want = base + "objective=regression", h.predict(X)
+    elif case == "binary":
+        y = (y > np.median(y)).astype(np.float32)
+        h = sk.HistGradientBoostingClassifier(loss="log_loss", **common).fit(X, y)
+        params, want = base + "objective=binary", h.decision_function(X)
+    else:
+        X[:, 4] = rng.integers(0, 12, n)
+        w = rng.integers(1, 4, n).astype(np.float32)
+        h = sk.HistGradientBoostingRegressor(loss="squared_error", categorical_features=[4], **common).fit(X, y.astype(np.float64), sample_weight=w.astype(np.float64))
+        params, want, ds_params = base + "objective=regression", h.predict(X), DS_PARAMS + " categorical_feature=4"
+    ds = capi.Dataset.from_mat(X, ds_params)
+    ds.set_field("label", y)
+    if w is not None:
+        ds.set_field("weight", w)
+    b = capi.Booster(ds, params)
+    for _ in range(15):
+        assert not b.update_one_iter()
+    got = b.predict_device(X, predict_type=1).ravel()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)

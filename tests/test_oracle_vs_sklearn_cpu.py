@@ -1,0 +1,82 @@
+"""Independent cross-check of the oracle ("cross-checked structurally against sklearn HGB where conditions allow").
+
+The real lightgbmlib 3.2.110 cannot run here, so the oracle is "parity unpinned" against it.  scikit-learn's
+HistGradientBoosting is an independent implementation of the same algorithm family (histogram GBDT, leaf-wise growth, the XGBoost
+gain, fp32 gradients, NaN bin with a learned default direction, LightGBM-style categorical splits).  On data where the two bin
+finders agree by construction (integer-valued features with < 255 distinct values: both put one bin per distinct value) the two must
+produce the SAME model; they do, to 1e-13, for regression / binary / max_depth / NaN / weights / categorical.  The one LightGBM-specific
+rule sklearn does not have — children inherit the parent's per-feature `is_splittable` flags — is isolated with the oracle's test-only
+switch `oracle_inherit_splittable=false`."""
+import numpy as np
+import pytest
+
+sk = pytest.importorskip("sklearn.ensemble")
+
+BASE = "num_leaves=31 learning_rate=0.1 min_data_in_leaf=20 min_sum_hessian_in_leaf=0.001 verbosity=-1 "
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle as O
+    return O
+
+
+def _data(seed=6, n=20000, F=8):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(-20, 30, size=(n, F)).astype(np.float64)
+    y = (0.3 * X[:, 0] - 0.02 * X[:, 1] ** 2 + 0.5 * (X[:, 2] > 3) * X[:, 3] + rng.standard_normal(n)).astype(np.float32)
+    return rng, X, y
+
+
+def _hgb_reg(iters, **kw):
+    return sk.HistGradientBoostingRegressor(loss="squared_error", learning_rate=0.1, max_iter=iters, max_leaf_nodes=31, min_samples_leaf=20,
+                                            max_bins=255, early_stopping=False, **kw)
+
+
+def _oracle_pred(O, X, y, params, iters, ds_params="max_bin=255", weight=None):
+    ds = O.OracleDataset(X, ds_params).set_field("label", y)
+    if weight is not None:
+        ds.set_field("weight", weight.astype(np.float32))
+    b = O.OracleBooster(ds, BASE + params)
+    b.train(iters)
+    return b.predict_raw(X)[:, 0]
+
+
+@pytest.mark.parametrize("case", ["plain", "max_depth", "nan", "weights", "l2_small", "categorical"])
+def test_regression_matches_sklearn_hgb(O, case):
+    rng, X, y = _data()
+    kw, params, ds_params, w, iters = {}, "objective=regression", "max_bin=255", None, 20
+    if case == "max_depth":
+        kw, params = dict(max_depth=4), params + " max_depth=4"
+    elif case == "nan":
+        X = X.copy(); X[rng.random(X.shape) < 0.1] = np.nan
+    elif case == "weights":
+        w = rng.integers(1, 4, len(y)).astype(np.float64)
+    elif case == "l2_small":
+        kw, params, iters = dict(l2_regularization=0.5), params + " lambda_l2=0.5", 5
+    elif case == "categorical":
+        X = X.copy(); X[:, 4] = rng.integers(0, 12, len(y))
+        kw, ds_params, iters = dict(categorical_features=[4]), "max_bin=255 categorical_feature=4", 10
+    h = _hgb_reg(iters, **kw).fit(X, y.astype(np.float64), sample_weight=w)
+    got = _oracle_pred(O, X, y, params, iters, ds_params, w)
+    np.testing.assert_allclose(got, h.predict(X), rtol=0, atol=1e-10)
+
+
+def test_binary_logloss_matches_sklearn_hgb(O):
+    _, X, y = _data(7)
+    yb = (y > np.median(y)).astype(np.float32)
+    h = sk.HistGradientBoostingClassifier(loss="log_loss", learning_rate=0.1, max_iter=20, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255,
+                                          early_stopping=False).fit(X, yb)
+    got = _oracle_pred(O, X, yb, "objective=binary", 20)
+    np.testing.assert_allclose(got, h.decision_function(X), rtol=0, atol=1e-10)      # incl. the log-odds init score
+
+
+def test_splittable_inheritance_is_the_only_structural_difference(O):
+    """Strong L2 makes some features unsplittable in a parent; LightGBM's children then never look at them again, sklearn's do."""
+    _, X, y = _data()
+    h = _hgb_reg(3, l2_regularization=50.0).fit(X, y.astype(np.float64))
+    ref = h.predict(X)
+    without_rule = _oracle_pred(O, X, y, "objective=regression lambda_l2=50 oracle_inherit_splittable=false", 3)
+    with_rule = _oracle_pred(O, X, y, "objective=regression lambda_l2=50", 3)
+    np.testing.assert_allclose(without_rule, ref, rtol=0, atol=1e-10)
+    assert np.abs(with_rule - ref).max() > 1e-3          # the LightGBM rule changes this model (HistogramPool flags)
