@@ -1687,28 +1687,31 @@ void Booster::UploadForest() {
   const size_t T = model.trees.size();
   std::vector<int> toff(T + 1, 0), loff(T + 1, 0), nl(T), sf, dt, lc, rc, cbeg, clen;
   std::vector<unsigned> cwords;
-  std::vector<double> thr, lv;
+  std::vector<double> thr, lv, ncnt, lcnt, expv(T, 0.0);
   for (size_t t = 0; t < T; ++t) {
     const HostTree& tr = *model.trees[t];
     nl[t] = tr.num_leaves;
+    expv[t] = tr.ExpectedValue();
+    if (tr.num_leaves > 1) f.max_depth = std::max(f.max_depth, tr.MaxDepth());
     toff[t + 1] = toff[t] + std::max(tr.num_leaves - 1, 0);
     loff[t + 1] = loff[t] + tr.num_leaves;
     for (int i = 0; i < tr.num_leaves - 1; ++i) {
       sf.push_back(tr.split_feature[i]); dt.push_back(tr.decision_type[i]); lc.push_back(tr.left_child[i]); rc.push_back(tr.right_child[i]);
-      thr.push_back(tr.threshold[i]);
+      thr.push_back(tr.threshold[i]); ncnt.push_back(tr.internal_count[i]);
       if (tr.decision_type[i] & 1) {
         const int ci = static_cast<int>(tr.threshold[i]);
         cbeg.push_back(static_cast<int>(cwords.size())); clen.push_back(tr.cat_boundaries[ci + 1] - tr.cat_boundaries[ci]);
         for (int w = tr.cat_boundaries[ci]; w < tr.cat_boundaries[ci + 1]; ++w) cwords.push_back(tr.cat_threshold[w]);
       } else { cbeg.push_back(0); clen.push_back(0); }
     }
-    for (int i = 0; i < tr.num_leaves; ++i) lv.push_back(tr.leaf_value[i]);
+    for (int i = 0; i < tr.num_leaves; ++i) { lv.push_back(tr.leaf_value[i]); lcnt.push_back(tr.leaf_count[i]); }
   }
   if (!stream_) B200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   auto up_i = [&](DevBuf<int>& d, std::vector<int>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
   auto up_d = [&](DevBuf<double>& d, std::vector<double>& h) { d.Alloc(std::max<size_t>(h.size(), 1)); if (!h.empty()) d.Upload(h.data(), h.size(), stream_); };
   up_i(f.tree_offset, toff); up_i(f.leaf_offset, loff); up_i(f.num_leaves, nl); up_i(f.split_feature, sf); up_i(f.decision_type, dt);
   up_i(f.left_child, lc); up_i(f.right_child, rc); up_d(f.threshold, thr); up_d(f.leaf_value, lv); up_i(f.cat_begin, cbeg); up_i(f.cat_len, clen);
+  up_d(f.node_count, ncnt); up_d(f.leaf_count, lcnt); up_d(f.expected, expv);
   f.cat_words.Alloc(std::max<size_t>(cwords.size(), 1));
   if (!cwords.empty()) f.cat_words.Upload(cwords.data(), cwords.size(), stream_);
   B200_CUDA(cudaStreamSynchronize(stream_));
@@ -1719,19 +1722,34 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
                               double* out) {
   EnsureDevice();
   if (data_type != 0 && data_type != 1) Fatal("PredictBatch: unknown data type");
-  if (predict_type < 0 || predict_type > 2) Fatal("PredictBatch supports normal / raw-score / leaf-index prediction (SHAP stays on the host predictor)");
+  if (predict_type < 0 || predict_type > 3) Fatal("PredictBatch: unknown predict type");
   if (ncol < model.max_feature_idx + 1) Fatal("PredictBatch: the matrix has fewer columns than the model has features");
   UploadForest();
   const ForestBufs& fb = *forest_;
   ForestDev f{fb.tree_offset.p, fb.leaf_offset.p, fb.num_leaves.p, fb.split_feature.p, fb.threshold.p, fb.decision_type.p, fb.left_child.p, fb.right_child.p, fb.leaf_value.p,
-              fb.cat_begin.p, fb.cat_len.p, fb.cat_words.p};
+              fb.cat_begin.p, fb.cat_len.p, fb.cat_words.p, fb.node_count.p, fb.leaf_count.p, fb.expected.p};
   int t0, t1;
   model.IterRange(start_iteration, num_iteration, &t0, &t1);
   const int Kc = model.num_tree_per_iteration;
-  const int64_t per_row = predict_type == 2 ? (t1 - t0) : Kc;
+  const int F1 = model.max_feature_idx + 2;            // contributions: one per feature + the expected value
+  const int64_t per_row = predict_type == 2 ? (t1 - t0) : predict_type == 3 ? static_cast<int64_t>(Kc) * F1 : Kc;
   const size_t esz = data_type == 0 ? 4 : 8;
   const bool on_device = IsDevicePointer(data);
-  const int64_t chunk = on_device ? nrow : std::max<int64_t>(1, std::min<int64_t>(nrow, (512LL << 20) / (static_cast<int64_t>(ncol) * esz)));
+  int64_t chunk = on_device ? nrow : std::max<int64_t>(1, std::min<int64_t>(nrow, (512LL << 20) / (static_cast<int64_t>(ncol) * esz)));
+  chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (1024LL << 20) / (per_row * 8)));      // bound the device output buffer too (contributions are wide)
+  // TreeSHAP scratch: per thread (depth+2)(depth+3)/2 path elements + depth+3 stack frames (kernels.cuh k_predict_contrib)
+  const int shap_threads = 128;
+  int shap_grid = 0, path_stride = 0, frame_stride = 0;
+  DevBuf<ShapPathElem> shap_paths;
+  DevBuf<ShapFrame> shap_frames;
+  if (predict_type == 3) {
+    const int md = fb.max_depth + 2;
+    path_stride = md * (md + 1) / 2 + md;
+    frame_stride = md + 2;
+    shap_grid = static_cast<int>(std::min<int64_t>((std::min(chunk, nrow) + shap_threads - 1) / shap_threads, static_cast<int64_t>(num_sms_ > 0 ? num_sms_ : 148) * 4));
+    shap_paths.Alloc(static_cast<size_t>(shap_grid) * shap_threads * path_stride);
+    shap_frames.Alloc(static_cast<size_t>(shap_grid) * shap_threads * frame_stride);
+  }
   DevBuf<unsigned char> xin;
   if (!on_device) xin.Alloc(static_cast<size_t>(chunk) * ncol * esz);
   DevBuf<double> dout; dout.Alloc(static_cast<size_t>(std::min(chunk, nrow)) * per_row);
@@ -1745,7 +1763,11 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
     const void* x = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esz;
     if (!on_device) { B200_CUDA(cudaMemcpyAsync(xin.p, x, static_cast<size_t>(rows) * ncol * esz, cudaMemcpyHostToDevice, stream_)); x = xin.p; }
     const int grid = static_cast<int>(std::min<int64_t>((rows * per_row + 255) / 256, static_cast<int64_t>(sms) * 16));
-    if (predict_type == 2) {
+    if (predict_type == 3) {
+      B200_CUDA(cudaMemsetAsync(dout.p, 0, static_cast<size_t>(rows) * per_row * sizeof(double), stream_));
+      if (data_type == 0) k_predict_contrib<float><<<shap_grid, shap_threads, 0, stream_>>>(f, static_cast<const float*>(x), rows, ncol, Kc, t0, t1, F1, shap_paths.p, path_stride, shap_frames.p, frame_stride, dout.p);
+      else k_predict_contrib<double><<<shap_grid, shap_threads, 0, stream_>>>(f, static_cast<const double*>(x), rows, ncol, Kc, t0, t1, F1, shap_paths.p, path_stride, shap_frames.p, frame_stride, dout.p);
+    } else if (predict_type == 2) {
       if (data_type == 0) k_predict_leaf<float><<<grid, 256, 0, stream_>>>(f, static_cast<const float*>(x), rows, ncol, t0, t1, dout.p);
       else k_predict_leaf<double><<<grid, 256, 0, stream_>>>(f, static_cast<const double*>(x), rows, ncol, t0, t1, dout.p);
     } else {
@@ -1762,7 +1784,7 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
   cudaEventElapsedTime(&ms, e0, e1);
   last_predict_ms = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  const bool avg = model.average_output && t1 > t0 && predict_type != 2;      // rf: raw score = mean over the iterations
+  const bool avg = model.average_output && t1 > t0 && predict_type < 2;       // rf: raw score = mean over the iterations
   if (avg && predict_type == 1)
     for (int64_t i = 0; i < nrow * Kc; ++i) out[i] /= ((t1 - t0) / Kc);
   if (predict_type == 0) {          // objective transform on the host, identical to the single-row predictor

@@ -259,7 +259,7 @@ class Booster {
   unsigned epoch_ = 0;
   void SetupPeerReduce();
   // flattened forest for PredictBatch
-  struct ForestBufs { DevBuf<int> tree_offset, leaf_offset, num_leaves, split_feature, decision_type, left_child, right_child, cat_begin, cat_len; DevBuf<double> threshold, leaf_value; DevBuf<unsigned> cat_words; size_t trees = 0; };
+  struct ForestBufs { DevBuf<int> tree_offset, leaf_offset, num_leaves, split_feature, decision_type, left_child, right_child, cat_begin, cat_len; DevBuf<double> threshold, leaf_value, node_count, leaf_count, expected; DevBuf<unsigned> cat_words; size_t trees = 0; int max_depth = 0; };
   std::unique_ptr<ForestBufs> forest_;
   void UploadForest();
   std::vector<ValidSet*> valids_;

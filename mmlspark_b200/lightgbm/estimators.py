@@ -158,7 +158,9 @@ class _ModelBase(Params):
             out = out.with_column(self.get("leafPredictionCol"), self.booster._handle().predict_device(
                 X, capi.PREDICT_LEAF_INDEX, self.booster.startIteration, self.booster.numIterations))
         if self.get("featuresShapCol"):
-            out = out.with_column(self.get("featuresShapCol"), np.stack([self.booster.featuresShap(r) for r in X]))
+            # batched TreeSHAP on the GPU (k_predict_contrib); same values as the per-row featuresShap() the reference's UDF calls
+            out = out.with_column(self.get("featuresShapCol"), self.booster._handle().predict_device(
+                X, capi.PREDICT_CONTRIB, self.booster.startIteration, self.booster.numIterations))
         return out
 
     @classmethod

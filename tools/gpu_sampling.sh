@@ -1,4 +1,4 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "sklearn" 2>&1 | tail -30
+timeout 500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_estimators.py -m gpu -x -q -k "treeshap or shap" 2>&1 | tail -30
