@@ -80,3 +80,15 @@ def test_splittable_inheritance_is_the_only_structural_difference(O):
     with_rule = _oracle_pred(O, X, y, "objective=regression lambda_l2=50", 3)
     np.testing.assert_allclose(without_rule, ref, rtol=0, atol=1e-10)
     assert np.abs(with_rule - ref).max() > 1e-3          # the LightGBM rule changes this model (HistogramPool flags)
+
+
+def test_poisson_matches_sklearn_hgb(O):
+    """log-link Poisson deviance: same gradients/hessians once LightGBM's hessian safeguard `poisson_max_delta_step` is 0
+    (sklearn has none); init score log(mean y) in both."""
+    rng, X, _ = _data(9)
+    mu = np.exp(0.03 * X[:, 0] - 0.001 * X[:, 1] ** 2 + 0.02 * (X[:, 2] > 3) * X[:, 3])
+    y = rng.poisson(mu).astype(np.float32)
+    h = sk.HistGradientBoostingRegressor(loss="poisson", learning_rate=0.1, max_iter=15, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255,
+                                         early_stopping=False).fit(X, y.astype(np.float64))
+    got = _oracle_pred(O, X, y, "objective=poisson poisson_max_delta_step=0", 15)
+    np.testing.assert_allclose(got, h._raw_predict(X).ravel(), rtol=0, atol=1e-10)
