@@ -640,7 +640,7 @@ static float LabelWeightedPercentile(const float* y, const float* w, int cnt, do
 
 // =============================================================================== booster
 static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
-constexpr int kScanSmem = 8 * (768 + 32) * 8;     // k_scan: per-warp scratch of the categorical split search
+constexpr int kScanSmem = 8 * (768 + 64) * 8;     // k_scan: per-warp scratch of the categorical split search
 
 Booster::Booster(const std::string& model_text) {
   std::unique_ptr<HostModel> m = HostModel::FromString(model_text);
@@ -710,6 +710,12 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
 }
 
 Booster::~Booster() {
+  if (split_op_trees_ > 0) {
+    double tot = 0; for (auto& kv : split_op_ms_) tot += kv.second;
+    fprintf(stderr, "[b200gbm split timing] %d trees, %.3f ms per tree in split operations:", split_op_trees_, tot / split_op_trees_);
+    for (auto& kv : split_op_ms_) fprintf(stderr, " %s=%.1fus", kv.first.c_str(), 1000.0 * kv.second / split_op_trees_ / std::max(cfg.num_leaves - 1, 1));
+    fprintf(stderr, " (per split)\n");
+  }
   for (auto* v : valids_) delete v;
   for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   if (tree_host_) cudaFreeHost(tree_host_);
@@ -1252,11 +1258,20 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, num_sms_ * 8));
   const dim3 sgrid((d.nf + 7) / 8, 2);
   std::vector<cudaEvent_t> evs;
+  // B200GBM_SPLIT_TIMING=1 (debug): an event after every operation of a split; per-operation averages go to stderr when the booster is freed
+  static const bool split_timing = getenv("B200GBM_SPLIT_TIMING") != nullptr;
+  std::vector<cudaEvent_t> sev;
+  auto mark = [&]() { if (split_timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); sev.push_back(e); } };
   for (int split = 0; split < L - 1; ++split) {
+    mark();
     k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 0);
+    mark();
     B200_CUDA(cudaMemsetAsync(H_.p, 0, slot_elems_ * sizeof(long long), s));
+    mark();
     if (profile_hist) { cudaEvent_t a, b; B200_CUDA(cudaEventCreate(&a)); B200_CUDA(cudaEventCreate(&b)); evs.push_back(a); evs.push_back(b); B200_CUDA(cudaEventRecord(a, s)); }
-    k_gather_q<<<egrid, 256, 0, s>>>(&ctrl->hist_work, idx0_.p, idx1_.p, qgh_.p, qord_.p);
+    // leaf order of the (g,h) words: written by the previous split's k_part_scatter; only a bagged root needs its own pass
+    if (split == 0 && use_bag_) k_gather_q<<<egrid, 256, 0, s>>>(&ctrl->hist_work, idx0_.p, idx1_.p, qgh_.p, qord_.p);
+    mark();
     if (const_hessian_)
       k4_hist_build_ws<3><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
@@ -1264,6 +1279,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k4_hist_build_ws<4><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
     if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
+    mark();
     if (fused_) {
       // C2+K5+C3 fused over NVLink peer memory: signal "histogram ready", then the scan reduces its owned slice from all peers
       ++epoch_;
@@ -1272,13 +1288,18 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
     } else {
       if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2 (fallback)
-      k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);   // the scratch is only touched by categorical features
-      k_pick<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_);
+      mark();
+      // scan + (last block) pick; the dynamic scratch is only touched by categorical features
+      k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+      mark();
     }
     k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
-    k_part_scan<<<1, 1024, 0, s>>>(ctrl, part_chunks_.p);
-    k_part_scatter<<<pgrid, 256, 0, s>>>(ctrl, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
-    timing.launches += 8; timing.hist_launches += 1;
+    mark();
+    k_part_scan<<<1, 1024, 0, s>>>(ctrl, leaves_.p, parallel_ ? 1 : 0, part_chunks_.p);
+    mark();
+    k_part_scatter<<<pgrid, 256, 0, s>>>(ctrl, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p, qgh_.p, qord_.p);
+    mark();
+    timing.launches += fused_ ? 7 : 6; timing.hist_launches += 1;
   }
   k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 1);
   if (renew_kind_) RenewTreeOutput(k, is_rf_ ? rf_init_scores_[k] : 0.0);
@@ -1297,6 +1318,14 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   B200_CUDA(cudaMemcpyAsync(tree_host_, tree_blob_.p, tree_blob_bytes_, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl, sizeof(TreeCtrl), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
+  if (split_timing && !fused_ && !sev.empty()) {
+    static const char* kOps[] = {"round_ctl", "memset_H", "gather_q(bagged root)", "K4", "allreduce", "scan+pick", "part_count", "part_scan", "part_scatter"};
+    const int per = 10;      // marks per split
+    for (size_t b0 = 0; b0 + per <= sev.size(); b0 += per)
+      for (int o = 0; o < per - 1; ++o) { float ms = 0; cudaEventElapsedTime(&ms, sev[b0 + o], sev[b0 + o + 1]); split_op_ms_[kOps[o]] += ms; }
+    split_op_trees_ += 1;
+    for (auto e : sev) cudaEventDestroy(e);
+  }
   if (profile_hist) {
     for (size_t i = 0; i + 1 < evs.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); timing.hist_ms += ms; }
     for (auto e : evs) cudaEventDestroy(e);

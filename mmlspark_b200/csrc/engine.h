@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -155,6 +156,7 @@ class Booster {
   // instrumentation for bench.py / parity tests (B200GBM_* extensions of the C ABI)
   struct Timing { double hist_ms = 0, total_ms = 0; long long hist_rows = 0; long long hist_launches = 0, launches = 0; };
   Timing timing;
+  std::map<std::string, double> split_op_ms_; int split_op_trees_ = 0;      // B200GBM_SPLIT_TIMING debug accounting
   bool profile_hist = false;                              // time K4 with events on the engine stream
   void ExportLastHistogram(double* out);                  // fp64 view of the scratch histogram of the last round
   std::vector<double> trace;                              // per split records (see B200GBM_BoosterGetTrace)

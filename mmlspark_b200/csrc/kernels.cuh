@@ -65,6 +65,8 @@ struct TreeCtrl {
   double inv_g, inv_h;         // hist value -> real value
   long long root_q[4];         // sum q_g, sum q_h, local rows, unused  (allreduced)
   long long trace_rows;        // sum of rows scanned by K4 this tree (for the roofline byte model)
+  unsigned scan_ticket;        // blocks of k_scan that finished this round (the last one runs the pick step)
+  int q_side;                  // partition: side (0 left, 1 right) whose rows K4 will scan next = the smaller child
 };
 
 struct TreeDev {               // SoA tree under construction (sizes: num_leaves / num_leaves-1)
@@ -593,7 +595,7 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
 // Categorical split search for one feature by one warp (FeatureHistogram::FindBestThresholdCategoricalInner [UPSTREAM]):
 // one-hot when num_bin <= max_cat_to_onehot; otherwise the bins holding >= cat_smooth rows are ranked by g/(h+cat_smooth)
 // (stable, ties by bin) and accumulated from both ends, at most max_cat_threshold bins, lambda_l2 += cat_l2.
-// ws = this warp's shared scratch: g[256], h[256], ctr[256] doubles + order[256] bytes.
+// ws = this warp's shared scratch: g[256], h[256], ctr[256] doubles + order[256] + used[256] bytes.
 __device__ __forceinline__ void d_scan_feature_cat(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
                                                    double inv_g, double inv_h, const SplitParams& p, uint8_t* flag, SplitCand* outp, double* ws) {
   SplitCand& out = *outp;
@@ -654,37 +656,32 @@ __device__ __forceinline__ void d_scan_feature_cat(const long long (&qg)[8], con
     }
     return;
   }
-  // ---- rank the used bins by ctr (stable): rank = #{used j : ctr_j < ctr_i  or (== and j < i)}
-  // every lane needs the global used set: 8 words via ballots of the per-bin flags
-  unsigned used_words[8];
-#pragma unroll
-  for (int wd = 0; wd < 8; ++wd) used_words[wd] = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // bin = lane*8 + j  -> word = lane>>2, bit = (lane&3)*8 + j
-    const unsigned bal = __ballot_sync(0xffffffffu, (used_mask >> j) & 1u);
-    for (int l = 0; l < 32; ++l) if ((bal >> l) & 1u) used_words[l >> 2] |= 1u << (((l & 3) << 3) + j);
-  }
+  // ---- rank the used bins by ctr (stable): rank = #{used j : ctr_j < ctr_i  or (== and j < i)}.
+  // Uniform loop over the bins: sc[bj] / usedb[bj] are broadcast loads, the 8 comparisons of a lane are independent.
+  unsigned char* usedb = order + 256;
   int used_bin = 0;
-#pragma unroll
-  for (int wd = 0; wd < 8; ++wd) used_bin += __popc(used_words[wd]);
+  double ci[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (!((used_mask >> j) & 1u)) continue;
-    const int bi = lane * 8 + j;
-    const double ci = sc[bi];
-    int rank = 0;
-    for (int wd = 0; wd < 8; ++wd) {
-      unsigned wbits = used_words[wd];
-      while (wbits) {
-        const int bj = wd * 32 + __ffs(wbits) - 1;
-        wbits &= wbits - 1;
-        const double cj = sc[bj];
-        rank += (cj < ci) || (cj == ci && bj < bi);
-      }
-    }
-    order[rank] = static_cast<unsigned char>(bi);
+    const int b = lane * 8 + j;
+    const bool u = (used_mask >> j) & 1u;
+    usedb[b] = u ? 1 : 0;
+    ci[j] = sc[b];
+    used_bin += __popc(__ballot_sync(0xffffffffu, u));
   }
+  __syncwarp();
+  int rank[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rank[j] = 0;
+  for (int bj = 1; bj < m.num_bin; ++bj) {
+    if (!usedb[bj]) continue;             // same bj in every lane: no divergence
+    const double cj = sc[bj];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rank[j] += (cj < ci[j]) || (cj == ci[j] && bj < lane * 8 + j);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if ((used_mask >> j) & 1u) order[rank[j]] = static_cast<unsigned char>(lane * 8 + j);
   __syncwarp();
   if (lane == 0) {
     SplitParams pc = p;
@@ -727,23 +724,145 @@ __device__ __forceinline__ void d_scan_feature_cat(const long long (&qg)[8], con
   }
 }
 
+__device__ __forceinline__ void d_choose_leaf(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitParams& p, int lane) {
+  double bg = kNegInf; int bf = 0x7fffffff, bl = 0x7fffffff;
+  const int nl = ctrl->num_leaves;
+  for (int l = lane; l < nl; l += 32) {
+    const double g = leaves[l].best.gain;
+    const int fi = leaves[l].best.feature;
+    const int f = fi < 0 ? 0x7fffffff : meta[fi].real_index;
+    if (g > bg || (g == bg && (f < bf || (f == bf && l < bl)))) { bg = g; bf = f; bl = l; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, bg, o);
+    const int of = __shfl_xor_sync(0xffffffffu, bf, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (og > bg || (og == bg && (of < bf || (of == bf && ol < bl)))) { bg = og; bf = of; bl = ol; }
+  }
+  if (lane != 0) return;
+  const int best_leaf = bl == 0x7fffffff ? 0 : bl;
+  const LeafBest& b = leaves[best_leaf].best;
+  if (!(b.gain > 0.0) || ctrl->num_leaves >= p.num_leaves) {
+    ctrl->finished = 1; ctrl->split_leaf = -1; ctrl->part_count = 0;
+  } else {
+    const LeafState& L = leaves[best_leaf];
+    const FeatMeta fm = meta[b.feature];
+    ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
+    ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
+    ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
+    ctrl->split_is_cat = b.is_cat;
+    for (int wd = 0; wd < 8; ++wd) ctrl->split_cat_bits[wd] = b.cat_bits[wd];
+    ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
+    ctrl->part_left_total = 0;
+  }
+}
+
+// candidates are written by other blocks of the same kernel: read them through L2 (ld.global.cg), never from this SM's L1
+__device__ __forceinline__ SplitCand d_load_cand(const SplitCand* c) {
+  static_assert(sizeof(SplitCand) % 8 == 0, "SplitCand is copied in 8-byte words");
+  SplitCand out;
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(c);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(&out);
+#pragma unroll
+  for (int i = 0; i < static_cast<int>(sizeof(SplitCand) / 8); ++i) dst[i] = __ldcg(src + i);
+  return out;
+}
+// best candidate per leaf (argmax over features, ties -> smaller real feature index), then the leaf to split; one 256-thread block
+__device__ void
+d_pick_block(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* cands, const SplitParams& p) {
+  __shared__ double s_gain[256];
+  __shared__ int s_feat[256], s_idx[256];
+  if (ctrl->go) {
+    for (int which = 0; which < 2; ++which) {
+      const int leaf = which ? ctrl->larger : ctrl->smaller;
+      if (leaf < 0) continue;
+      double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
+      for (int u = threadIdx.x; u < p.nf; u += blockDim.x) {
+        const double cg = __ldcg(&cands[which * p.nf_pad + u].gain);
+        const int rf = meta[u].real_index;
+        if (cg > bg || (cg == bg && rf < bf)) { bg = cg; bf = rf; bi = u; }
+      }
+      s_gain[threadIdx.x] = bg; s_feat[threadIdx.x] = bf; s_idx[threadIdx.x] = bi;
+      __syncthreads();
+      for (int s = 128; s; s >>= 1) {
+        if (threadIdx.x < s) {
+          double og = s_gain[threadIdx.x + s]; int of = s_feat[threadIdx.x + s];
+          if (og > s_gain[threadIdx.x] || (og == s_gain[threadIdx.x] && of < s_feat[threadIdx.x])) {
+            s_gain[threadIdx.x] = og; s_feat[threadIdx.x] = of; s_idx[threadIdx.x] = s_idx[threadIdx.x + s];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        LeafState& L = leaves[leaf];
+        LeafBest b;
+        b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
+        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
+        for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
+        if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
+          const SplitCand c = d_load_cand(&cands[which * p.nf_pad + s_idx[0]]);
+          const double sum_h = L.sum_h + 2 * kEpsD;
+          b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
+          b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
+          b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
+          b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
+          SplitParams pc = p;
+          pc.l2 += c.l2_extra;
+          b.left_out = d_calc_output(c.left_g, c.left_h, pc);
+          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, pc);
+          b.is_cat = c.is_cat;
+          for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = c.cat_bits[wd];
+        }
+        L.best = b;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
+}
 __global__ void __launch_bounds__(256)
-k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const FeatMeta* __restrict__ meta,
+k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* cands, SplitParams p) {
+  d_pick_block(ctrl, leaves, meta, cands, p);
+}
+
+__device__ __forceinline__ void
+d_scan_one(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const long long* __restrict__ H, long long* __restrict__ pool,
+           size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* cands, const SplitParams& p, int which, int leaf, int u, int lane, int warp);
+
+__global__ void __launch_bounds__(256)
+k_scan(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta,
        const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
-       SplitCand* __restrict__ cands, SplitParams p) {
-  if (!ctrl->go) return;
+       SplitCand* cands, SplitParams p) {
   const int which = blockIdx.y;
   const int leaf = which ? ctrl->larger : ctrl->smaller;
-  if (leaf < 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u = blockIdx.x * 8 + warp;
-  if (u >= p.nf) return;
+  if (ctrl->go && leaf >= 0 && u < p.nf) d_scan_one(ctrl, leaves, meta, H, pool, slot_elems, flags, cands, p, which, leaf, u, lane, warp);
+  // the block that finishes last picks the best candidate per leaf and the next leaf to split (was a separate kernel)
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctrl->scan_ticket, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    d_pick_block(ctrl, leaves, meta, cands, p);
+    if (threadIdx.x == 0) ctrl->scan_ticket = 0u;
+  }
+}
+
+__device__ __forceinline__ void
+d_scan_one(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const long long* __restrict__ H, long long* __restrict__ pool,
+           size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* cands, const SplitParams& p, int which, int leaf, int u, int lane, int warp) {
   SplitCand out;
   out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
   out.l2_extra = 0; out.is_cat = 0; out.pad = 0;
   for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
   uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
-  if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
+  if (!*flag) { if (lane == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); } return; }
 
   const LeafState& L = leaves[leaf];
   long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
@@ -761,13 +880,14 @@ k_scan(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, 
     qg[j] = s.x; qh[j] = s.y;
   }
   if (meta[u].is_categorical) {
-    extern __shared__ double scan_ws[];      // 8 warps x (3*256 doubles + 256 bytes)
-    d_scan_feature_cat(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out, scan_ws + warp * (768 + 32));
+    extern __shared__ double scan_ws[];      // 8 warps x (3*256 doubles + 2*256 bytes)
+    d_scan_feature_cat(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out, scan_ws + warp * (768 + 64));
   } else {
     d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
   }
   if (lane == 0) {
     cands[which * p.nf_pad + u] = out;
+    __threadfence();       // visible to the block that runs the pick step
   }
 }
 
@@ -867,93 +987,10 @@ k_scan_dp(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leave
 }
 
 // leaf choice by warp 0: ArgMax over leaves with SplitInfo::operator> (gain desc, real feature asc, first index), stop on gain <= 0
-__device__ __forceinline__ void d_choose_leaf(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitParams& p, int lane) {
-  double bg = kNegInf; int bf = 0x7fffffff, bl = 0x7fffffff;
-  const int nl = ctrl->num_leaves;
-  for (int l = lane; l < nl; l += 32) {
-    const double g = leaves[l].best.gain;
-    const int fi = leaves[l].best.feature;
-    const int f = fi < 0 ? 0x7fffffff : meta[fi].real_index;
-    if (g > bg || (g == bg && (f < bf || (f == bf && l < bl)))) { bg = g; bf = f; bl = l; }
-  }
-  for (int o = 16; o; o >>= 1) {
-    const double og = __shfl_xor_sync(0xffffffffu, bg, o);
-    const int of = __shfl_xor_sync(0xffffffffu, bf, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
-    if (og > bg || (og == bg && (of < bf || (of == bf && ol < bl)))) { bg = og; bf = of; bl = ol; }
-  }
-  if (lane != 0) return;
-  const int best_leaf = bl == 0x7fffffff ? 0 : bl;
-  const LeafBest& b = leaves[best_leaf].best;
-  if (!(b.gain > 0.0) || ctrl->num_leaves >= p.num_leaves) {
-    ctrl->finished = 1; ctrl->split_leaf = -1; ctrl->part_count = 0;
-  } else {
-    const LeafState& L = leaves[best_leaf];
-    const FeatMeta fm = meta[b.feature];
-    ctrl->split_leaf = best_leaf; ctrl->new_leaf = ctrl->num_leaves; ctrl->pending = 1;
-    ctrl->split_feature = b.feature; ctrl->split_threshold = b.threshold; ctrl->split_default_left = b.default_left;
-    ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
-    ctrl->split_is_cat = b.is_cat;
-    for (int wd = 0; wd < 8; ++wd) ctrl->split_cat_bits[wd] = b.cat_bits[wd];
-    ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
-    ctrl->part_left_total = 0;
-  }
-}
 
 // argmax over features per leaf (gain desc, real feature index asc), then over leaves
 // (SplitInfo::operator> : gain desc, feature asc; ArrayArgs::ArgMax keeps the first on full ties).
-__global__ void __launch_bounds__(256)
-k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* __restrict__ cands, SplitParams p) {
-  __shared__ double s_gain[256];
-  __shared__ int s_feat[256], s_idx[256];
-  if (ctrl->go) {
-    for (int which = 0; which < 2; ++which) {
-      const int leaf = which ? ctrl->larger : ctrl->smaller;
-      if (leaf < 0) continue;
-      double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
-      for (int u = threadIdx.x; u < p.nf; u += blockDim.x) {
-        const SplitCand& c = cands[which * p.nf_pad + u];
-        const int rf = meta[u].real_index;
-        if (c.gain > bg || (c.gain == bg && rf < bf)) { bg = c.gain; bf = rf; bi = u; }
-      }
-      s_gain[threadIdx.x] = bg; s_feat[threadIdx.x] = bf; s_idx[threadIdx.x] = bi;
-      __syncthreads();
-      for (int s = 128; s; s >>= 1) {
-        if (threadIdx.x < s) {
-          double og = s_gain[threadIdx.x + s]; int of = s_feat[threadIdx.x + s];
-          if (og > s_gain[threadIdx.x] || (og == s_gain[threadIdx.x] && of < s_feat[threadIdx.x])) {
-            s_gain[threadIdx.x] = og; s_feat[threadIdx.x] = of; s_idx[threadIdx.x] = s_idx[threadIdx.x + s];
-          }
-        }
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        LeafState& L = leaves[leaf];
-        LeafBest b;
-        b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
-        for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
-        if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
-          const SplitCand& c = cands[which * p.nf_pad + s_idx[0]];
-          const double sum_h = L.sum_h + 2 * kEpsD;
-          b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
-          b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
-          b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
-          b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
-          SplitParams pc = p;
-          pc.l2 += c.l2_extra;
-          b.left_out = d_calc_output(c.left_g, c.left_h, pc);
-          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, pc);
-          b.is_cat = c.is_cat;
-          for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = c.cat_bits[wd];
-        }
-        L.best = b;
-      }
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
-}
+
 
 // data-parallel pick: local argmax over the OWNED features, exchange of the per-rank winners through the peers'
 // mailboxes (C3, SyncUpGlobalBestSplit), global argmax with the same tie-breaks on every rank, then the usual leaf choice.
@@ -1081,7 +1118,7 @@ k_part_count(const TreeCtrl* __restrict__ ctrl, const uint8_t* __restrict__ bins
 }
 // pass 2: exclusive scan of the chunk counts (single block)
 __global__ void __launch_bounds__(1024)
-k_part_scan(TreeCtrl* ctrl, int* __restrict__ chunk_left) {
+k_part_scan(TreeCtrl* ctrl, const LeafState* __restrict__ leaves, int parallel, int* __restrict__ chunk_left) {
   const int n = ctrl->part_count;
   if (n <= 0) return;
   const int chunks = (n + kPartChunk - 1) / kPartChunk;
@@ -1109,17 +1146,25 @@ k_part_scan(TreeCtrl* ctrl, int* __restrict__ chunk_left) {
     if (threadIdx.x == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) ctrl->part_left_total = s_carry;
+  if (threadIdx.x == 0) {
+    ctrl->part_left_total = s_carry;
+    // the child K4 scans next is the one with fewer rows by the rule of k_round_ctl (global counts of the split in data-parallel
+    // mode, true counts otherwise; ties -> right): k_part_scatter puts that child's (g,h) words into partition order (qord)
+    const LeafBest& b = leaves[ctrl->split_leaf].best;
+    const int lc = parallel ? b.left_count : s_carry, rc = parallel ? b.right_count : n - s_carry;
+    ctrl->q_side = lc < rc ? 0 : 1;
+  }
 }
 // pass 3: stable scatter into the other index buffer (lefts first, then rights, original order kept)
 __global__ void __launch_bounds__(256)
 k_part_scatter(const TreeCtrl* __restrict__ ctrl, int* __restrict__ idx0, int* __restrict__ idx1, const unsigned* __restrict__ bits,
-               const int* __restrict__ chunk_left) {
+               const int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord) {
   const int n = ctrl->part_count;
   if (n <= 0) return;
   const int* src = ctrl->part_buf ? idx1 : idx0;
   int* dst = ctrl->part_identity ? idx0 : (ctrl->part_buf ? idx0 : idx1);
   const int begin = ctrl->part_begin, total_left = ctrl->part_left_total;
+  const bool q_left = ctrl->q_side == 0;
   const int chunks = (n + kPartChunk - 1) / kPartChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ int s_wl[64];
@@ -1154,6 +1199,7 @@ k_part_scatter(const TreeCtrl* __restrict__ ctrl, int* __restrict__ idx0, int* _
         if (left) pos = begin + left_base + lefts_before;
         else pos = begin + total_left + right_base + (w * 32 + lane - lefts_before);
         dst[pos] = r;
+        if (left == q_left) qord[pos] = qgh[r];      // replaces a separate gather pass before K4 (k_gather_q)
       }
     }
     __syncthreads();
