@@ -242,8 +242,25 @@ class LightGBMBase(Params):
         except Exception:
             return 1
 
+    def getCategoricalIndexes(self):             # LightGBMBase.getCategoricalIndexes (:168-198)
+        """categoricalSlotIndexes united with the positions of categoricalSlotNames in slotNames (first occurrences kept, like
+        Scala's union.distinct).  A Frame carries no ML attribute metadata, so names can only be resolved through slotNames."""
+        names = list(self.get("slotNames") or ())
+        by_name = [names.index(c) if c in names else -1 for c in (self.get("categoricalSlotNames") or ())] if names else []
+        out = []
+        for i in list(self.get("categoricalSlotIndexes") or ()) + by_name:
+            if i not in out:
+                out.append(int(i))
+        return out
+
+    def validateSlotNames(self):                 # LightGBMBase.validateSlotNames (:218-232)
+        bad = [n for n in (self.get("slotNames") or ()) if any(ch in n for ch in '",:[]{}')]
+        if bad:
+            raise ValueError("Invalid slot names detected in features column: " + ",".join(bad))
+
     def fit(self, data):                         # train (:43-66)
         df = Frame.of(data)
+        self.validateSlotNames()
         nb = self.get("numBatches")
         if nb and nb > 0:
             n = df.num_rows()
@@ -379,7 +396,7 @@ class LightGBMClassifier(LightGBMBase):
     def getTrainParams(self, numTasks, frame):
         labels = np.asarray(frame[self.get("labelCol")])
         num_class = int(labels.max()) + 1 if self.get("objective") != "binary" else 2      # getNumClasses
-        return TrainParams("classifier", self.params_dict(), numTasks, self.get("categoricalSlotIndexes"), num_class, self.get("slotNames"))
+        return TrainParams("classifier", self.params_dict(), numTasks, self.getCategoricalIndexes(), num_class, self.get("slotNames"))
 
     def getModel(self, train_params, booster):
         m = LightGBMClassificationModel(booster, featuresCol=self.get("featuresCol"), predictionCol=self.get("predictionCol"),
@@ -397,7 +414,7 @@ class LightGBMRegressor(LightGBMBase):
     _kind = "regressor"
 
     def getTrainParams(self, numTasks, frame):
-        return TrainParams("regressor", self.params_dict(), numTasks, self.get("categoricalSlotIndexes"), 1, self.get("slotNames"))
+        return TrainParams("regressor", self.params_dict(), numTasks, self.getCategoricalIndexes(), 1, self.get("slotNames"))
 
     def getModel(self, train_params, booster):
         return LightGBMRegressionModel(booster, featuresCol=self.get("featuresCol"), predictionCol=self.get("predictionCol"),
@@ -411,7 +428,7 @@ class LightGBMRanker(LightGBMBase):
     _kind = "ranker"
 
     def getTrainParams(self, numTasks, frame):
-        return TrainParams("ranker", self.params_dict(), numTasks, self.get("categoricalSlotIndexes"), 1, self.get("slotNames"))
+        return TrainParams("ranker", self.params_dict(), numTasks, self.getCategoricalIndexes(), 1, self.get("slotNames"))
 
     def _partitions(self, df, num_tasks):
         """repartition by grouping column: whole query groups stay on one rank (LightGBMRanker.scala:93-108)."""
@@ -429,8 +446,9 @@ class LightGBMRanker(LightGBMBase):
     def _preprocess(self, df):
         """sortWithinPartitions(groupCol) — here: one stable sort by group id before partitioning."""
         g = np.asarray(df[self.get("groupCol")])
-        if g.dtype.kind not in "iu":
-            raise ValueError("group column must be int or long")      # VerifyLightGBMRanker.scala:77-82
+        is_text = g.dtype.kind in "US" or (g.dtype.kind == "O" and all(isinstance(v, str) for v in g.tolist()))
+        if g.dtype.kind not in "iu" and not is_text:      # int, long and string query columns are accepted (VerifyLightGBMRanker.scala:60-82)
+            raise ValueError("group column must be of type int, long or string")
         order = np.argsort(g, kind="stable")
         return df.rows(order)
 

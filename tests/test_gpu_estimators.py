@@ -290,3 +290,93 @@ def test_dart_mode_parameters(built):
     # skip_drop = 1 never drops => identical to plain gbdt
     m0 = LightGBMClassifier(numIterations=40, numLeaves=15, numTasks=1).fit(df)
     np.testing.assert_allclose(m0.transform(df)["probability"], m1.transform(df)["probability"], rtol=0, atol=1e-12)
+
+
+def test_continued_training_with_initial_score(built):
+    """'continued training with initial score' (VerifyLightGBMClassifier.scala): the raw score of a first model is fed back as
+    initScoreCol; the second fit starts from it (no boost-from-average) and improves the training AUC."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier
+    df = _binary_frame(5)
+    m1 = LightGBMClassifier(numIterations=10, numLeaves=7, numTasks=1).fit(df)
+    out1 = m1.transform(df)
+    df2 = Frame({"features": df["features"], "label": df["label"], "init": out1["rawPrediction"][:, 1]})
+    m2 = LightGBMClassifier(numIterations=10, numLeaves=7, numTasks=1, initScoreCol="init").fit(df2)
+    raw2 = m2.transform(df2)["rawPrediction"][:, 1] + df2["init"]          # the model holds only the increment
+    assert _auc(df["label"], raw2) > _auc(df["label"], out1["rawPrediction"][:, 1])
+    # same as training 20 iterations in one go up to the init-score handling of the first tree
+    m20 = LightGBMClassifier(numIterations=20, numLeaves=7, numTasks=1).fit(df)
+    assert abs(_auc(df["label"], raw2) - _auc(df["label"], m20.transform(df)["rawPrediction"][:, 1])) < 0.01
+
+
+def test_max_delta_step_and_tweedie(built):
+    """'max delta step parameter' (classifier) and 'tweedie distribution' (regressor, VerifyLightGBMRegressor.scala:147-154)."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier, LightGBMRegressor
+    df = _binary_frame(6)
+    base = dict(numIterations=30, numLeaves=15, numTasks=1, learningRate=0.9)
+    p1 = LightGBMClassifier(**base).fit(df).transform(df)["probability"][:, 1]
+    m2 = LightGBMClassifier(maxDeltaStep=0.5, **base).fit(df)
+    p2 = m2.transform(df)["probability"][:, 1]
+    assert "[max_delta_step: 0.5]" in m2.getNativeModel()
+    assert np.abs(p1 - p2).max() > 1e-3
+    from mmlspark_b200.modeltext import parse_model
+    for t in parse_model(m2.getNativeModel())["trees"][1:]:          # |leaf output| <= learning_rate * max_delta_step (first tree also carries the bias)
+        assert np.abs(t["leaf_value"]).max() <= 0.9 * 0.5 + 1e-12
+    rng = np.random.default_rng(3)
+    X = rng.random((8000, 6))
+    y = rng.poisson(np.exp(1.5 * X[:, 0] - X[:, 1])) * rng.gamma(2.0, 1.0, 8000)
+    dfr = Frame({"features": X, "label": y})
+    mt = LightGBMRegressor(objective="tweedie", tweedieVariancePower=1.5, numIterations=30, numTasks=1).fit(dfr)
+    pred = mt.transform(dfr)["prediction"]
+    assert "objective=tweedie" in mt.getNativeModel() and "[tweedie_variance_power: 1.5]" in mt.getNativeModel()
+    assert (pred > 0).all() and np.corrcoef(pred, np.exp(1.5 * X[:, 0] - X[:, 1]))[0, 1] > 0.8
+
+
+def test_slot_names_and_categorical_slots(built):
+    """'slot names parameter' (renamed slot shows up in the model string) and 'categorical parameter for dense dataset' /
+    'Regressor categorical parameter': categoricalSlotNames / categoricalSlotIndexes reach the engine as categorical_feature."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier, LightGBMRegressor
+    from mmlspark_b200.modeltext import parse_model
+    rng = np.random.default_rng(9)
+    n = 12000
+    X = rng.standard_normal((n, 5))
+    X[:, 3] = rng.integers(0, 8, n)
+    effect = np.array([2.0, -1.0, 0.5, 3.0, -2.5, 0.0, 1.0, -0.5])[X[:, 3].astype(int)]       # non-monotone in the category id
+    y = (X[:, 0] + effect + 0.3 * rng.standard_normal(n) > 0.5).astype(np.float64)
+    df = Frame({"features": X, "label": y})
+    names = ["f0", "f1", "f2", "Age_years", "f4"]
+    mc = LightGBMClassifier(numIterations=20, numLeaves=15, numTasks=1, slotNames=names, categoricalSlotNames=["Age_years"]).fit(df)
+    s = mc.getNativeModel()
+    assert "Age_years" in s and "feature_names=f0 f1 f2 Age_years f4" in s
+    trees = parse_model(s)["trees"]
+    assert any(t.get("num_cat", 0) > 0 for t in trees)                       # bitset splits on the categorical slot
+    mnum = LightGBMClassifier(numIterations=20, numLeaves=15, numTasks=1, slotNames=names).fit(df)
+    assert all(t.get("num_cat", 0) == 0 for t in parse_model(mnum.getNativeModel())["trees"])
+    assert _auc(y, mc.transform(df)["probability"][:, 1]) >= _auc(y, mnum.transform(df)["probability"][:, 1]) - 1e-3
+    mr = LightGBMRegressor(numIterations=10, numTasks=1, categoricalSlotIndexes=[3]).fit(Frame({"features": X, "label": effect + X[:, 0]}))
+    assert any(t.get("num_cat", 0) > 0 for t in parse_model(mr.getNativeModel())["trees"])
+    with pytest.raises(ValueError, match="Invalid slot names"):
+        LightGBMRegressor(numIterations=2, numTasks=1, slotNames=["a", "b", "c[", "d", "e"]).fit(df)
+
+
+def test_ranker_query_column_types_and_shap(built):
+    """'Ranker with int, long and string query column', 'Throws error when group column is not long, int or string',
+    'Ranker feature shaps' (predict == sum of SHAP, VerifyLightGBMRanker.scala:110-125)."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMRanker
+    rng = np.random.default_rng(21)
+    nq, per = 300, 12
+    q = np.repeat(np.arange(nq), per)
+    X = rng.standard_normal((nq * per, 4))
+    rel = np.clip(np.round(X[:, 0] + 0.5 * rng.standard_normal(nq * per) + 1.5), 0, 4)
+    kw = dict(numIterations=8, numLeaves=7, numTasks=1, groupCol="query", evalAt=(1, 2, 3), minDataInLeaf=5)
+    preds = []
+    for qcol in (q.astype(np.int64), q.astype(np.int32), np.array(["str_%04d" % v for v in q])):
+        m = LightGBMRanker(featuresShapCol="shap", **kw).fit(Frame({"features": X, "label": rel, "query": qcol}))
+        out = m.transform(Frame({"features": X, "label": rel, "query": qcol}))
+        preds.append(out["prediction"])
+        np.testing.assert_allclose(out["shap"].sum(axis=1), out["prediction"], rtol=0, atol=1e-9)
+    # same groups whatever the key type (zero-padded strings sort like the integers); lambdarank sums fp32 lambdas with shared-memory
+    # float atomics, so repeated fits agree to ~1e-9, not bit for bit
+    np.testing.assert_allclose(preds[0], preds[1], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(preds[0], preds[2], rtol=0, atol=1e-6)
+    with pytest.raises(ValueError, match="int, long or string"):
+        LightGBMRanker(**kw).fit(Frame({"features": X, "label": rel, "query": q.astype(np.float64) + 0.5}))

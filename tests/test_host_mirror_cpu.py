@@ -217,3 +217,20 @@ def test_bench_multi_rank_plumbing_gloo(tmp_path):
     assert r0[3] == r1[3] == "11.0" and r0[5] == r1[5] == "1001"            # max over ranks, total rows
     assert (r0[7], r0[9]) == ("0", "501") and (r1[7], r1[9]) == ("501", "500")   # contiguous shards cover all rows
     assert r0[10] == r1[10] and int(r1[11]) == int(r0[11]) + 1              # same machine list, own listen port
+
+
+def test_categorical_slot_names_and_slot_name_validation():
+    """LightGBMBase.getCategoricalIndexes (:168-198): indexes united with the positions of the named slots;
+    validateSlotNames (:218-232, 'Verify LightGBM Regressor with bad column names fails early')."""
+    from mmlspark_b200.lightgbm import LightGBMClassifier, LightGBMRegressor
+    est = LightGBMClassifier(slotNames=["a", "b", "c", "d"], categoricalSlotNames=["c", "a"], categoricalSlotIndexes=[3, 0])
+    assert est.getCategoricalIndexes() == [3, 0, 2]
+    tp = est.getTrainParams(1, {"label": np.array([0.0, 1.0])})
+    assert "categorical_feature=3,0,2 " in tp.to_string()
+    assert LightGBMRegressor(categoricalSlotIndexes=[1]).getCategoricalIndexes() == [1]
+    assert LightGBMRegressor().getCategoricalIndexes() == []
+    bad = LightGBMRegressor(slotNames=["ok", "b[a]d", 'q"uote', "fine:not"])
+    with pytest.raises(ValueError) as ei:
+        bad.validateSlotNames()
+    assert str(ei.value) == 'Invalid slot names detected in features column: b[a]d,q"uote,fine:not'
+    LightGBMRegressor(slotNames=["x_1", "y-2", "z 3"]).validateSlotNames()
