@@ -181,8 +181,10 @@ int B200GBM_DatasetHistogram(DatasetHandle handle, const float* grad, const floa
 int B200GBM_BoosterSetProfile(BoosterHandle handle, int profile_hist);
 int B200GBM_BoosterGetTiming(BoosterHandle handle, double* out6, int reset);
 int B200GBM_BoosterGetScores(BoosterHandle handle, int data_idx, double* out);    /* raw scores, class-major */
-/* batched GPU prediction: row-major matrix on the host or the device, predict_type NORMAL / RAW_SCORE / LEAF_INDEX;
- * raw scores are bit-identical to LGBM_BoosterPredictForMatSingle; out_result is a host buffer; elapsed_ms (may be NULL) = CUDA-event time */
+/* batched GPU prediction: row-major matrix on the host or the device, predict_type NORMAL / RAW_SCORE / LEAF_INDEX /
+ * CONTRIB (TreeSHAP, [nrow][num_class][num_feature+1]); values equal LGBM_BoosterPredictForMatSingle row by row (raw scores and leaf
+ * indices bit for bit, contributions to 1e-12); out_result is a host buffer sized by LGBM_BoosterCalcNumPredict; elapsed_ms (may be
+ * NULL) = CUDA-event time.  Replaces the per-row UDF calls of LightGBMBooster.scala:390-423,528-545 for whole partitions. */
 int B200GBM_BoosterPredictForMatDevice(BoosterHandle handle, const void* data, int data_type, int64_t nrow, int32_t ncol, int predict_type,
                                        int start_iteration, int num_iteration, int64_t* out_len, double* out_result, double* elapsed_ms);
 /* out = {num_machines, rank, fused_peer_reduce (1 = K5 reduces over NVLink peer memory, 0 = NCCL allreduce), constant_hessian} */
