@@ -192,3 +192,38 @@ def test_sample_indices_matches_lcg(capi):
     from oracle import oracle as O
     for n, k in ((1000, 10), (5000, 4000), (300000, 200000)):
         np.testing.assert_array_equal(capi.sample_indices(n, k, 1), O.random_sample(1, n, k))
+
+
+def test_jni_shim_compiles_and_links(built, tmp_path):
+    """jvm/b200gbm_jni.c against a stand-in jni.h and the real libb200gbm.so: every native the reference's Scala
+    code reaches through com.microsoft.ml.lightgbm.lightgbmlib (grep of lightgbm/src/main/scala) is defined and
+    every C symbol it forwards to resolves (-Wl,--no-undefined)."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "lib_lightgbm_swig.so")
+    cmd = [cc, "-shared", "-fPIC", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "jvm", "stub"), "-I" + os.path.join(root, "include"),
+           os.path.join(root, "jvm", "b200gbm_jni.c"), "-L" + os.path.dirname(g.LIB), "-lb200gbm", "-Wl,--no-undefined", "-o", out]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    syms = subprocess.run(["nm", "-D", "--defined-only", out], check=True, capture_output=True, text=True).stdout
+    used_by_reference = [
+        "LGBM_GetLastError", "LGBM_NetworkInit", "LGBM_NetworkFree", "LGBM_DatasetCreateFromMat", "LGBM_DatasetCreateFromCSR", "LGBM_DatasetSetField",
+        "LGBM_DatasetGetField", "LGBM_DatasetGetNumData", "LGBM_DatasetGetNumFeature", "LGBM_DatasetSetFeatureNames", "LGBM_DatasetFree", "LGBM_BoosterCreate",
+        "LGBM_BoosterLoadModelFromString", "LGBM_BoosterMerge", "LGBM_BoosterAddValidData", "LGBM_BoosterFree", "LGBM_BoosterUpdateOneIter",
+        "LGBM_BoosterUpdateOneIterCustom", "LGBM_BoosterResetParameter", "LGBM_BoosterGetEvalNamesSWIG", "LGBM_BoosterGetEval", "LGBM_BoosterGetPredict",
+        "LGBM_BoosterGetNumClasses", "LGBM_BoosterNumModelPerIteration", "LGBM_BoosterNumberOfTotalModel", "LGBM_BoosterGetNumFeature",
+        "LGBM_BoosterFeatureImportance", "LGBM_BoosterSaveModelToStringSWIG", "LGBM_BoosterDumpModelSWIG", "LGBM_BoosterPredictForMatSingle",
+        "LGBM_BoosterPredictForCSRSingle", "StringArrayHandle_get_strings", "StringArrayHandle_free", "new_intp", "delete_intp", "intp_value",
+        "new_int32_tp", "int32_tp_value", "new_int64_tp", "int64_tp_assign", "int64_tp_value", "delete_int64_tp", "new_voidpp", "voidpp_handle", "voidpp_value",
+        "new_intArray", "delete_intArray", "intArray_getitem", "intArray_setitem", "new_floatArray", "delete_floatArray", "floatArray_setitem",
+        "new_doubleArray", "delete_doubleArray", "doubleArray_getitem", "doubleArray_setitem", "int_to_voidp_ptr", "float_to_voidp_ptr", "double_to_voidp_ptr",
+        "new_floatChunkedArray", "delete_floatChunkedArray", "floatChunkedArray_add", "floatChunkedArray_get_add_count", "floatChunkedArray_get_chunks_count",
+        "floatChunkedArray_get_last_chunk_add_count", "floatChunkedArray_getitem", "floatChunkedArray_coalesce_to", "floatChunkedArray_release",
+        "new_doubleChunkedArray", "doubleChunkedArray_add", "doubleChunkedArray_coalesce_to", "doubleChunkedArray_release", "new_int32ChunkedArray"]
+    for name in used_by_reference:
+        mangled = "Java_com_microsoft_ml_lightgbm_lightgbmlibJNI_" + name.replace("_", "_1")
+        assert mangled in syms, name
