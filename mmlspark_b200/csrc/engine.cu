@@ -609,17 +609,18 @@ void Dataset::SetFeatureNames(const char** names, int n) {
 
 // ---- host percentiles for the init score of regression_l1 / quantile / mape
 // [LightGBM regression_objective.hpp PercentileFun / WeightedPercentileFun, T = label_t]: the alpha percentile counted from the
-// top of the descending order, position (cnt-1)(1-alpha), linear interpolation; weighted: upper_bound on the running weight sum.
+// top of the descending order d[]: fp = (cnt-1)(1-alpha), interpolation between d[int(fp)] and d[int(fp)+1]; weighted: upper_bound on
+// the running weight sum.
 static float LabelPercentile(const float* y, int cnt, double alpha) {
   if (cnt <= 1) return y[0];
   const double float_pos = static_cast<double>(cnt - 1) * (1.0 - alpha);
-  const int pos = static_cast<int>(float_pos);
+  const int pos = static_cast<int>(float_pos) + 1;
   if (pos < 1) return *std::max_element(y, y + cnt);
   if (pos >= cnt) return *std::min_element(y, y + cnt);
   std::vector<float> v(y, y + cnt);
-  std::nth_element(v.begin(), v.begin() + pos, v.end(), std::greater<float>());
+  std::nth_element(v.begin(), v.begin() + pos, v.end(), std::greater<float>());      // v[pos] = (pos+1)-th largest, larger ones before it
   const float v2 = v[pos], v1 = *std::min_element(v.begin(), v.begin() + pos);
-  return static_cast<float>(v1 - (v1 - v2) * (float_pos - pos));
+  return static_cast<float>(v1 - (v1 - v2) * (float_pos - (pos - 1)));
 }
 static float LabelWeightedPercentile(const float* y, const float* w, int cnt, double alpha) {
   if (cnt <= 1) return y[0];

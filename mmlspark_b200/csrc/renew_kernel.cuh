@@ -53,7 +53,7 @@ __global__ void k_renew_offsets(const TreeCtrl* __restrict__ ctrl, const LeafSta
     seg_begin[ctrl->num_leaves] = acc;
   }
 }
-// PercentileFun(double, residual, cnt, alpha): position (cnt-1)(1-alpha) of the DESCENDING order, linear interpolation
+// PercentileFun(double, residual, cnt, alpha): fp = (cnt-1)(1-alpha) in the DESCENDING order d[], interpolate d[int(fp)] .. d[int(fp)+1]
 __global__ void k_renew_unweighted(const TreeCtrl* __restrict__ ctrl, const int* __restrict__ seg_begin, const unsigned* __restrict__ grouped_pos,
                                    const double* __restrict__ res_of_pos, double alpha, double* __restrict__ out, double* __restrict__ has_rows) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,10 +64,10 @@ __global__ void k_renew_unweighted(const TreeCtrl* __restrict__ ctrl, const int*
   auto desc = [&](int j) { return res_of_pos[grouped_pos[b + cnt - 1 - j]]; };
   if (cnt <= 1) { out[l] = desc(0); return; }
   const double float_pos = __dmul_rn(static_cast<double>(cnt - 1), 1.0 - alpha);
-  const int pos = static_cast<int>(float_pos);
+  const int pos = static_cast<int>(float_pos) + 1;
   if (pos < 1) { out[l] = desc(0); return; }
   if (pos >= cnt) { out[l] = desc(cnt - 1); return; }
-  const double bias = float_pos - pos;
+  const double bias = float_pos - (pos - 1);
   const double v1 = desc(pos - 1), v2 = desc(pos);
   out[l] = __dsub_rn(v1, __dmul_rn(__dsub_rn(v1, v2), bias));
 }

@@ -557,17 +557,18 @@ struct Objective {
 };
 
 // [LightGBM src/objective/regression_objective.hpp PercentileFun / WeightedPercentileFun]
-// percentile at `alpha` counted from the TOP of the descending order: position (cnt-1)(1-alpha), linear interpolation
+// percentile at `alpha` counted from the TOP of the descending order d[]: float position fp = (cnt-1)(1-alpha), linear interpolation
+// between d[int(fp)] and d[int(fp)+1] (LightGBM >= 3.0: pos = int(fp) + 1, bias = fp - (pos - 1)); median of {1,2,3,4} = 2.5
 template <typename T, typename Reader>
 static T PercentileOf(Reader data_reader, int cnt, double alpha) {
   if (cnt <= 1) return data_reader(0);
   std::vector<T> ref(cnt);
   for (int i = 0; i < cnt; ++i) ref[i] = data_reader(i);
   const double float_pos = static_cast<double>(cnt - 1) * (1.0 - alpha);
-  const int pos = static_cast<int>(float_pos);
+  const int pos = static_cast<int>(float_pos) + 1;
   if (pos < 1) return *std::max_element(ref.begin(), ref.end());
   if (pos >= cnt) return *std::min_element(ref.begin(), ref.end());
-  const double bias = float_pos - pos;
+  const double bias = float_pos - (pos - 1);
   std::sort(ref.begin(), ref.end(), std::greater<T>());
   const T v1 = ref[pos - 1], v2 = ref[pos];
   return static_cast<T>(v1 - (v1 - v2) * bias);

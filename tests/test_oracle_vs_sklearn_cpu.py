@@ -92,3 +92,28 @@ def test_poisson_matches_sklearn_hgb(O):
                                          early_stopping=False).fit(X, y.astype(np.float64))
     got = _oracle_pred(O, X, y, "objective=poisson poisson_max_delta_step=0", 15)
     np.testing.assert_allclose(got, h._raw_predict(X).ravel(), rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("loss,params,kw,atol", [
+    ("absolute_error", "objective=regression_l1", {}, 1e-6),              # the init score is a label_t (float32) percentile in LightGBM
+    ("quantile", "objective=quantile alpha=0.8", {"quantile": 0.8}, 1e-5),        # LightGBM keeps alpha as float32
+])
+def test_percentile_objectives_match_sklearn_hgb(O, loss, params, kw, atol):
+    """L1 / quantile: sign-type gradients, percentile init score AND the per-leaf renewal of the outputs (median / quantile of the
+    leaf's residuals) agree with sklearn's `_update_leaves_values`; pins PercentileFun's interpolation (fp = (cnt-1)(1-alpha) in the
+    descending order, between d[int(fp)] and d[int(fp)+1]) = numpy's linear percentile."""
+    _, X, y = _data(9)
+    h = sk.HistGradientBoostingRegressor(
+        loss=loss, learning_rate=0.1, max_iter=10, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255, early_stopping=False, **kw).fit(X, y.astype(np.float64))
+    got = _oracle_pred(O, X, y, params, 10)
+    np.testing.assert_allclose(got, h._raw_predict(X).ravel(), rtol=0, atol=atol)
+
+
+@pytest.mark.parametrize("y,alpha", [([1, 2, 3, 4, 5], 0.5), ([1, 2, 3, 4], 0.5), ([1, 2, 3, 4, 5], 0.8), ([10, 0], 0.25), ([7], 0.3), ([3, 1, 2], 0.999)])
+def test_percentile_init_score_known_answers(O, y, alpha):
+    yy = np.array(y, dtype=np.float32)
+    ds = O.OracleDataset(np.zeros((len(y), 1)), "max_bin=255").set_field("label", yy)
+    b = O.OracleBooster(ds, "objective=quantile alpha=%r verbosity=-1" % alpha)
+    b.train(1)                                           # no usable feature: a single constant tree = the init score
+    want = np.percentile(yy.astype(np.float64), 100 * float(np.float32(alpha)))
+    np.testing.assert_allclose(b.predict_raw(np.zeros((1, 1)))[0, 0], want, rtol=1e-6, atol=1e-6)

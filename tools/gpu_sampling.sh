@@ -1,4 +1,3 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 500 python -m pytest tests/test_gpu_estimators.py -m gpu -x -q 2>&1 | tail -6
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "percentile or golden" 2>&1 | tail -6
