@@ -1,3 +1,4 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "percentile or golden" 2>&1 | tail -6
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
