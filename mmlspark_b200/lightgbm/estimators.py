@@ -143,6 +143,12 @@ class _ModelBase(Params):
     def getNativeModel(self): return self.booster.modelStr
     def getFeatureImportances(self, importance_type="split"): return self.booster.getFeatureImportances(importance_type)
     def getFeatureShaps(self, vector): return self.booster.featuresShap(np.asarray(vector, dtype=np.float64)).tolist()
+    def getDenseFeatureShaps(self, features): return self.getFeatureShaps(features)          # LightGBMModelMethods.scala:33-36
+
+    def getSparseFeatureShaps(self, size, indices, values):                                  # LightGBMModelMethods.scala:38-46
+        """SHAP values of a sparse vector (size, indices, values) through LGBM_BoosterPredictForCSRSingle."""
+        return self.booster._handle().predict_for_csr_single(np.asarray(indices, dtype=np.int32), np.asarray(values, dtype=np.float64), int(size),
+                                                             capi.PREDICT_CONTRIB, self.booster.startIteration, self.booster.numIterations).tolist()
     def getBoosterBestIteration(self): return self.booster.bestIteration
     def getBoosterNumTotalIterations(self): return self.booster.numTotalIterations
     def getBoosterNumTotalModel(self): return self.booster.numTotalModel

@@ -234,3 +234,21 @@ def test_categorical_slot_names_and_slot_name_validation():
         bad.validateSlotNames()
     assert str(ei.value) == 'Invalid slot names detected in features column: b[a]d,q"uote,fine:not'
     LightGBMRegressor(slotNames=["x_1", "y-2", "z 3"]).validateSlotNames()
+
+
+def test_model_shap_accessors_dense_and_sparse_agree():
+    """getFeatureShaps / getDenseFeatureShaps / getSparseFeatureShaps (LightGBMModelMethods.scala:25-46) on a loaded golden model:
+    host predictor only, no GPU needed."""
+    import json
+    import os
+    from mmlspark_b200.lightgbm import LightGBMRegressionModel
+    here = os.path.dirname(os.path.abspath(__file__))
+    text = json.load(open(os.path.join(here, "golden", "oracle_golden.json")))["models"]["regression"]["model"]
+    m = LightGBMRegressionModel.loadNativeModelFromString(text)
+    x = np.array([0.3, 0.0, 0.0, -1.2, 2.0, 0.0, 0.7, 0.0, 0.0, 1.1])
+    dense = np.array(m.getFeatureShaps(x))
+    assert len(dense) == 11 and np.allclose(dense, m.getDenseFeatureShaps(x))
+    nz = np.nonzero(x)[0]
+    sparse = np.array(m.getSparseFeatureShaps(10, nz, x[nz]))
+    np.testing.assert_allclose(sparse, dense, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dense.sum(), m.predict(x), rtol=0, atol=1e-12)          # contributions + expected value = prediction
