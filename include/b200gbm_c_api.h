@@ -162,7 +162,7 @@ int B200GBM_HostFreePinned(void* ptr);
 int B200GBM_Memcpy(void* dst, const void* src, size_t bytes);   /* cudaMemcpyDefault + sync */
 /* LightGBM's LCG row sampler (the rows that define the bins) */
 int B200GBM_SampleIndices(int num_total_row, int sample_cnt, int seed, int* out, int* out_len);
-/* counter-based synthetic generators: kind 0 = regression, 1 = binary.
+/* counter-based synthetic generators: kind 0 = regression, 1 = binary, 2 = graded relevance 0..4 (ranking).
  * x(row, col) and label(row) are pure functions of (seed, row, col). */
 int B200GBM_SyntheticFill(void* dev_x_f32, void* dev_label_f32, int64_t row_start, int32_t nrow, int32_t ncol,
                           uint64_t seed, int kind);
@@ -170,6 +170,11 @@ int B200GBM_SyntheticRows(const int* rows, int32_t nrows, int32_t ncol, uint64_t
                           float* host_label_out);
 /* dataset introspection for the bit-exact bin parity tests */
 int B200GBM_DatasetGetBins(DatasetHandle handle, uint8_t* out_row_major);          /* [num_data][num_feature] */
+/* bins of the selected rows only, gathered on the device: out [nrows][num_feature] uint16 (trivial features 0).  Lets a test or
+ * bench.py check rows of a dataset far too large to download (the 100M x 512 benchmark matrix) against host-side binning. */
+int B200GBM_DatasetGetBinsRows(DatasetHandle handle, const int32_t* rows, int32_t nrows, uint16_t* out);
+/* {min, max} of the sampled values of a feature (the feature_infos entry of the model text) */
+int B200GBM_DatasetGetFeatureRange(DatasetHandle handle, int feature, double* out2);
 int B200GBM_DatasetGetFeatureInfo(DatasetHandle handle, int feature, int* out5);   /* num_bin, missing, default_bin, most_freq_bin, trivial */
 int B200GBM_DatasetGetUpperBounds(DatasetHandle handle, int feature, double* out, int* out_len);
 int B200GBM_DatasetGetIngestMs(DatasetHandle handle, double* out_ms);

@@ -232,6 +232,18 @@ class Dataset:
         check(load().B200GBM_DatasetGetBins(self.handle, _ptr(out)))
         return out
 
+    def get_bins_rows(self, rows):
+        """bins of the selected rows only (device gather): [len(rows)][num_feature] uint16"""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.zeros((len(rows), self.num_feature()), dtype=np.uint16)
+        check(load().B200GBM_DatasetGetBinsRows(self.handle, _ptr(rows), C.c_int32(len(rows)), _ptr(out)))
+        return out
+
+    def feature_range(self, f):
+        out = np.zeros(2, dtype=np.float64)
+        check(load().B200GBM_DatasetGetFeatureRange(self.handle, C.c_int(f), _ptr(out)))
+        return float(out[0]), float(out[1])
+
     def feature_info(self, f):
         info = np.zeros(5, dtype=np.int32)
         check(load().B200GBM_DatasetGetFeatureInfo(self.handle, C.c_int(f), _ptr(info)))
@@ -303,7 +315,9 @@ class Booster:
         return [bufs[i].value.decode() for i in range(out_n.value)]
 
     def get_eval(self, data_idx):
-        out = np.zeros(64, dtype=np.float64); n = C.c_int(0)
+        cnt = C.c_int(0)
+        check(load().LGBM_BoosterGetEvalCounts(self.handle, C.byref(cnt)))
+        out = np.zeros(max(cnt.value, 1), dtype=np.float64); n = C.c_int(0)
         check(load().LGBM_BoosterGetEval(self.handle, C.c_int(data_idx), C.byref(n), _ptr(out)))
         return out[:n.value].copy()
 

@@ -453,6 +453,7 @@ __device__ float syn_label(unsigned long long seed, long long row, int ncol, int
   if (ncol >= 2) s += 2.0f * (syn_u(seed, row, 0) - 0.5f) * (syn_u(seed, row, 1) - 0.5f) * 4.0f;
   const float noise = syn_u(seed ^ 0xABCDEF12345ULL, row, 1 << 20) + syn_u(seed ^ 0xABCDEF12345ULL, row, (1 << 20) + 1) - 1.0f;
   if (kind == 0) return s + 0.1f * noise * 2.449f;
+  if (kind == 2) return fminf(fmaxf(floorf(2.0f + 0.6f * s + 1.5f * noise), 0.0f), 4.0f);      // graded relevance 0..4 (lambdarank, BASELINE cfg4)
   const float p = 1.0f / (1.0f + __expf(-s));
   return syn_u(seed ^ 0x55AA55AA55ULL, row, 1 << 21) < p ? 1.0f : 0.0f;
 }
@@ -500,6 +501,18 @@ int B200GBM_DatasetGetBins(DatasetHandle handle, uint8_t* out_row_major) {
   API_BEGIN();
   EnsureDevice();
   DS(handle)->GetBinsRowMajor(out_row_major);
+  API_END();
+}
+int B200GBM_DatasetGetBinsRows(DatasetHandle handle, const int32_t* rows, int32_t nrows, uint16_t* out) {
+  API_BEGIN();
+  EnsureDevice();
+  DS(handle)->GetBinsOfRows(rows, nrows, out);
+  API_END();
+}
+int B200GBM_DatasetGetFeatureRange(DatasetHandle handle, int feature, double* out2) {
+  API_BEGIN();
+  const FeatureBins& fb = DS(handle)->mappers.at(feature);
+  out2[0] = fb.min_val; out2[1] = fb.max_val;
   API_END();
 }
 int B200GBM_DatasetGetFeatureInfo(DatasetHandle handle, int feature, int* out5) {

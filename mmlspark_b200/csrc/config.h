@@ -102,6 +102,9 @@ struct Config {
         o == "l2_root" || o == "root_mean_squared_error" || o == "rmse")
       return "regression";
     if (o == "softmax") return "multiclass";
+    if (o == "multiclass_ova" || o == "ova" || o == "ovr") return "multiclassova";
+    if (o == "xentropy") return "cross_entropy";
+    if (o == "xentlambda") return "cross_entropy_lambda";
     if (o == "rank" ) return "lambdarank";
     if (o == "l1" || o == "mean_absolute_error" || o == "mae") return "regression_l1";
     if (o == "mean_absolute_percentage_error") return "mape";
@@ -117,6 +120,7 @@ struct Config {
       return "multi_logloss";
     if (m == "ndcg" || m == "lambdarank" || m == "rank_xendcg" || m == "xendcg") return "ndcg";
     if (m == "map" || m == "mean_average_precision") return "map";
+    if (m == "xentropy" || m == "cross_entropy") return "cross_entropy";
     if (m == "mean_absolute_percentage_error") return "mape";
     return m;
   }

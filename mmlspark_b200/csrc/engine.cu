@@ -464,6 +464,27 @@ void Dataset::GetBinsRowMajor(uint8_t* out) const {
   }
 }
 
+__global__ void k_gather_bin_rows(const uint8_t* __restrict__ bins, size_t rows_stride, int nf, const FeatMeta* __restrict__ meta, const int* __restrict__ rows,
+                                  int nrows, int F, uint16_t* __restrict__ out) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < static_cast<long long>(nrows) * nf;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e / nf), u = static_cast<int>(e % nf);
+    out[static_cast<size_t>(i) * F + meta[u].real_index] = bins[(static_cast<size_t>(u >> 5) * rows_stride + rows[i]) * 32 + (u & 31)];
+  }
+}
+void Dataset::GetBinsOfRows(const int32_t* rows, int nrows, uint16_t* out) const {
+  if (nrows <= 0) return;
+  for (int i = 0; i < nrows; ++i) if (rows[i] < 0 || rows[i] >= num_data) Fatal("GetBinsOfRows: row index out of range");
+  DevBuf<int> dr; dr.Alloc(nrows);
+  DevBuf<uint16_t> dout; dout.Alloc(static_cast<size_t>(nrows) * num_total_features);
+  dr.Upload(rows, nrows, stream);
+  dout.Zero(stream);
+  if (nf > 0) k_gather_bin_rows<<<148 * 4, 256, 0, stream>>>(bins.p, rows_stride, nf, meta.p, dr.p, nrows, num_total_features, dout.p);
+  B200_CUDA(cudaGetLastError());
+  dout.Download(out, dout.n, stream);
+  B200_CUDA(cudaStreamSynchronize(stream));
+}
+
 void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const {
   EnsureDevice();
   B200_CUDA(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
@@ -533,21 +554,160 @@ Dataset* Dataset::CreateFromMat(const void* data, int data_type, int nrow, int n
   return d.release();
 }
 
-Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type,
-                                int64_t nindptr, int64_t nelem, int64_t num_col, const char* params, const Dataset* reference) {
-  (void)nelem;
-  if (num_col <= 0) Fatal("CreateFromCSR: num_col must be given");
-  const int64_t nrow = nindptr - 1;
-  std::vector<double> dense(static_cast<size_t>(nrow) * num_col, 0.0);
-  for (int64_t r = 0; r < nrow; ++r) {
-    int64_t a = indptr_type == 2 ? static_cast<const int32_t*>(indptr)[r] : static_cast<const int64_t*>(indptr)[r];
-    int64_t b = indptr_type == 2 ? static_cast<const int32_t*>(indptr)[r + 1] : static_cast<const int64_t*>(indptr)[r + 1];
-    for (int64_t k = a; k < b; ++k) {
-      double v = data_type == 0 ? static_cast<const float*>(data)[k] : static_cast<const double*>(data)[k];
-      if (indices[k] < num_col) dense[static_cast<size_t>(r) * num_col + indices[k]] = v;
+// ---- CSR ingestion without densifying (replaces LGBM_DatasetCreateFromCSR, reference call site DatasetAggregator.scala:438-459).
+// Bin finding walks the nonzeros of the sampled rows only; binning fills every row of a tile with the features' zero bins and then
+// scatters one thread per stored element.  Memory: O(nnz) + the uint8 bins, never nrow x num_col doubles.
+__global__ void k_fill_default_bins(const FeatMeta* __restrict__ meta, int nf, uint8_t* __restrict__ bins, size_t rows_stride, long long nrow, int num_tiles) {
+  const long long total = nrow * num_tiles * 32;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int lane = static_cast<int>(e & 31);
+    const long long rt = e >> 5;
+    const int tile = static_cast<int>(rt / nrow);
+    const long long r = rt - static_cast<long long>(tile) * nrow;
+    const int u = tile * 32 + lane;
+    bins[(static_cast<size_t>(tile) * rows_stride + r) * 32 + lane] = u < nf ? static_cast<uint8_t>(meta[u].default_bin) : 0;
+  }
+}
+template <typename TI, typename TV>
+__global__ void k_bin_csr(const TI* __restrict__ indptr, const int* __restrict__ indices, const TV* __restrict__ vals, long long nrow, const int* __restrict__ inner_of,
+                          const FeatMeta* __restrict__ meta, const double* __restrict__ ub, const uint8_t* __restrict__ catbin, uint8_t* __restrict__ bins,
+                          size_t rows_stride, long long elem_base) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5, nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp; r < nrow; r += nwarps) {
+    const long long a = static_cast<long long>(indptr[r]) - elem_base, b = static_cast<long long>(indptr[r + 1]) - elem_base;
+    for (long long k = a + lane; k < b; k += 32) {
+      const int u = inner_of[indices[k]];
+      if (u < 0) continue;
+      const FeatMeta m = meta[u];
+      double v = static_cast<double>(vals[k]);
+      const double* myub = ub + static_cast<size_t>(u) * 256;
+      unsigned bin = 0;
+      if (m.is_categorical) {
+        if (!isnan(v)) {
+          const int iv = static_cast<int>(v);
+          if (iv >= 0) {
+            int lo = 0, hi = m.num_sorted_cats;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (static_cast<int>(myub[mid]) < iv) lo = mid + 1; else hi = mid; }
+            if (lo < m.num_sorted_cats && static_cast<int>(myub[lo]) == iv) bin = catbin[static_cast<size_t>(u) * 256 + lo];
+          }
+        }
+      } else {
+        if (isnan(v)) { if (m.missing_type == 2) bin = m.num_bin - 1; else v = 0.0; }
+        if (!isnan(v)) {
+          int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
+          while (lo < hi) { int mid = (hi + lo - 1) / 2; if (v <= myub[mid]) hi = mid; else lo = mid + 1; }
+          bin = lo;
+        }
+      }
+      bins[(static_cast<size_t>(u >> 5) * rows_stride + r) * 32 + (u & 31)] = static_cast<uint8_t>(bin);
     }
   }
-  return CreateFromMat(dense.data(), 1, static_cast<int>(nrow), static_cast<int>(num_col), 1, params, reference);
+}
+
+Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type,
+                                int64_t nindptr, int64_t nelem, int64_t num_col, const char* params, const Dataset* reference) {
+  EnsureDevice();
+  if (num_col <= 0) Fatal("CreateFromCSR: num_col must be given");
+  if (num_col > std::numeric_limits<int>::max()) Fatal("CreateFromCSR: too many columns");
+  if (indptr_type != 2 && indptr_type != 3) Fatal("CreateFromCSR: indptr must be int32 or int64");
+  if (data_type != 0 && data_type != 1) Fatal("Unknown data type in CreateFromCSR (expect C_API_DTYPE_FLOAT32 or FLOAT64)");
+  const int64_t nrow = nindptr - 1;
+  if (nrow <= 0) Fatal("Dataset should have at least one row and one column");
+  if (nrow > std::numeric_limits<int>::max()) Fatal("CreateFromCSR: too many rows for one partition");
+  auto ip = [&](int64_t r) -> int64_t { return indptr_type == 2 ? static_cast<const int32_t*>(indptr)[r] : static_cast<const int64_t*>(indptr)[r]; };
+  auto val = [&](int64_t k) -> double { return data_type == 0 ? static_cast<double>(static_cast<const float*>(data)[k]) : static_cast<const double*>(data)[k]; };
+  if (ip(0) < 0 || ip(nrow) > nelem) Fatal("CreateFromCSR: indptr does not match the number of elements");
+  {
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t r = 0; r < nrow; ++r) {
+      if (ip(r) > ip(r + 1)) bad |= 1;
+      else for (int64_t k = ip(r); k < ip(r + 1); ++k) if (indices[k] < 0 || indices[k] >= num_col) bad |= 2;
+    }
+    if (bad & 1) Fatal("CreateFromCSR: indptr is not non-decreasing");
+    if (bad & 2) Fatal("CreateFromCSR: a column index is negative or >= num_col");
+  }
+  std::unique_ptr<Dataset> d(new Dataset());
+  d->device = CurrentDevice();
+  B200_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  d->num_data = static_cast<int>(nrow); d->num_total_features = static_cast<int>(num_col);
+  d->cfg.Parse(params);
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, d->stream));
+  const int F = d->num_total_features;
+  if (reference) {
+    if (reference->num_total_features != F) Fatal("Validation data has a different number of features than the reference dataset");
+    d->mappers = reference->mappers;
+    d->feature_names = reference->feature_names;
+  } else {
+    if (d->cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+    if (d->cfg.max_bin < 2) Fatal("max_bin should be >= 2");
+    if (d->cfg.zero_as_missing) Fatal("zero_as_missing=true is not supported by this build");
+    LcgRandom rnd(d->cfg.data_random_seed);
+    int sample_cnt = d->num_data < d->cfg.bin_construct_sample_cnt ? d->num_data : d->cfg.bin_construct_sample_cnt;
+    std::vector<int> rows = rnd.Sample(d->num_data, sample_cnt);
+    sample_cnt = static_cast<int>(rows.size());
+    std::vector<std::vector<double>> nz(F);
+    for (int r : rows)
+      for (int64_t k = ip(r); k < ip(r + 1); ++k) {
+        const double v = val(k);
+        if (std::fabs(v) > kZeroThr || std::isnan(v)) nz[indices[k]].push_back(v);
+      }
+    d->FindBinsFromColumns(&nz, sample_cnt);
+    d->feature_names.resize(F);
+    for (int f = 0; f < F; ++f) d->feature_names[f] = "Column_" + std::to_string(f);
+  }
+  d->UploadMeta();
+  d->rows_stride = static_cast<size_t>(nrow);
+  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  k_fill_default_bins<<<148 * 8, 256, 0, d->stream>>>(d->meta.p, d->nf, d->bins.p, d->rows_stride, nrow, d->num_tiles);
+  B200_CUDA(cudaGetLastError());
+  if (d->nf > 0) {
+    DevBuf<int> d_inner; d_inner.Alloc(F); d_inner.Upload(d->inner_of.data(), F, d->stream);
+    // row blocks of bounded element count: the stored elements are staged through one device buffer per block
+    const size_t isz = indptr_type == 2 ? 4 : 8, vsz = data_type == 0 ? 4 : 8;
+    const int64_t kBlockElems = 64LL << 20;
+    DevBuf<unsigned char> d_ip, d_ix, d_v;
+    int64_t r0 = 0;
+    while (r0 < nrow) {
+      int64_t r1 = r0 + 1;
+      while (r1 < nrow && ip(r1 + 1) - ip(r0) <= kBlockElems) ++r1;
+      const int64_t e0k = ip(r0), ne = ip(r1) - e0k, nr = r1 - r0;
+      if (d_ip.n < static_cast<size_t>(nr + 1) * isz) d_ip.Alloc(static_cast<size_t>(nr + 1) * isz);
+      if (ne > 0) {
+        if (d_ix.n < static_cast<size_t>(ne) * 4) d_ix.Alloc(static_cast<size_t>(ne) * 4);
+        if (d_v.n < static_cast<size_t>(ne) * vsz) d_v.Alloc(static_cast<size_t>(ne) * vsz);
+        B200_CUDA(cudaMemcpyAsync(d_ix.p, indices + e0k, static_cast<size_t>(ne) * 4, cudaMemcpyHostToDevice, d->stream));
+        B200_CUDA(cudaMemcpyAsync(d_v.p, static_cast<const unsigned char*>(data) + static_cast<size_t>(e0k) * vsz, static_cast<size_t>(ne) * vsz, cudaMemcpyHostToDevice, d->stream));
+      }
+      B200_CUDA(cudaMemcpyAsync(d_ip.p, static_cast<const unsigned char*>(indptr) + static_cast<size_t>(r0) * isz, static_cast<size_t>(nr + 1) * isz, cudaMemcpyHostToDevice, d->stream));
+      if (ne > 0) {
+        const int grid = static_cast<int>(std::min<int64_t>((nr + 7) / 8, 148 * 8));
+        uint8_t* base = d->bins.p + static_cast<size_t>(r0) * 32;       // row offset inside every tile
+#define B200_CSR_LAUNCH(TI, TV)                                                                                                              \
+        k_bin_csr<TI, TV><<<grid, 256, 0, d->stream>>>(reinterpret_cast<const TI*>(d_ip.p), reinterpret_cast<const int*>(d_ix.p),               \
+                                                      reinterpret_cast<const TV*>(d_v.p), nr, d_inner.p, d->meta.p, d->ub.p, d->catbin.p, base,  \
+                                                      d->rows_stride, e0k)
+        if (indptr_type == 2 && data_type == 0) B200_CSR_LAUNCH(int32_t, float);
+        else if (indptr_type == 2) B200_CSR_LAUNCH(int32_t, double);
+        else if (data_type == 0) B200_CSR_LAUNCH(int64_t, float);
+        else B200_CSR_LAUNCH(int64_t, double);
+#undef B200_CSR_LAUNCH
+        B200_CUDA(cudaGetLastError());
+      }
+      B200_CUDA(cudaStreamSynchronize(d->stream));      // the staging buffers are reused by the next block
+      r0 = r1;
+    }
+  }
+  B200_CUDA(cudaEventRecord(e1, d->stream));
+  B200_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  d->ingest_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return d.release();
 }
 
 void Dataset::SetField(const char* name, const void* data, int n, int type) {
@@ -667,7 +827,9 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   else if (cfg.objective == "mape") renew_kind_ = 3;
   if (renew_kind_ == 2 && !(cfg.alpha > 0.0 && cfg.alpha < 1.0)) Fatal("Check failed: alpha_ > 0 && alpha_ < 1");
   renew_alpha_ = renew_kind_ == 2 ? static_cast<double>(static_cast<float>(cfg.alpha)) : 0.5;     // quantile keeps alpha as score_t
-  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !regvar_kind_ && !renew_kind_)
+  is_ova_ = cfg.objective == "multiclassova";
+  if (cfg.objective != "regression" && cfg.objective != "binary" && cfg.objective != "multiclass" && cfg.objective != "lambdarank" && !is_ova_ &&
+      cfg.objective != "cross_entropy" && !regvar_kind_ && !renew_kind_)
     Fatal("Unknown/unsupported objective type name: " + cfg.objective);
   balanced_bagging_ = cfg.bagging_freq > 0 && (cfg.pos_bagging_fraction < 1.0 || cfg.neg_bagging_fraction < 1.0) && cfg.objective == "binary";
   bagging_ = cfg.bagging_freq > 0 && (cfg.bagging_fraction < 1.0 || balanced_bagging_);
@@ -683,9 +845,9 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   }
   if (cfg.num_leaves < 2) Fatal("num_leaves should be >= 2");
   if (train->label.empty()) Fatal("label should not be empty for training");
-  if (cfg.objective == "multiclass" && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
+  if ((cfg.objective == "multiclass" || is_ova_) && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
   if (cfg.objective == "lambdarank" && train->query_boundaries.empty()) Fatal("Ranking tasks require query information");
-  K = cfg.objective == "multiclass" ? cfg.num_class : 1;
+  K = (cfg.objective == "multiclass" || is_ova_) ? cfg.num_class : 1;
   parallel_ = Net().active && Net().world > 1;
   cfg.num_machines = parallel_ ? Net().world : 1;
   if (balanced_bagging_) {      // [LightGBM GBDT::ResetBaggingConfig] needs (globally) at least one positive row
@@ -700,7 +862,7 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
   }
   shrinkage_ = is_rf_ ? 1.0 : cfg.learning_rate;      // "no shrinkage rate for the RF"
   model.average_output = is_rf_;
-  model.num_class = cfg.objective == "multiclass" ? cfg.num_class : 1;
+  model.num_class = K;
   model.num_tree_per_iteration = K;
   model.label_index = 0;
   model.max_feature_idx = train->num_total_features - 1;
@@ -730,6 +892,7 @@ Booster::~Booster() {
 std::string Booster::ObjectiveString() const {
   if (cfg.objective == "binary") return "binary sigmoid:" + Config::Num(cfg.sigmoid);
   if (cfg.objective == "multiclass") return "multiclass num_class:" + std::to_string(cfg.num_class);
+  if (is_ova_) return "multiclassova num_class:" + std::to_string(cfg.num_class) + " sigmoid:" + Config::Num(cfg.sigmoid);
   return cfg.objective;
 }
 
@@ -849,6 +1012,39 @@ void Booster::InitTraining() {
     for (int k = 0; k < K; ++k) {
       class_init_probs_[k] /= class_init_probs_[K];
       class_need_train_[k] = !(std::fabs(class_init_probs_[k]) <= kEps || std::fabs(class_init_probs_[k]) >= 1.0 - kEps);
+    }
+  } else if (is_ova_) {       // [UPSTREAM MulticlassOVA::Init]: one BinaryLogloss::Init per class on (label == k)
+    std::vector<double> cnt(K, 0.0);
+    for (int i = 0; i < n; ++i) {
+      const int l = static_cast<int>(train->label[i]);
+      if (l < 0 || l >= K) Fatal("Label must be in [0, " + std::to_string(K) + "), but found " + std::to_string(l) + " in label");
+      cnt[l] += 1;
+    }
+    double total = n;
+    AllReduceHost(cnt.data(), K, ncclSum, stream_);
+    AllReduceHost(&total, 1, ncclSum, stream_);
+    std::vector<double> cw(2 * static_cast<size_t>(K), 1.0);
+    std::vector<uint8_t> need(K, 1);
+    for (int k = 0; k < K; ++k) {
+      const double pos = cnt[k], neg = total - cnt[k];
+      class_need_train_[k] = !(pos == 0 || neg == 0);
+      need[k] = class_need_train_[k] ? 1 : 0;
+      if (cfg.is_unbalance && pos > 0 && neg > 0) {
+        if (pos > neg) { cw[2 * k + 1] = 1.0; cw[2 * k] = pos / neg; }
+        else { cw[2 * k + 1] = neg / pos; cw[2 * k] = 1.0; }
+      }
+      cw[2 * k + 1] *= cfg.scale_pos_weight;
+    }
+    ova_w_.Alloc(cw.size()); ova_w_.Upload(cw.data(), cw.size(), stream_);
+    ova_need_.Alloc(K); ova_need_.Upload(need.data(), K, stream_);
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  } else if (cfg.objective == "cross_entropy") {      // [UPSTREAM CrossEntropy::Init]
+    for (int i = 0; i < n; ++i)
+      if (!(train->label[i] >= 0.0f && train->label[i] <= 1.0f)) Fatal("[cross_entropy]: does not tolerate label " + std::to_string(train->label[i]) + " outside [0, 1]");
+    if (!train->weight.empty()) {
+      double sw = 0;
+      for (int i = 0; i < n; ++i) { if (train->weight[i] < 0) Fatal("[cross_entropy]: at least one weight is negative"); sw += train->weight[i]; }
+      if (!(sw > 0)) Fatal("[cross_entropy]: sum of weights is zero");
     }
   } else if (cfg.objective == "lambdarank") {
     std::vector<double> lg = cfg.label_gain;
@@ -1153,6 +1349,19 @@ double Booster::ObjectiveInitScore(int k) {
     return std::log(pavg / (1.0 - pavg)) / cfg.sigmoid;
   }
   if (cfg.objective == "multiclass") return std::log(std::max(kEps, class_init_probs_[k]));
+  if (is_ova_ || cfg.objective == "cross_entropy") {      // BinaryLogloss::BoostFromScore on (label == k) / CrossEntropy::BoostFromScore on the label itself
+    double s[2] = {0, 0};
+    for (int i = 0; i < n; ++i) {
+      const double w = train->weight.empty() ? 1.0 : static_cast<double>(train->weight[i]);
+      const double y = is_ova_ ? (static_cast<int>(train->label[i]) == k ? 1.0 : 0.0) : static_cast<double>(train->label[i]);
+      s[0] += y * w; s[1] += w;
+    }
+    AllReduceHost(s, 2, ncclSum, stream_);
+    double pavg = s[0] / s[1];
+    pavg = std::min(pavg, 1.0 - kEps);
+    pavg = std::max(pavg, kEps);
+    return std::log(pavg / (1.0 - pavg)) / (is_ova_ ? cfg.sigmoid : 1.0);
+  }
   return 0.0;
 }
 
@@ -1188,6 +1397,10 @@ void Booster::ComputeGradientsAt(const double* score_p) {
       k_grad_binary<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, cfg.sigmoid, binary_w_[0], binary_w_[1]);
   } else if (cfg.objective == "multiclass") {
     k_grad_softmax<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, K, static_cast<double>(K) / (K - 1.0));
+  } else if (is_ova_) {
+    k_grad_ova<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n, K, cfg.sigmoid, ova_w_.p, ova_need_.p);
+  } else if (cfg.objective == "cross_entropy") {
+    k_grad_xent<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n);
   } else if (cfg.objective == "lambdarank") {
     const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
     size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4), 1024);
@@ -1543,11 +1756,13 @@ std::vector<std::string> Booster::EvalNames() const {
   return names;
 }
 int64_t Booster::NumPredict(int data_idx) const {
+  if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data (use the predict entry points)");
   if (data_idx == 0) return static_cast<int64_t>(K) * train->num_data;
   if (data_idx - 1 >= static_cast<int>(valids_.size())) Fatal("data_idx out of range");
   return static_cast<int64_t>(K) * valids_[data_idx - 1]->ds->num_data;
 }
 void Booster::GetPredict(int data_idx, int64_t* out_len, double* out) {
+  if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data (use the predict entry points)");
   EnsureDevice();
   if (is_dart_ && data_idx == 0 && !dart_dropped_this_iter_) DroppingTrees();      // DART::GetTrainingScore
   const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
@@ -1589,6 +1804,7 @@ static double AucOf(const std::vector<double>& score, const std::vector<float>& 
 }
 
 std::vector<double> Booster::GetEval(int data_idx) {
+  if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data to evaluate");
   EnsureDevice();
   const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
   const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
@@ -1654,6 +1870,15 @@ std::vector<double> Booster::GetEval(int data_idx) {
         sw += wi;
       }
       out.push_back(avg(loss, sw));
+    } else if (m == "cross_entropy") {       // [UPSTREAM xentropy_metric.hpp XentLoss], log argument floored at 1e-12
+      double loss = 0, sw = 0;
+      for (int i = 0; i < n; ++i) {
+        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
+        const double p = 1.0 / (1.0 + std::exp(-raw[i]));
+        const double a = lab * (p > 1e-12 ? std::log(p) : std::log(1e-12)), b = (1.0 - lab) * (1.0 - p > 1e-12 ? std::log(1.0 - p) : std::log(1e-12));
+        loss += -(a + b) * wi; sw += wi;
+      }
+      out.push_back(avg(loss, sw));
     } else if (m == "auc") {
       std::vector<double> s1(raw.begin(), raw.begin() + n);
       out.push_back(AucOf(s1, y, w));
@@ -1703,6 +1928,7 @@ std::vector<double> Booster::GetEval(int data_idx) {
 }
 
 void Booster::GetRawScores(int data_idx, double* out) {
+  if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data");
   EnsureDevice();
   const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
   const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;

@@ -81,6 +81,7 @@ class Dataset {
                                           int num_sample_row, int num_total_row, const char* params);
   void PushRows(const void* data, int data_type, int nrow, int ncol, int start_row);
   void GetBinsRowMajor(uint8_t* out) const;
+  void GetBinsOfRows(const int32_t* rows, int nrows, uint16_t* out) const;      // [nrows][num_total_features], gathered on the device
   // K4 on this dataset's bins for the given rows (kernel-level parity entry), fp64 [F][256][2]
   void Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const;
   void SetField(const char* name, const void* data, int n, int type);
@@ -188,6 +189,9 @@ class Booster {
   bool binary_need_train_ = true;
   std::vector<double> class_init_probs_;
   int regvar_kind_ = 0;                 // 1 huber, 2 fair, 3 poisson, 4 gamma, 5 tweedie
+  bool is_ova_ = false;                 // multiclassova: K independent binary objectives on (label == k)
+  DevBuf<double> ova_w_;                // [K][2] {w_neg, w_pos}
+  DevBuf<uint8_t> ova_need_;            // [K] class has both positives and negatives
   LcgRandom col_rand_{2};               // ColSampler (feature_fraction)
   std::vector<uint8_t> feature_used_host_;
   DevBuf<uint8_t> feature_used_;

@@ -204,6 +204,35 @@ __global__ void k_grad_binary(const double* __restrict__ score, const float* __r
     g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
   }
 }
+// [UPSTREAM MulticlassOVA::GetGradients]: class k is a BinaryLogloss on (label == k); cw = per-class {w_neg, w_pos}, need = per-class need_train
+__global__ void k_grad_ova(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight, float* __restrict__ g,
+                           float* __restrict__ h, int n, int K, double sigmoid, const double* __restrict__ cw, const uint8_t* __restrict__ need) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int li = static_cast<int>(label[i]);
+    for (int k = 0; k < K; ++k) {
+      if (!need[k]) continue;
+      const size_t id = static_cast<size_t>(n) * k + i;
+      const int is_pos = li == k;
+      const double lab = is_pos ? 1.0 : -1.0;
+      const double lw = cw[2 * k + is_pos];
+      const double response = -lab * sigmoid / (1.0 + exp(lab * sigmoid * score[id]));
+      const double abs_response = fabs(response);
+      double gg = response * lw, hh = abs_response * (sigmoid - abs_response) * lw;
+      if (weight) { gg *= weight[i]; hh *= weight[i]; }
+      g[id] = static_cast<float>(gg); h[id] = static_cast<float>(hh);
+    }
+  }
+}
+// [UPSTREAM CrossEntropy::GetGradients]: labels are probabilities
+__global__ void k_grad_xent(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight, float* __restrict__ g,
+                            float* __restrict__ h, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double z = 1.0 / (1.0 + exp(-score[i]));
+    double gg = z - label[i], hh = z * (1.0 - z);
+    if (weight) { gg *= weight[i]; hh *= weight[i]; }
+    g[i] = static_cast<float>(gg); h[i] = static_cast<float>(hh);
+  }
+}
 // [UPSTREAM MulticlassSoftmax::GetGradients]; score/g/h are class-major [K][n]
 __global__ void k_grad_softmax(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
                                float* __restrict__ g, float* __restrict__ h, int n, int K, double factor) {

@@ -373,6 +373,10 @@ struct HostModel {
     m->max_feature_idx = std::atoi(need("max_feature_idx").c_str());
     if (head.count("objective")) m->objective_str = head["objective"];
     {
+      OutputTransform t;      // an objective whose output transform is unknown must not silently predict raw scores as probabilities
+      if (!ObjectiveTransform(m->objective_str, &t)) throw std::runtime_error("Unknown objective type name: " + m->objective_str);
+    }
+    {
       std::istringstream is(need("feature_names"));
       std::string x;
       while (is >> x) m->feature_names.push_back(x);
@@ -411,24 +415,52 @@ struct HostModel {
     return m;
   }
 
-  // objective output transform (ConvertOutput)
+  // objective output transform ([UPSTREAM] ObjectiveFunction::ConvertOutput of the objective named in the model header).
+  // kind: 0 identity, 1 sigmoid(sig * x), 2 softmax, 3 exp, 4 per-class sigmoid (multiclassova), 5 log1p(exp(x)) (cross_entropy_lambda),
+  // 6 sign(x) * x^2 (regression with the `sqrt` flag)
+  struct OutputTransform { int kind = 0; double sigmoid = 1.0; };
+  static bool ObjectiveTransform(const std::string& o, OutputTransform* t) {
+    std::istringstream is(o);
+    std::string name, tok;
+    is >> name;
+    OutputTransform r;
+    bool sqrt_flag = false;
+    while (is >> tok) {
+      if (tok.rfind("sigmoid:", 0) == 0) r.sigmoid = std::atof(tok.c_str() + 8);
+      else if (tok == "sqrt") sqrt_flag = true;
+    }
+    if (name.empty() || name == "custom" || name == "none" || name == "null" || name == "na") r.kind = 0;
+    else if (name == "regression" || name == "regression_l1" || name == "huber" || name == "fair" || name == "quantile" || name == "mape" ||
+             name == "lambdarank" || name == "rank_xendcg") r.kind = (name == "regression" && sqrt_flag) ? 6 : 0;
+    else if (name == "binary") r.kind = 1;
+    else if (name == "multiclass") r.kind = 2;
+    else if (name == "poisson" || name == "gamma" || name == "tweedie") r.kind = 3;
+    else if (name == "multiclassova") r.kind = 4;
+    else if (name == "cross_entropy") { r.kind = 1; r.sigmoid = 1.0; }
+    else if (name == "cross_entropy_lambda") r.kind = 5;
+    else return false;
+    *t = r;
+    return true;
+  }
   void Convert(const double* raw, double* out) const {
-    const std::string& o = objective_str;
-    if (o.rfind("binary", 0) == 0) {
-      double sig = 1.0;
-      size_t p = o.find("sigmoid:");
-      if (p != std::string::npos) sig = std::atof(o.c_str() + p + 8);
-      out[0] = 1.0 / (1.0 + std::exp(-sig * raw[0]));
-    } else if (o.rfind("multiclass", 0) == 0 && o.rfind("multiclassova", 0) != 0) {
-      double mx = raw[0];
-      for (int k = 1; k < num_class; ++k) mx = std::max(mx, raw[k]);
-      double s = 0;
-      for (int k = 0; k < num_class; ++k) { out[k] = std::exp(raw[k] - mx); s += out[k]; }
-      for (int k = 0; k < num_class; ++k) out[k] /= s;
-    } else if (o.rfind("poisson", 0) == 0 || o.rfind("gamma", 0) == 0 || o.rfind("tweedie", 0) == 0) {
-      out[0] = std::exp(raw[0]);
-    } else {
-      for (int k = 0; k < num_tree_per_iteration; ++k) out[k] = raw[k];
+    OutputTransform t;
+    if (!ObjectiveTransform(objective_str, &t)) throw std::runtime_error("Unknown objective type name: " + objective_str);
+    const int K = num_tree_per_iteration;
+    switch (t.kind) {
+      case 1: out[0] = 1.0 / (1.0 + std::exp(-t.sigmoid * raw[0])); break;
+      case 2: {
+        double mx = raw[0];
+        for (int k = 1; k < num_class; ++k) mx = std::max(mx, raw[k]);
+        double s = 0;
+        for (int k = 0; k < num_class; ++k) { out[k] = std::exp(raw[k] - mx); s += out[k]; }
+        for (int k = 0; k < num_class; ++k) out[k] /= s;
+        break;
+      }
+      case 3: out[0] = std::exp(raw[0]); break;
+      case 4: for (int k = 0; k < K; ++k) out[k] = 1.0 / (1.0 + std::exp(-t.sigmoid * raw[k])); break;
+      case 5: out[0] = std::log1p(std::exp(raw[0])); break;
+      case 6: out[0] = (raw[0] >= 0 ? 1.0 : -1.0) * raw[0] * raw[0]; break;
+      default: for (int k = 0; k < K; ++k) out[k] = raw[k];
     }
   }
   void IterRange(int start_iteration, int num_iteration, int* t0, int* t1) const {

@@ -297,7 +297,9 @@ class LightGBMBase(Params):
         valid = None
         if vcol and vcol in df:
             mask = np.asarray(df[vcol]).astype(bool)
-            valid = df.rows(mask)
+            # the reference runs preprocessData (the ranker's sortWithinPartitions(groupCol)) on the validation frame too
+            # (LightGBMBase.scala:465-468): without it count_cardinality(valid[groupCol]) would fragment shuffled query groups
+            valid = self._preprocess(df.rows(mask))
             df = df.rows(~mask)
         df = self._preprocess(df)
         parts = self._partitions(df, num_tasks)

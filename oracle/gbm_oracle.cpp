@@ -123,6 +123,8 @@ struct Config {
         o == "l2_root" || o == "root_mean_squared_error" || o == "rmse")
       return "regression";
     if (o == "softmax") return "multiclass";
+    if (o == "multiclass_ova" || o == "ova" || o == "ovr") return "multiclassova";
+    if (o == "xentropy") return "cross_entropy";
     if (o == "l1" || o == "mean_absolute_error" || o == "mae") return "regression_l1";
     if (o == "mean_absolute_percentage_error") return "mape";
     return o;
@@ -803,6 +805,90 @@ struct MulticlassSoftmax : Objective {
   std::string ToString() const override { return "multiclass num_class:" + std::to_string(K); }
 };
 
+// [UPSTREAM multiclass_objective.hpp MulticlassOVA]: num_class independent BinaryLogloss objectives, class k's labels = (label == k)
+struct MulticlassOVA : Objective {
+  int K = 1;
+  std::vector<double> w_neg, w_pos;       // BinaryLogloss::label_weights_ per class
+  std::vector<char> class_need_train;
+  void Init(const Dataset* d, const Config& c) override {
+    Objective::Init(d, c);
+    K = c.num_class; num_tree_per_iter = K;
+    w_neg.assign(K, 1.0); w_pos.assign(K, 1.0); class_need_train.assign(K, 1);
+    for (int k = 0; k < K; ++k) {
+      long cnt_pos = 0, cnt_neg = 0;
+      for (int i = 0; i < d->n; ++i) { if (static_cast<int>(d->label[i]) == k) ++cnt_pos; else ++cnt_neg; }
+      class_need_train[k] = !(cnt_neg == 0 || cnt_pos == 0);
+      if (c.is_unbalance && cnt_pos > 0 && cnt_neg > 0) {
+        if (cnt_pos > cnt_neg) { w_pos[k] = 1.0; w_neg[k] = static_cast<double>(cnt_pos) / cnt_neg; }
+        else { w_pos[k] = static_cast<double>(cnt_neg) / cnt_pos; w_neg[k] = 1.0; }
+      }
+      w_pos[k] *= c.scale_pos_weight;
+    }
+  }
+  void GetGradients(const double* score, float* g, float* h) const override {
+    const int n = ds->n;
+    const double sig = cfg.sigmoid;
+    const float* y = ds->label.data();
+    const float* w = ds->weight.empty() ? nullptr : ds->weight.data();
+    for (int k = 0; k < K; ++k) {
+      if (!class_need_train[k]) continue;
+      const size_t off = static_cast<size_t>(n) * k;
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; ++i) {
+        const int is_pos = static_cast<int>(y[i]) == k;
+        const int label = is_pos ? 1 : -1;
+        const double lw = is_pos ? w_pos[k] : w_neg[k];
+        const double response = -label * sig / (1.0 + std::exp(label * sig * score[off + i]));
+        const double abs_response = std::fabs(response);
+        if (!w) { g[off + i] = static_cast<float>(response * lw); h[off + i] = static_cast<float>(abs_response * (sig - abs_response) * lw); }
+        else { g[off + i] = static_cast<float>(response * lw * w[i]); h[off + i] = static_cast<float>(abs_response * (sig - abs_response) * lw * w[i]); }
+      }
+    }
+  }
+  double BoostFromScore(int k, int, int) const override {
+    double suml = 0, sumw = 0;
+    const int n = ds->n;
+    if (!ds->weight.empty()) { for (int i = 0; i < n; ++i) { suml += (static_cast<int>(ds->label[i]) == k) * static_cast<double>(ds->weight[i]); sumw += ds->weight[i]; } }
+    else { sumw = n; for (int i = 0; i < n; ++i) suml += (static_cast<int>(ds->label[i]) == k); }
+    double pavg = suml / sumw;
+    pavg = std::min(pavg, 1.0 - kEpsilon);
+    pavg = std::max(pavg, kEpsilon);
+    return std::log(pavg / (1.0 - pavg)) / cfg.sigmoid;
+  }
+  bool GlobalInitScore() const override { return true; }
+  bool ClassNeedTrain(int k) const override { return class_need_train[k] != 0; }
+  std::string ToString() const override {
+    std::ostringstream s; s << "multiclassova num_class:" << K << " sigmoid:" << cfg.sigmoid; return s.str();
+  }
+};
+
+// [UPSTREAM xentropy_objective.hpp CrossEntropy]: labels are probabilities in [0, 1]
+struct CrossEntropy : Objective {
+  void GetGradients(const double* score, float* g, float* h) const override {
+    const int n = ds->n;
+    const float* y = ds->label.data();
+    const float* w = ds->weight.empty() ? nullptr : ds->weight.data();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      const double z = 1.0 / (1.0 + std::exp(-score[i]));
+      if (!w) { g[i] = static_cast<float>(z - y[i]); h[i] = static_cast<float>(z * (1.0 - z)); }
+      else { g[i] = static_cast<float>((z - y[i]) * w[i]); h[i] = static_cast<float>(z * (1.0 - z) * w[i]); }
+    }
+  }
+  double BoostFromScore(int, int, int) const override {
+    double suml = 0, sumw = 0;
+    const int n = ds->n;
+    if (!ds->weight.empty()) { for (int i = 0; i < n; ++i) { suml += static_cast<double>(ds->label[i]) * ds->weight[i]; sumw += ds->weight[i]; } }
+    else { sumw = n; for (int i = 0; i < n; ++i) suml += ds->label[i]; }
+    double pavg = suml / sumw;
+    pavg = std::min(pavg, 1.0 - kEpsilon);
+    pavg = std::max(pavg, kEpsilon);
+    return std::log(pavg / (1.0 - pavg));
+  }
+  bool GlobalInitScore() const override { return true; }
+  std::string ToString() const override { return "cross_entropy"; }
+};
+
 struct LambdarankNDCG : Objective {
   std::vector<double> label_gain, inverse_max_dcg, discount;
   std::vector<float> sigmoid_table;
@@ -919,6 +1005,8 @@ static Objective* CreateObjective(const Config& c) {
   if (c.objective == "mape") return new RegressionPercentile(2);
   if (c.objective == "binary") return new BinaryLogloss();
   if (c.objective == "multiclass") return new MulticlassSoftmax();
+  if (c.objective == "multiclassova") return new MulticlassOVA();
+  if (c.objective == "cross_entropy") return new CrossEntropy();
   if (c.objective == "lambdarank") return new LambdarankNDCG();
   return nullptr;
 }
@@ -1900,7 +1988,7 @@ struct Booster {
   std::string ModelToString() const {
     std::ostringstream ss;
     ss << "tree\n" << "version=v3\n";
-    ss << "num_class=" << (cfg.objective == "multiclass" ? cfg.num_class : 1) << '\n';
+    ss << "num_class=" << ((cfg.objective == "multiclass" || cfg.objective == "multiclassova") ? cfg.num_class : 1) << '\n';
     ss << "num_tree_per_iteration=" << K << '\n';
     ss << "label_index=0\n";
     ss << "max_feature_idx=" << ds->F - 1 << '\n';
@@ -1945,6 +2033,40 @@ void* orc_dataset_create(const double* X, int n, int F, const char* params, int 
   return d;
 }
 void orc_dataset_free(void* h) { delete static_cast<Dataset*>(h); }
+// Dataset from PRE-COMPUTED bins (row-major uint8 [n][F]) plus the mapper descriptions of every feature: for the mid-scale parity
+// tests, where the raw matrix only ever exists on the device (synthesised in chunks) and the bins are downloaded from the product
+// after they were checked row-sample-wise.  meta5[f] = {num_bin, missing_type, default_bin, most_freq_bin, is_trivial};
+// upper = concatenated bin upper bounds, upper_off[F+1]; minmax[2f..2f+1] = the feature's sampled value range (feature_infos).
+void* orc_dataset_create_from_bins(const uint8_t* bins_rm, int n, int F, const int* meta5, const double* upper, const int* upper_off,
+                                   const double* minmax, const char* params, int num_ranks, const int* rank_rows) {
+  Dataset* d = new Dataset();
+  d->n = n; d->F = F;
+  d->cfg.parse(params);
+  int one = n;
+  if (num_ranks <= 1 || !rank_rows) { num_ranks = 1; rank_rows = &one; }
+  d->rank_rows.assign(rank_rows, rank_rows + num_ranks);
+  d->mappers.assign(F, BinMapper());
+  for (int f = 0; f < F; ++f) {
+    BinMapper& m = d->mappers[f];
+    m.num_bin = meta5[f * 5]; m.missing_type = meta5[f * 5 + 1]; m.default_bin = meta5[f * 5 + 2]; m.most_freq_bin = meta5[f * 5 + 3];
+    m.is_trivial = meta5[f * 5 + 4] != 0;
+    m.upper.assign(upper + upper_off[f], upper + upper_off[f + 1]);
+    m.min_val = minmax[2 * f]; m.max_val = minmax[2 * f + 1];
+  }
+  d->inner_of.assign(F, -1);
+  for (int f = 0; f < F; ++f) if (!d->mappers[f].is_trivial) { d->inner_of[f] = static_cast<int>(d->used.size()); d->used.push_back(f); }
+  d->bins.resize(d->used.size() * static_cast<size_t>(n));
+#pragma omp parallel for schedule(static)
+  for (int u = 0; u < static_cast<int>(d->used.size()); ++u) {
+    const int f = d->used[u];
+    uint8_t* col = &d->bins[static_cast<size_t>(u) * n];
+    for (int i = 0; i < n; ++i) col[i] = bins_rm[static_cast<size_t>(i) * F + f];
+  }
+  d->feature_names.resize(F);
+  for (int f = 0; f < F; ++f) d->feature_names[f] = "Column_" + std::to_string(f);
+  return d;
+}
+
 int orc_dataset_num_used(void* h) { return static_cast<int>(static_cast<Dataset*>(h)->used.size()); }
 // bins out: row-major uint8 [n][F]; trivial features are written as 0
 void orc_dataset_bins(void* h, uint8_t* out) {

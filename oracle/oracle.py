@@ -48,6 +48,8 @@ def lib():
         L = C.CDLL(so)
         L.orc_dataset_create.restype = C.c_void_p
         L.orc_dataset_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_dataset_create_from_bins.restype = C.c_void_p
+        L.orc_dataset_create_from_bins.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
         L.orc_dataset_free.argtypes = [C.c_void_p]
         L.orc_dataset_num_used.argtypes = [C.c_void_p]
         L.orc_dataset_bins.argtypes = [C.c_void_p, C.c_void_p]
@@ -98,6 +100,29 @@ class OracleDataset:
         self.h = lib().orc_dataset_create(_p(X), self.n, self.F, params.encode(), nr, _p(rr))
         self._keep = []
 
+    @classmethod
+    def from_bins(cls, bins, infos, uppers, minmax, params="max_bin=255", rank_rows=None):
+        """Dataset over pre-computed bins (row-major uint8 [n][F]); infos[f] = feature_info dict, uppers[f] = bin upper bounds,
+        minmax[f] = (min, max) of the sampled values.  Mid-scale parity tests build it from the product's downloaded bins."""
+        self = cls.__new__(cls)
+        bins = np.ascontiguousarray(bins, dtype=np.uint8)
+        self.n, self.F = bins.shape
+        meta = np.zeros((self.F, 5), dtype=np.int32)
+        off = np.zeros(self.F + 1, dtype=np.int32)
+        for f, inf in enumerate(infos):
+            meta[f] = [inf["num_bin"], inf["missing_type"], inf["default_bin"], inf["most_freq_bin"], int(inf["is_trivial"])]
+            off[f + 1] = off[f] + len(uppers[f])
+        up = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.float64) for u in uppers]) if self.F else np.zeros(0))
+        mm = np.ascontiguousarray(np.asarray(minmax, dtype=np.float64).reshape(self.F, 2))
+        rr, nr = None, 1
+        if rank_rows is not None:
+            rr = np.ascontiguousarray(rank_rows, dtype=np.int32)
+            nr = len(rr)
+            assert int(rr.sum()) == self.n
+        self.h = lib().orc_dataset_create_from_bins(_p(bins), self.n, self.F, _p(meta), _p(up), _p(off), _p(mm), params.encode(), nr, _p(rr))
+        self._keep = []
+        return self
+
     def set_field(self, name, arr):
         dt = {"label": np.float32, "weight": np.float32, "init_score": np.float64, "group": np.int32}[name]
         a = np.ascontiguousarray(arr, dtype=dt)
@@ -135,7 +160,7 @@ class OracleBooster:
             raise ValueError("oracle: unsupported objective in: " + params)
         self.K = 1
         for tok in params.split():
-            if tok.startswith("num_class=") and ("objective=multiclass" in params or "objective=softmax" in params):
+            if tok.startswith("num_class=") and any(("objective=" + o) in params for o in ("multiclass", "softmax", "multiclassova", "ova", "ovr")):
                 self.K = int(tok.split("=")[1])
 
     def update(self):

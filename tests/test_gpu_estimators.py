@@ -199,6 +199,35 @@ def test_ranker(built):
     assert abs(sum(shap) - m.predict(df["features"][0])) < 1e-9               # VerifyLightGBMRanker.scala:124
 
 
+def test_ranker_validation_rows_are_grouped_before_counting(built):
+    """preprocessData (sortWithinPartitions(groupCol)) also runs on the validation frame (LightGBMBase.scala:465-468): with shuffled
+    validation rows the query sizes handed to the validation dataset must still be the true group sizes (a fragmented group list
+    still sums to num_data, so nothing else would notice), and validation NDCG must not collapse to the trivial single-document value."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMRanker
+    from mmlspark_b200.lightgbm import train_utils as tu
+    rng = np.random.default_rng(19)
+    sizes = rng.integers(8, 25, 400)
+    q = np.repeat(np.arange(400), sizes)
+    n = len(q)
+    X = rng.standard_normal((n, 6))
+    rel = np.clip(np.round(X[:, 0] + 0.5 * X[:, 1] + 0.4 * rng.standard_normal(n) + 1.5), 0, 4)
+    is_valid = np.isin(q, np.arange(0, 400, 4))            # every 4th query is validation data
+    seen = []
+
+    class Spy(LightGBMRanker):
+        def _make_dataset(self, part, params_str, reference=None):
+            if reference is not None:
+                seen.append(tu.count_cardinality(part[self.get("groupCol")].tolist()))
+            return super()._make_dataset(part, params_str, reference=reference)
+
+    order = rng.permutation(n)
+    df = Frame({"features": X[order], "label": rel[order], "query": q[order], "valid": is_valid[order]})
+    m = Spy(groupCol="query", validationIndicatorCol="valid", numIterations=10, numTasks=1, minDataInLeaf=5, evalAt=[1, 3]).fit(df)
+    assert len(seen) == 1
+    assert seen[0] == [int(s) for s in sizes[0::4]]         # whole groups, in group-id order
+    assert m.getBoosterNumTotalIterations() == 10
+
+
 def test_batches_and_empty_partition_do_not_hang(built):
     from mmlspark_b200.lightgbm import LightGBMClassifier
     df = _binary_frame(10, n=9000)

@@ -29,7 +29,7 @@ def _params(objective, machines, extra=""):
             "min_data_in_leaf=20 objective=%s num_threads=0 %s" % (machines, objective, extra))
 
 
-def run_ranks(X, y, rank_rows, params, iters, base_port, weight=None):
+def run_ranks(X, y, rank_rows, params, iters, base_port, weight=None, push_chunk=0):
     """Replays TrainUtils/LightGBMBase.trainLightGBM per rank-thread: NetworkInit -> DatasetCreateFromMat ->
     SetField -> BoosterCreate -> UpdateOneIter* -> (rank 0) SaveModelToString -> free -> NetworkFree."""
     from mmlspark_b200 import capi
@@ -44,7 +44,14 @@ def run_ranks(X, y, rank_rows, params, iters, base_port, weight=None):
             capi.set_device(r)
             capi.network_init(machines, base_port + r, 120, R)
             sl = slice(int(offs[r]), int(offs[r + 1]))
-            ds = capi.Dataset.from_mat(X[sl], DS_PARAMS)
+            if push_chunk:       # the benchmark's ingestion path: bins from the rank's own column sample, rows pushed in chunks (f32)
+                Xr = np.ascontiguousarray(X[sl], dtype=np.float32)
+                rows = capi.sample_indices(len(Xr), 200000, 1)
+                ds = capi.Dataset.from_sampled_columns(Xr[rows].astype(np.float64), len(Xr), DS_PARAMS)
+                for off in range(0, len(Xr), push_chunk):
+                    ds.push_rows(Xr[off:off + push_chunk], off)
+            else:
+                ds = capi.Dataset.from_mat(X[sl], DS_PARAMS)
             ds.set_field("label", y[sl])
             if weight is not None:
                 ds.set_field("weight", weight[sl])
@@ -151,3 +158,31 @@ def test_data_parallel_row_sampling(built, mode, monkeypatch):
     compare_models(parse_model(res[0]["model"]), parse_model(ob.model_string()))
     got_scores = np.concatenate([res[r]["scores"] for r in range(2)])
     np.testing.assert_allclose(got_scores, ob.scores(), rtol=1e-6, atol=1e-6)
+
+
+def test_data_parallel_push_rows_ingestion(built, monkeypatch):
+    """The path bench.py builds its shards with (LGBM_DatasetCreateFromSampledColumn + LGBM_DatasetPushRows, f32 chunks, ragged tail) on
+    2 ranks: distributed bin finding from every rank's own sample, bins and trees equal to the oracle's 2-rank emulation."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("B200GBM_FUSED_REDUCE", "0")
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    n, F = 120000, 40
+    X = rng.standard_normal((n, F)).astype(np.float32).astype(np.float64)      # f32-representable: both paths see the same values
+    X[:, 3] = np.where(rng.random(n) < 0.6, 0.0, X[:, 3])
+    s = 1.5 * X[:, 0] + np.sin(2 * X[:, 1]) + X[:, 2] * X[:, 3] + 0.3 * rng.standard_normal(n)
+    y = (s > 0).astype(np.float32)
+    rank_rows = [n // 2 + 1111, n - n // 2 - 1111]
+    params = _params("binary", 2, "is_unbalance=false")
+    res = run_ranks(X, y, rank_rows, params, 6, 24100, push_chunk=17000)
+    ods = O.OracleDataset(X, DS_PARAMS, rank_rows=rank_rows).set_field("label", y)
+    ob = O.OracleBooster(ods, params)
+    ob.train(6)
+    obins = ods.bins()
+    offs = np.concatenate([[0], np.cumsum(rank_rows)])
+    for r in range(2):
+        assert np.array_equal(res[r]["bins"], obins[offs[r]:offs[r + 1]]), "rank %d pushed bins differ" % r
+    assert res[1]["model"] == res[0]["model"]
+    compare_models(parse_model(res[0]["model"]), parse_model(ob.model_string()))

@@ -269,3 +269,58 @@ def test_multirank_emulation_counts_come_from_hessians(O):
     ts, tm = parse_model(s.model_string())["trees"], parse_model(m.model_string())["trees"]
     assert ts[0]["leaf_count"].sum() == n                    # serial: true counts
     assert abs(int(tm[0]["leaf_count"].sum()) - n) <= 7      # emulation: rounded hessian shares, close but need not be exact
+
+
+def test_dataset_from_precomputed_bins_trains_the_same_model(O):
+    """OracleDataset.from_bins (used by the mid-scale GPU parity test, where the raw matrix never exists on the host) is the same
+    dataset as the one built from the raw matrix."""
+    rng = np.random.default_rng(41)
+    n, F = 6000, 9
+    X = rng.standard_normal((n, F))
+    X[:, 2] = np.where(rng.random(n) < 0.3, np.nan, X[:, 2])
+    X[:, 4] = 1.0
+    y = (X[:, 0] + np.nan_to_num(X[:, 2]) * X[:, 1] > 0).astype(np.float32)
+    params = "objective=binary num_leaves=15 min_data_in_leaf=20 learning_rate=0.1 verbosity=-1"
+    a = O.OracleDataset(X, "max_bin=63").set_field("label", y)
+    infos = [a.feature_info(f) for f in range(F)]
+    uppers = [a.upper_bounds(f) for f in range(F)]
+    minmax = [(float(np.nanmin(X[:, f])), float(np.nanmax(X[:, f]))) for f in range(F)]
+    b = O.OracleDataset.from_bins(a.bins(), infos, uppers, minmax, "max_bin=63").set_field("label", y)
+    ba, bb = O.OracleBooster(a, params), O.OracleBooster(b, params)
+    ba.train(5); bb.train(5)
+    ta = ba.model_string().split("feature_infos=")[1].split("\n", 1)[1]
+    tb = bb.model_string().split("feature_infos=")[1].split("\n", 1)[1]
+    assert ta == tb
+    assert np.array_equal(ba.scores(), bb.scores())
+
+
+def test_multiclassova_is_k_independent_binary_problems(O):
+    """[UPSTREAM MulticlassOVA]: class k's trees equal the trees of a binary booster trained on (label == k)."""
+    rng = np.random.default_rng(43)
+    n, F, K = 5000, 6, 3
+    X = rng.standard_normal((n, F))
+    y = np.argmax(X[:, :K] + 0.3 * rng.standard_normal((n, K)), axis=1).astype(np.float32)
+    base = "num_leaves=7 min_data_in_leaf=20 learning_rate=0.2 verbosity=-1 sigmoid=1.3 "
+    ds = O.OracleDataset(X, "max_bin=63").set_field("label", y)
+    ova = O.OracleBooster(ds, base + "objective=multiclassova num_class=3")
+    ova.train(4)
+    sc = ova.scores().reshape(K, n)
+    assert "objective=multiclassova num_class:3 sigmoid:1.3" in ova.model_string()
+    for k in range(K):
+        dk = O.OracleDataset(X, "max_bin=63").set_field("label", (y == k).astype(np.float32))
+        bk = O.OracleBooster(dk, base + "objective=binary")
+        bk.train(4)
+        np.testing.assert_allclose(sc[k], bk.scores(), rtol=1e-12, atol=1e-12)
+
+
+def test_cross_entropy_on_hard_labels_equals_binary_logloss(O):
+    """with labels in {0, 1} and sigmoid = 1 the cross-entropy gradients are the binary log-loss gradients"""
+    rng = np.random.default_rng(47)
+    n, F = 4000, 5
+    X = rng.standard_normal((n, F))
+    y = (X[:, 0] - X[:, 1] > 0).astype(np.float32)
+    base = "num_leaves=7 min_data_in_leaf=20 learning_rate=0.2 verbosity=-1 "
+    a = O.OracleBooster(O.OracleDataset(X, "max_bin=63").set_field("label", y), base + "objective=cross_entropy")
+    b = O.OracleBooster(O.OracleDataset(X, "max_bin=63").set_field("label", y), base + "objective=binary")
+    a.train(5); b.train(5)
+    np.testing.assert_allclose(a.scores(), b.scores(), rtol=1e-9, atol=1e-9)
