@@ -2,6 +2,7 @@
 // device-resident leaf-wise tree learner.  See engine.h / kernels.cuh / hist_kernel.cuh.
 #include "engine.h"
 #include "renew_kernel.cuh"
+#include "metric_kernels.cuh"
 
 #include <arpa/inet.h>
 #include <netdb.h>
@@ -844,6 +845,7 @@ Booster::Booster(const Dataset* tr, const char* params) : train(tr) {
     if (!(bagging_ || ff)) Fatal("Check failed: (config->bagging_freq > 0 && config->bagging_fraction < 1.0f && config->bagging_fraction > 0.0f) || (config->feature_fraction < 1.0f && config->feature_fraction > 0.0f)");
   }
   if (cfg.num_leaves < 2) Fatal("num_leaves should be >= 2");
+  ValidateMetrics();      // an unknown metric must fail LGBM_BoosterCreate, not the first LGBM_BoosterGetEval inside the training loop
   if (train->label.empty()) Fatal("label should not be empty for training");
   if ((cfg.objective == "multiclass" || is_ova_) && cfg.num_class < 2) Fatal("Number of classes should be specified and greater than 1 for multiclass training");
   if (cfg.objective == "lambdarank" && train->query_boundaries.empty()) Fatal("Ranking tasks require query information");
@@ -927,7 +929,15 @@ void Booster::InitTraining() {
   grad_.Alloc(static_cast<size_t>(K) * n); hess_.Alloc(static_cast<size_t>(K) * n);
   qgh_.Alloc(n); qord_.Alloc(n); idx0_.Alloc(n); idx1_.Alloc(n);
   slot_elems_ = static_cast<size_t>(train->nf_pad) * 512;
-  H_.Alloc(slot_elems_); pool_.Alloc(slot_elems_ * L);
+  H_.Alloc(slot_elems_); H_.Zero(stream_); pool_.Alloc(slot_elems_ * L);
+  {
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_partition, 256, 0));
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_);
+    if (!coop || per_sm < 1) Fatal("this device cannot launch the cooperative partition kernel");
+    part_max_blocks_ = per_sm * num_sms_;
+  }
   flags_.Alloc(static_cast<size_t>(L) * train->nf_pad);
   cands_.Alloc(2 * static_cast<size_t>(train->nf_pad));
   leaves_.Alloc(L); ctrl_.Alloc(1); ctrl_.Zero(stream_);
@@ -1065,7 +1075,7 @@ void Booster::InitTraining() {
       double m = 0;
       for (int j = 0; j < k; ++j) {
         while (top > 0 && label_cnt[top] <= 0) --top;
-        m += lg[top] / std::log2(2.0 + j);
+        m += (1.0 / std::log2(2.0 + j)) * lg[top];      // discount_[j] * label_gain_[top] as [UPSTREAM DCGCalculator::CalMaxDCGAtK]
         --label_cnt[top];
       }
       imd[q] = m > 0.0 ? 1.0 / m : m;
@@ -1078,8 +1088,11 @@ void Booster::InitTraining() {
     std::vector<float> tab(bins_n);
     for (size_t i = 0; i < bins_n; ++i) tab[i] = static_cast<float>(1.0 / (1.0 + std::exp((i / lr_idx_factor_ + lr_min_in_) * cfg.sigmoid)));
     lr_sig_table_.Alloc(bins_n); lr_sig_table_.Upload(tab.data(), bins_n, stream_);
+    std::vector<double> disc(static_cast<size_t>(std::max(lr_max_q_, 1)) + 1);       // [UPSTREAM DCGCalculator::Init] discount table, host log2
+    for (size_t i = 0; i < disc.size(); ++i) disc[i] = 1.0 / std::log2(2.0 + i);
+    lr_discount_.Alloc(disc.size()); lr_discount_.Upload(disc.data(), disc.size(), stream_);
     B200_CUDA(cudaStreamSynchronize(stream_));
-    size_t smem = static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4);
+    size_t smem = static_cast<size_t>(lr_max_q_) * (8 + 8 + 4 + 4);
     if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
     B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
   }
@@ -1403,9 +1416,9 @@ void Booster::ComputeGradientsAt(const double* score_p) {
     k_grad_xent<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n);
   } else if (cfg.objective == "lambdarank") {
     const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
-    size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 4 + 4 + 4 + 4), 1024);
-    k_grad_lambdarank<<<std::min(nq, num_sms_ * 8), 256, smem, stream_>>>(
-        score_p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
+    size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 8 + 4 + 4), 1024);
+    k_grad_lambdarank<<<std::min(nq, num_sms_ * 16), 128, smem, stream_>>>(
+        score_p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_discount_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
         lr_max_in_, lr_idx_factor_, cfg.sigmoid, cfg.lambdarank_truncation_level, cfg.lambdarank_norm ? 1 : 0, grad_.p, hess_.p, lr_max_q_);
   }
   B200_CUDA(cudaGetLastError());
@@ -1447,6 +1460,28 @@ void Booster::RenewTreeOutput(int k, double rf_pred) {
   timing.launches += weighted ? 7 : 6;
 }
 
+// k_partition is launched cooperatively: its software grid barriers need every block resident
+void Booster::LaunchPartition(int grid, int last) {
+  const Dataset& d = *train;
+  TreeCtrl* ctrl = ctrl_.p;
+  LeafState* leaves = leaves_.p;
+  TreeDev tree = tree_dev_;
+  uint8_t* flags = flags_.p;
+  const FeatMeta* meta = d.meta.p;
+  SplitParams sp = sp_;
+  const uint8_t* bins = d.bins.p;
+  size_t rows_stride = d.rows_stride;
+  int* i0 = idx0_.p; int* i1 = idx1_.p;
+  unsigned* bits = part_bits_.p;
+  int* chunks = part_chunks_.p;
+  const int4* qgh = qgh_.p;
+  int4* qord = qord_.p;
+  long long* H = H_.p;
+  size_t h_elems = slot_elems_;
+  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems};
+  B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_partition), dim3(grid), dim3(256), args, 0, stream_));
+}
+
 // One tree: the whole leaf-wise growth is enqueued without a host sync; leaf choice, smaller/larger
 // selection, partition sizes all live in TreeCtrl / LeafState on the device.
 void Booster::TrainOneTree(int k, HostTree* out) {
@@ -1469,23 +1504,23 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     B200_CUDA(cudaMemcpyAsync(idx0_.p, bag_idx_.p, static_cast<size_t>(bag_count_) * sizeof(int), cudaMemcpyDeviceToDevice, s));
   k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, use_bag_ ? bag_count_ : n, feature_used_.p, use_bag_ ? 1 : 0);
   timing.launches += 4;
-  const int pgrid = std::max(1, std::min(n / kPartChunk + 1, num_sms_ * 8));
+  const int pgrid = std::max(1, std::min(n / kPartChunk + 1, part_max_blocks_));
   const dim3 sgrid((d.nf + 7) / 8, 2);
   std::vector<cudaEvent_t> evs;
   // B200GBM_SPLIT_TIMING=1 (debug): an event after every operation of a split; per-operation averages go to stderr when the booster is freed
   static const bool split_timing = getenv("B200GBM_SPLIT_TIMING") != nullptr;
   std::vector<cudaEvent_t> sev;
   auto mark = [&]() { if (split_timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); sev.push_back(e); } };
+  // round 0's controller is its own launch; every later round's runs in the tail of the previous round's partition kernel
+  k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 0);
+  timing.launches += 1;
   for (int split = 0; split < L - 1; ++split) {
     mark();
-    k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 0);
-    mark();
-    B200_CUDA(cudaMemsetAsync(H_.p, 0, slot_elems_ * sizeof(long long), s));
-    mark();
     if (profile_hist) { cudaEvent_t a, b; B200_CUDA(cudaEventCreate(&a)); B200_CUDA(cudaEventCreate(&b)); evs.push_back(a); evs.push_back(b); B200_CUDA(cudaEventRecord(a, s)); }
-    // leaf order of the (g,h) words: written by the previous split's k_part_scatter; only a bagged root needs its own pass
+    // leaf order of the (g,h) words: written by the previous split's partition kernel; only a bagged root needs its own pass
     if (split == 0 && use_bag_) k_gather_q<<<egrid, 256, 0, s>>>(&ctrl->hist_work, idx0_.p, idx1_.p, qgh_.p, qord_.p);
     mark();
+    // the scratch histogram H is zero here: zeroed at set-up and by every partition kernel after the scan consumed it
     if (const_hessian_)
       k4_hist_build_ws<3><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
@@ -1500,22 +1535,18 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       const dim3 dgrid(std::max(1, (peers_.feat1 - peers_.feat0 + 7) / 8), 2);
       k_scan_dp<<<dgrid, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, peers_, pool_.p, slot_elems_, flags_.p, cands_.p, sp_, epoch_);
       k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
+      mark();
     } else {
-      if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2 (fallback)
+      if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
       mark();
       // scan + (last block) pick; the dynamic scratch is only touched by categorical features
       k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
-      mark();
     }
-    k_part_count<<<pgrid, 256, 0, s>>>(ctrl, d.bins.p, d.rows_stride, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p);
     mark();
-    k_part_scan<<<1, 1024, 0, s>>>(ctrl, leaves_.p, parallel_ ? 1 : 0, part_chunks_.p);
+    LaunchPartition(pgrid, split == L - 2 ? 1 : 0);
     mark();
-    k_part_scatter<<<pgrid, 256, 0, s>>>(ctrl, idx0_.p, idx1_.p, part_bits_.p, part_chunks_.p, qgh_.p, qord_.p);
-    mark();
-    timing.launches += fused_ ? 7 : 6; timing.hist_launches += 1;
+    timing.launches += fused_ ? 4 : 3; timing.hist_launches += 1;
   }
-  k_round_ctl<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, d.meta.p, sp_, 1);
   if (renew_kind_) RenewTreeOutput(k, is_rf_ ? rf_init_scores_[k] : 0.0);
   // rf keeps scores as the running average of (tree + init score) over the iterations [LightGBM rf.hpp MultiplyScore / UpdateScore]
   const double bias = is_rf_ ? rf_init_scores_[k] : 0.0, pre = is_rf_ ? static_cast<double>(iter + num_init_iteration) : 1.0;
@@ -1533,8 +1564,8 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   B200_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl, sizeof(TreeCtrl), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
   if (split_timing && !fused_ && !sev.empty()) {
-    static const char* kOps[] = {"round_ctl", "memset_H", "gather_q(bagged root)", "K4", "allreduce", "scan+pick", "part_count", "part_scan", "part_scatter"};
-    const int per = 10;      // marks per split
+    static const char* kOps[] = {"gather_q(bagged root)", "K4", "allreduce", "scan+pick", "partition+zeroH+ctl"};
+    const int per = 6;       // marks per split
     for (size_t b0 = 0; b0 + per <= sev.size(); b0 += per)
       for (int o = 0; o < per - 1; ++o) { float ms = 0; cudaEventElapsedTime(&ms, sev[b0 + o], sev[b0 + o + 1]); split_op_ms_[kOps[o]] += ms; }
     split_op_trees_ += 1;
@@ -1780,146 +1811,127 @@ void Booster::GetPredict(int data_idx, int64_t* out_len, double* out) {
   *out_len = static_cast<int64_t>(K) * n;
 }
 
-static double AucOf(const std::vector<double>& score, const std::vector<float>& label, const std::vector<float>& weight) {
-  const size_t n = score.size();
-  std::vector<int> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return score[a] > score[b]; });
-  double sum_pos = 0, accum = 0, cur_pos = 0, cur_neg = 0, threshold = score[order[0]], sum_neg_total = 0;
-  for (size_t i = 0; i < n; ++i) {
-    const int j = order[i];
-    const double w = weight.empty() ? 1.0 : weight[j];
-    if (score[j] != threshold) {
-      threshold = score[j];
-      accum += cur_neg * (cur_pos * 0.5 + sum_pos);
-      sum_pos += cur_pos;
-      cur_neg = cur_pos = 0;
-    }
-    if (label[j] > 0) cur_pos += w; else { cur_neg += w; sum_neg_total += w; }
-  }
-  accum += cur_neg * (cur_pos * 0.5 + sum_pos);
-  sum_pos += cur_pos;
-  if (sum_pos > 0 && sum_neg_total > 0) return accum / (sum_pos * sum_neg_total);
-  return 1.0;
+// ---- evaluation on the device (metric_kernels.cuh): only the reduced sums cross PCIe
+static int MetricKindOf(const std::string& m) {
+  static const std::map<std::string, int> kinds = {
+      {"l2", kMetL2}, {"rmse", kMetL2}, {"l1", kMetL1}, {"huber", kMetHuber}, {"fair", kMetFair}, {"poisson", kMetPoisson}, {"gamma", kMetGamma},
+      {"gamma_deviance", kMetGammaDeviance}, {"tweedie", kMetTweedie}, {"quantile", kMetQuantile}, {"mape", kMetMape},
+      {"binary_logloss", kMetBinLogloss}, {"binary_error", kMetBinError}, {"multi_logloss", kMetMultiLogloss}, {"multi_error", kMetMultiError},
+      {"cross_entropy", kMetXent}};
+  auto it = kinds.find(m);
+  return it == kinds.end() ? -1 : it->second;
+}
+void Booster::ValidateMetrics() const {
+  for (auto& m : cfg.metric)
+    if (MetricKindOf(m) < 0 && m != "auc" && m != "ndcg" && m != "map") Fatal("Unknown metric type name: " + m);
+  if (cfg.eval_at.size() > static_cast<size_t>(kMaxEvalAt)) Fatal("eval_at: at most " + std::to_string(kMaxEvalAt) + " positions are supported");
 }
 
 std::vector<double> Booster::GetEval(int data_idx) {
   if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data to evaluate");
   EnsureDevice();
+  if (is_dart_ && data_idx == 0 && !dart_dropped_this_iter_) DroppingTrees();      // DART::GetTrainingScore
   const Dataset* ds = data_idx == 0 ? train : valids_.at(data_idx - 1)->ds;
   const DevBuf<double>& sc = data_idx == 0 ? score_ : valids_[data_idx - 1]->score;
   const int n = ds->num_data;
-  std::vector<double> raw(static_cast<size_t>(K) * n);
-  sc.Download(raw.data(), raw.size(), stream_);
-  B200_CUDA(cudaStreamSynchronize(stream_));
-  const std::vector<float>& y = ds->label;
-  const std::vector<float>& w = ds->weight;
+  cudaStream_t s = stream_;
+  if (ds->label.empty()) Fatal("label should not be empty for evaluation");
+  const float* d_y = ds->d_label.p;
+  const float* d_w = ds->weight.empty() ? nullptr : ds->d_weight.p;
+  const int grid = std::max(1, std::min((n + kMetricBlock - 1) / kMetricBlock, num_sms_ * 8));
+  if (met_partial_.n < static_cast<size_t>(grid) * 2 * kMaxEvalAt) met_partial_.Alloc(static_cast<size_t>(grid) * 2 * kMaxEvalAt);
+  if (met_out_.n < 2 * kMaxEvalAt) met_out_.Alloc(2 * kMaxEvalAt);
   std::vector<double> out;
   auto avg = [&](double loss, double sw) {
     double v[2] = {loss, sw};
-    AllReduceHost(v, 2, ncclSum, stream_);     // averaged metrics are global in distributed mode (B.5)
+    AllReduceHost(v, 2, ncclSum, s);     // averaged metrics are global in distributed mode (B.5)
     return v[0] / v[1];
   };
+  auto fetch = [&](int count, double* host) {
+    met_out_.Download(host, count, s);
+    B200_CUDA(cudaStreamSynchronize(s));
+  };
+  bool rank_done = false;
+  std::vector<double> ndcg_vals, map_vals;
   for (auto& m : cfg.metric) {
-    if (m == "huber" || m == "fair" || m == "poisson" || m == "gamma" || m == "tweedie") {
-      double loss = 0, sw = 0;
-      const double rho = cfg.tweedie_variance_power, c = cfg.fair_c, a = cfg.alpha;
-      for (int i = 0; i < n; ++i) {
-        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
-        double sc = raw[i], l;
-        if (m == "huber") { double d = sc - lab; l = std::fabs(d) <= a ? 0.5 * d * d : a * (std::fabs(d) - 0.5 * a); }
-        else if (m == "fair") { double x = std::fabs(sc - lab); l = c * x - c * c * std::log(1.0 + x / c); }
-        else {
-          sc = std::exp(sc);                                  // ConvertOutput
-          if (m == "poisson") { sc = std::max(sc, 1e-10); l = sc - lab * std::log(sc); }
-          else if (m == "gamma") { double theta = -1.0 / sc, b = -(-theta > 0 ? std::log(-theta) : -INFINITY); double cc = (lab > 0 ? std::log(lab) : -INFINITY) - (lab > 0 ? std::log(lab) : -INFINITY); l = -((lab * theta - b) + cc); }
-          else { sc = std::max(sc, 1e-10); l = -lab * std::exp((1 - rho) * std::log(sc)) / (1 - rho) + std::exp((2 - rho) * std::log(sc)) / (2 - rho); }
-        }
-        loss += l * wi; sw += wi;
-      }
-      out.push_back(avg(loss, sw));
-    } else if (m == "quantile" || m == "mape") {      // [LightGBM regression_metric.hpp QuantileMetric / MAPEMetric]
-      double loss = 0, sw = 0;
-      const double a = cfg.alpha;
-      for (int i = 0; i < n; ++i) {
-        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
-        double l;
-        if (m == "quantile") { const double delta = lab - raw[i]; l = delta < 0 ? (a - 1.0) * delta : a * delta; }
-        else l = std::fabs(lab - raw[i]) / std::max(1.0, std::fabs(lab));
-        loss += l * wi; sw += wi;
-      }
-      out.push_back(avg(loss, sw));
-    } else if (m == "l2" || m == "rmse" || m == "l1") {
-      double loss = 0, sw = 0;
-      for (int i = 0; i < n; ++i) {
-        double wi = w.empty() ? 1.0 : w[i], d = raw[i] - y[i];
-        loss += (m == "l1" ? std::fabs(d) : d * d) * wi; sw += wi;
-      }
-      double v = avg(loss, sw);
-      out.push_back(m == "rmse" ? std::sqrt(v) : v);
-    } else if (m == "binary_logloss" || m == "binary_error") {
-      double loss = 0, sw = 0;
-      for (int i = 0; i < n; ++i) {
-        double wi = w.empty() ? 1.0 : w[i];
-        double p = 1.0 / (1.0 + std::exp(-cfg.sigmoid * raw[i]));
-        if (m == "binary_error") loss += ((p <= 0.5) == (y[i] > 0) ? 1.0 : 0.0) * wi;
-        else {
-          double pl = y[i] > 0 ? p : 1.0 - p;
-          loss += (pl > kEps ? -std::log(pl) : -std::log(kEps)) * wi;
-        }
-        sw += wi;
-      }
-      out.push_back(avg(loss, sw));
-    } else if (m == "cross_entropy") {       // [UPSTREAM xentropy_metric.hpp XentLoss], log argument floored at 1e-12
-      double loss = 0, sw = 0;
-      for (int i = 0; i < n; ++i) {
-        const double wi = w.empty() ? 1.0 : w[i], lab = y[i];
-        const double p = 1.0 / (1.0 + std::exp(-raw[i]));
-        const double a = lab * (p > 1e-12 ? std::log(p) : std::log(1e-12)), b = (1.0 - lab) * (1.0 - p > 1e-12 ? std::log(1.0 - p) : std::log(1e-12));
-        loss += -(a + b) * wi; sw += wi;
-      }
-      out.push_back(avg(loss, sw));
+    const int kind = MetricKindOf(m);
+    if (kind >= 0) {
+      MetricParams mp{kind, K, is_ova_ ? 1 : 0, 0, cfg.alpha, cfg.fair_c, cfg.tweedie_variance_power, cfg.sigmoid};
+      if ((kind == kMetMultiLogloss || kind == kMetMultiError) && K < 2) Fatal("metric " + m + " needs a multiclass objective");
+      k_metric_pointwise<<<grid, kMetricBlock, 0, s>>>(sc.p, d_y, d_w, n, mp, met_partial_.p);
+      k_metric_finish<<<1, 32, 0, s>>>(met_partial_.p, grid, 2, met_out_.p);
+      B200_CUDA(cudaGetLastError());
+      double v[2];
+      fetch(2, v);
+      const double a = avg(v[0], v[1]);
+      out.push_back(m == "rmse" ? std::sqrt(a) : a);
     } else if (m == "auc") {
-      std::vector<double> s1(raw.begin(), raw.begin() + n);
-      out.push_back(AucOf(s1, y, w));
-    } else if (m == "multi_logloss" || m == "multi_error") {
-      double loss = 0, sw = 0;
-      std::vector<double> r(K), p(K);
-      for (int i = 0; i < n; ++i) {
-        double wi = w.empty() ? 1.0 : w[i];
-        for (int k = 0; k < K; ++k) r[k] = raw[static_cast<size_t>(k) * n + i];
-        model.Convert(r.data(), p.data());
-        int l = static_cast<int>(y[i]);
-        if (m == "multi_error") { int larger = 0; for (int k = 0; k < K; ++k) if (p[k] >= p[l]) ++larger; loss += (larger > 1 ? 1.0 : 0.0) * wi; }
-        else loss += (p[l] > kEps ? -std::log(p[l]) : -std::log(kEps)) * wi;
-        sw += wi;
+      // [UPSTREAM AUCMetric::Eval] is rank-local (no network sync), like the reference's per-task evaluation
+      if (auc_keys_a_.n < static_cast<size_t>(n)) {
+        auc_keys_a_.Alloc(n); auc_keys_b_.Alloc(n); auc_rows_a_.Alloc(n); auc_rows_b_.Alloc(n); auc_wpos_.Alloc(n); auc_wneg_.Alloc(n);
+        auc_ppos_.Alloc(n); auc_pneg_.Alloc(n); auc_head_.Alloc(n); auc_start_.Alloc(n);
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, t1, auc_keys_a_.p, auc_keys_b_.p, auc_rows_a_.p, auc_rows_b_.p, n, 0, 64, s);
+        cub::DeviceScan::InclusiveSum(nullptr, t2, auc_wpos_.p, auc_ppos_.p, n, s);
+        cub::DeviceScan::InclusiveScan(nullptr, t3, auc_head_.p, auc_start_.p, cub::Max(), n, s);
+        auc_tmp_.Alloc(std::max(t1, std::max(t2, t3)) + 16);
       }
-      out.push_back(avg(loss, sw));
-    } else if (m == "ndcg") {
-      std::vector<double> lg = cfg.label_gain;
-      if (lg.empty()) { lg.push_back(0.0); for (int i = 1; i < 31; ++i) lg.push_back(static_cast<double>((1 << i) - 1)); }
-      const int nq = static_cast<int>(ds->query_boundaries.size()) - 1;
-      if (nq <= 0) Fatal("The NDCG metric requires query information");
-      std::vector<double> acc(cfg.eval_at.size(), 0.0);
-      double sumq = 0;
-      for (int q = 0; q < nq; ++q) {
-        const int s0 = ds->query_boundaries[q], cnt = ds->query_boundaries[q + 1] - s0;
-        std::vector<int> ord(cnt);
-        std::iota(ord.begin(), ord.end(), 0);
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return raw[s0 + a] > raw[s0 + b]; });
-        std::vector<int> lab(cnt);
-        for (int i = 0; i < cnt; ++i) lab[i] = static_cast<int>(y[s0 + i]);
-        std::vector<int> sorted_lab = lab;
-        std::sort(sorted_lab.begin(), sorted_lab.end(), std::greater<int>());
-        sumq += 1;
+      size_t tb = auc_tmp_.n;
+      const int eg = num_sms_ * 8;
+      k_auc_keys<<<eg, 256, 0, s>>>(sc.p, n, auc_keys_a_.p, auc_rows_a_.p);
+      B200_CUDA(cub::DeviceRadixSort::SortPairsDescending(auc_tmp_.p, tb, auc_keys_a_.p, auc_keys_b_.p, auc_rows_a_.p, auc_rows_b_.p, n, 0, 64, s));
+      k_auc_weights<<<eg, 256, 0, s>>>(auc_keys_b_.p, auc_rows_b_.p, d_y, d_w, n, auc_wpos_.p, auc_wneg_.p, auc_head_.p);
+      tb = auc_tmp_.n; B200_CUDA(cub::DeviceScan::InclusiveSum(auc_tmp_.p, tb, auc_wpos_.p, auc_ppos_.p, n, s));
+      tb = auc_tmp_.n; B200_CUDA(cub::DeviceScan::InclusiveSum(auc_tmp_.p, tb, auc_wneg_.p, auc_pneg_.p, n, s));
+      tb = auc_tmp_.n; B200_CUDA(cub::DeviceScan::InclusiveScan(auc_tmp_.p, tb, auc_head_.p, auc_start_.p, cub::Max(), n, s));
+      k_auc_terms<<<grid, kMetricBlock, 0, s>>>(auc_keys_b_.p, auc_start_.p, auc_ppos_.p, auc_pneg_.p, n, met_partial_.p);
+      k_metric_finish<<<1, 32, 0, s>>>(met_partial_.p, grid, 2, met_out_.p);
+      B200_CUDA(cudaGetLastError());
+      double v[2], tot[2];
+      fetch(2, v);
+      B200_CUDA(cudaMemcpyAsync(&tot[0], auc_ppos_.p + (n - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaMemcpyAsync(&tot[1], auc_pneg_.p + (n - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      out.push_back((tot[0] > 0 && tot[1] > 0) ? v[0] / (tot[0] * tot[1]) : 1.0);
+    } else if (m == "ndcg" || m == "map") {
+      if (!rank_done) {
+        const int nq = static_cast<int>(ds->query_boundaries.size()) - 1;
+        if (nq <= 0) Fatal("The " + std::string(m == "ndcg" ? "NDCG" : "MAP") + " metric requires query information");
+        std::vector<double> lg = cfg.label_gain;
+        if (lg.empty()) { lg.push_back(0.0); for (int i = 1; i < 31; ++i) lg.push_back(static_cast<double>((1 << i) - 1)); }
+        int max_q = 1;
+        for (int q = 0; q < nq; ++q) max_q = std::max(max_q, ds->query_boundaries[q + 1] - ds->query_boundaries[q]);
+        std::vector<double> disc(static_cast<size_t>(max_q) + 1);
+        for (size_t i = 0; i < disc.size(); ++i) disc[i] = 1.0 / std::log2(2.0 + i);
+        DevBuf<double> d_lg, d_disc;
+        d_lg.Alloc(lg.size()); d_lg.Upload(lg.data(), lg.size(), s);
+        d_disc.Alloc(disc.size()); d_disc.Upload(disc.data(), disc.size(), s);
+        RankEvalParams rp{};
+        std::vector<int> ks = cfg.eval_at;      // evaluated in ascending order ([UPSTREAM] Config sorts eval_at); reported in the given order
+        std::sort(ks.begin(), ks.end());
+        rp.nk = static_cast<int>(ks.size());
+        for (int e = 0; e < rp.nk; ++e) rp.ks[e] = ks[e];
+        rp.want_ndcg = std::find(cfg.metric.begin(), cfg.metric.end(), "ndcg") != cfg.metric.end();
+        rp.want_map = std::find(cfg.metric.begin(), cfg.metric.end(), "map") != cfg.metric.end();
+        const size_t smem = static_cast<size_t>(max_q) * (8 + 4 + 4);
+        if (smem > 200 * 1024) Fatal("a query group is too large for the ranking metric kernel");
+        B200_CUDA(cudaFuncSetAttribute(k_metric_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
+        const int rgrid = std::max(1, std::min(nq, num_sms_ * 8));
+        if (met_partial_.n < static_cast<size_t>(rgrid) * 2 * kMaxEvalAt) met_partial_.Alloc(static_cast<size_t>(rgrid) * 2 * kMaxEvalAt);
+        k_metric_rank<<<rgrid, 128, std::max<size_t>(smem, 1024), s>>>(sc.p, d_y, ds->d_qb.p, nq, d_lg.p, static_cast<int>(lg.size()), d_disc.p, rp, max_q, met_partial_.p);
+        k_metric_finish<<<1, 32, 0, s>>>(met_partial_.p, rgrid, 2 * kMaxEvalAt, met_out_.p);
+        B200_CUDA(cudaGetLastError());
+        double v[2 * kMaxEvalAt];
+        fetch(2 * kMaxEvalAt, v);
         for (size_t e = 0; e < cfg.eval_at.size(); ++e) {
-          int k = std::min(cfg.eval_at[e], cnt);
-          double maxdcg = 0, dcg = 0;
-          for (int j = 0; j < k; ++j) { maxdcg += lg[sorted_lab[j]] / std::log2(2.0 + j); dcg += lg[lab[ord[j]]] / std::log2(2.0 + j); }
-          acc[e] += maxdcg > 0 ? dcg / maxdcg : 1.0;
+          const size_t pos = std::find(ks.begin(), ks.end(), cfg.eval_at[e]) - ks.begin();
+          ndcg_vals.push_back(avg(v[pos], nq));
+          map_vals.push_back(avg(v[kMaxEvalAt + pos], nq));
         }
+        rank_done = true;
       }
-      for (size_t e = 0; e < acc.size(); ++e) out.push_back(avg(acc[e], sumq));
+      const std::vector<double>& vals = m == "ndcg" ? ndcg_vals : map_vals;
+      out.insert(out.end(), vals.begin(), vals.end());
     } else {
       Fatal("Unknown metric type name: " + m);
     }
@@ -2054,14 +2066,6 @@ int64_t Booster::PredictBatch(const void* data, int data_type, int64_t nrow, int
     }
   }
   return nrow * per_row;
-}
-
-void Booster::ExportLastHistogram(double* out) {
-  EnsureDevice();
-  DevBuf<double> d; d.Alloc(slot_elems_);
-  k_hist_to_double<<<num_sms_ * 4, 256, 0, stream_>>>(H_.p, d.p, slot_elems_, ctrl_.p);
-  d.Download(out, slot_elems_, stream_);
-  B200_CUDA(cudaStreamSynchronize(stream_));
 }
 
 }  // namespace b200gbm

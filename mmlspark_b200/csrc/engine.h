@@ -143,6 +143,7 @@ class Booster {
   void MergeFrom(const Booster* other);
   std::vector<std::string> EvalNames() const;
   std::vector<double> GetEval(int data_idx);
+  void ValidateMetrics() const;
   void GetPredict(int data_idx, int64_t* out_len, double* out);
   int64_t NumPredict(int data_idx) const;
   void GetRawScores(int data_idx, double* out);
@@ -159,7 +160,6 @@ class Booster {
   Timing timing;
   std::map<std::string, double> split_op_ms_; int split_op_trees_ = 0;      // B200GBM_SPLIT_TIMING debug accounting
   bool profile_hist = false;                              // time K4 with events on the engine stream
-  void ExportLastHistogram(double* out);                  // fp64 view of the scratch histogram of the last round
   std::vector<double> trace;                              // per split records (see B200GBM_BoosterGetTrace)
 
   Config cfg;
@@ -174,6 +174,8 @@ class Booster {
   void ComputeGradients();
   bool TrainTrees(const float* custom_g, const float* custom_h);
   void TrainOneTree(int class_id, HostTree* out);
+  void LaunchPartition(int grid, int last);
+  int part_max_blocks_ = 148;
   double BoostFromAverage(int class_id);
   double ObjectiveInitScore(int class_id);
   std::string ObjectiveString() const;
@@ -251,7 +253,7 @@ class Booster {
   DevBuf<unsigned> part_bits_;
   DevBuf<int> part_chunks_;
   // lambdarank
-  DevBuf<double> lr_inv_max_dcg_, lr_label_gain_;
+  DevBuf<double> lr_inv_max_dcg_, lr_label_gain_, lr_discount_;
   DevBuf<float> lr_sig_table_;
   double lr_min_in_ = -50, lr_max_in_ = 50, lr_idx_factor_ = 0;
   int lr_max_q_ = 0;
@@ -269,6 +271,11 @@ class Booster {
   std::unique_ptr<ForestBufs> forest_;
   void UploadForest();
   std::vector<ValidSet*> valids_;
+  // device-side evaluation scratch (metric_kernels.cuh)
+  DevBuf<double> met_partial_, met_out_, auc_wpos_, auc_wneg_, auc_ppos_, auc_pneg_;
+  DevBuf<unsigned long long> auc_keys_a_, auc_keys_b_;
+  DevBuf<int> auc_rows_a_, auc_rows_b_, auc_head_, auc_start_;
+  DevBuf<unsigned char> auc_tmp_;
   int num_sms_ = 148;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;
 };

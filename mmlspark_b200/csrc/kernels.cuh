@@ -66,7 +66,9 @@ struct TreeCtrl {
   long long root_q[4];         // sum q_g, sum q_h, local rows, unused  (allreduced)
   long long trace_rows;        // sum of rows scanned by K4 this tree (for the roofline byte model)
   unsigned scan_ticket;        // blocks of k_scan that finished this round (the last one runs the pick step)
-  int q_side;                  // partition: side (0 left, 1 right) whose rows K4 will scan next = the smaller child
+  int q_side;                  // (unused since the fused partition kernel decides the side itself)
+  unsigned part_barrier;       // k_partition: grid-barrier arrive counter (reset by its last block)
+  unsigned part_ticket;        // k_partition: finished-block ticket (the last block runs the next round's controller)
 };
 
 struct TreeDev {               // SoA tree under construction (sizes: num_leaves / num_leaves-1)
@@ -254,32 +256,37 @@ __global__ void k_grad_softmax(const double* __restrict__ score, const float* __
 }
 
 // [UPSTREAM LambdarankNDCG::GetGradientsForOneQuery] — one block per query (K2).
-// Sorting: stable rank by score descending (O(cnt^2) rank counting; queries are ~100 docs).
-__global__ void __launch_bounds__(256)
+// Sorting: stable rank by score descending (rank counting out of shared memory; queries are ~100 docs).
+// Accumulation: one thread per DOCUMENT adds the pairs it takes part in, in the reference's own (i, j) pair order — pairs (i, p) with
+// i < min(p, truncation) ascending, then pairs (p, j), j > p, when p < truncation — with the reference's fp32 `+=` / `-=` on a score_t
+// accumulator.  Every pair is evaluated twice (once per side) but there are no atomics (shared-memory float atomicAdd is a CAS loop on
+// sm_100a) and each document's lambda / hessian is the same sequence of fp32 additions as the sequential reference, so gradients are
+// reproducible run to run and equal to the oracle's up to the fp64 rounding of the normalisation factor.  discount[] = 1 / log2(2 + pos)
+// is the host-computed table the reference uses (DCGCalculator::GetDiscount), not a device log2.
+__global__ void __launch_bounds__(128)
 k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
                   const int* __restrict__ qb, int nq, const double* __restrict__ inv_max_dcg, const double* __restrict__ label_gain,
-                  const float* __restrict__ sig_table, int sig_bins, double min_in, double max_in, double idx_factor, double sigmoid,
-                  int truncation, int norm, float* __restrict__ g, float* __restrict__ h, int max_q) {
+                  const double* __restrict__ discount, const float* __restrict__ sig_table, int sig_bins, double min_in, double max_in,
+                  double idx_factor, double sigmoid, int truncation, int norm, float* __restrict__ g, float* __restrict__ h, int max_q) {
   extern __shared__ unsigned char lr_smem[];
-  double* s_score = reinterpret_cast<double*>(lr_smem);                 // [max_q] sorted scores
-  float* s_lam = reinterpret_cast<float*>(s_score + max_q);              // [max_q] by sorted pos
-  float* s_hes = s_lam + max_q;
-  int* s_lab = reinterpret_cast<int*>(s_hes + max_q);                    // label by sorted pos
-  int* s_orig = s_lab + max_q;                                           // original index by sorted pos
-  __shared__ double s_sum_lambda;
+  double* r_score = reinterpret_cast<double*>(lr_smem);                  // [max_q] scores in document order
+  double* s_score = r_score + max_q;                                     // [max_q] scores by sorted position
+  int* s_lab = reinterpret_cast<int*>(s_score + max_q);                  // label by sorted position
+  int* s_orig = s_lab + max_q;                                           // document index by sorted position
+  __shared__ double s_part[128];
   for (int q = blockIdx.x; q < nq; q += gridDim.x) {
     const int start = qb[q], cnt = qb[q + 1] - start;
     __syncthreads();
-    if (threadIdx.x == 0) s_sum_lambda = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) r_score[i] = score[start + i];
+    __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      double si = score[start + i];
+      const double si = r_score[i];
       int rank = 0;
       for (int j = 0; j < cnt; ++j) {
-        double sj = score[start + j];
+        const double sj = r_score[j];
         rank += (sj > si) || (sj == si && j < i);
       }
       s_score[rank] = si; s_lab[rank] = static_cast<int>(label[start + i]); s_orig[rank] = i;
-      s_lam[rank] = 0.f; s_hes[rank] = 0.f;
     }
     __syncthreads();
     const double imd = inv_max_dcg[q];
@@ -287,45 +294,66 @@ k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ la
     int worst_idx = cnt - 1;
     if (worst_idx > 0 && s_score[worst_idx] == kNegInf) worst_idx -= 1;
     const double worst_score = s_score[worst_idx];
-    // pairs (i<j), i below the truncation level.  Accumulation order differs from the sequential
-    // reference only in fp32 addition order of per-document lambdas (documented tolerance).
-    const int ilim = min(cnt - 1, truncation);
-    double local_sum = 0.0;
-    for (int p = threadIdx.x; p < ilim * cnt; p += blockDim.x) {
-      const int i = p / cnt, j = p % cnt;
-      if (j <= i) continue;
-      if (s_score[i] == kNegInf || s_score[j] == kNegInf) continue;
-      if (s_lab[i] == s_lab[j]) continue;
-      int hr, lr;
-      if (s_lab[i] > s_lab[j]) { hr = i; lr = j; } else { hr = j; lr = i; }
-      const double delta_score = s_score[hr] - s_score[lr];
-      const double dcg_gap = label_gain[s_lab[hr]] - label_gain[s_lab[lr]];
-      const double paired_discount = fabs(1.0 / log2(2.0 + hr) - 1.0 / log2(2.0 + lr));
+    const bool do_div = norm && best_score != worst_score;
+    // pair (i, j), i < j (sorted positions): returns p_lambda / p_hessian and whether position i is the higher-labelled one
+    auto pair = [&](int i, int j, double* p_lambda, double* p_hessian, bool* i_high) -> bool {
+      const double sci = s_score[i], scj = s_score[j];
+      if (sci == kNegInf || scj == kNegInf) return false;
+      const int li = s_lab[i], lj = s_lab[j];
+      if (li == lj) return false;
+      const bool ih = li > lj;
+      const int hr = ih ? i : j, lr = ih ? j : i;
+      const double delta_score = ih ? sci - scj : scj - sci;
+      const double dcg_gap = label_gain[ih ? li : lj] - label_gain[ih ? lj : li];
+      const double paired_discount = fabs(discount[hr] - discount[lr]);
       double delta = dcg_gap * paired_discount * imd;
-      if (norm && best_score != worst_score) delta /= (0.01f + fabs(delta_score));
-      double p_lambda;
-      if (delta_score <= min_in) p_lambda = sig_table[0];
-      else if (delta_score >= max_in) p_lambda = sig_table[sig_bins - 1];
-      else p_lambda = sig_table[static_cast<size_t>((delta_score - min_in) * idx_factor)];
-      double p_hessian = p_lambda * (1.0f - p_lambda);
-      p_lambda *= -sigmoid * delta;
-      p_hessian *= sigmoid * sigmoid * delta;
-      atomicAdd(&s_lam[lr], -static_cast<float>(p_lambda));
-      atomicAdd(&s_hes[lr], static_cast<float>(p_hessian));
-      atomicAdd(&s_lam[hr], static_cast<float>(p_lambda));
-      atomicAdd(&s_hes[hr], static_cast<float>(p_hessian));
-      local_sum -= 2 * p_lambda;
+      if (do_div) delta /= (0.01f + fabs(delta_score));
+      double pl;
+      if (delta_score <= min_in) pl = sig_table[0];
+      else if (delta_score >= max_in) pl = sig_table[sig_bins - 1];
+      else pl = sig_table[static_cast<size_t>((delta_score - min_in) * idx_factor)];
+      double ph = pl * (1.0f - pl);
+      pl *= -sigmoid * delta;
+      ph *= sigmoid * sigmoid * delta;
+      *p_lambda = pl; *p_hessian = ph; *i_high = ih;
+      return true;
+    };
+    double local_sum = 0.0;
+    for (int pbase = 0; pbase < cnt; pbase += blockDim.x) {
+      const int p = pbase + threadIdx.x;
+      float lam = 0.f, hes = 0.f;
+      if (p < cnt) {
+        const int ilim = min(p, min(truncation, cnt - 1));
+        for (int i = 0; i < ilim; ++i) {            // this document is the later position j of the pair
+          double pl, ph; bool ih;
+          if (!pair(i, p, &pl, &ph, &ih)) continue;
+          lam = ih ? __fsub_rn(lam, static_cast<float>(pl)) : __fadd_rn(lam, static_cast<float>(pl));      // low: -=, high: +=
+          hes = __fadd_rn(hes, static_cast<float>(ph));
+        }
+        if (p < truncation && p < cnt - 1) {
+          for (int j = p + 1; j < cnt; ++j) {       // this document is the earlier position i of the pair
+            double pl, ph; bool ih;
+            if (!pair(p, j, &pl, &ph, &ih)) continue;
+            lam = ih ? __fadd_rn(lam, static_cast<float>(pl)) : __fsub_rn(lam, static_cast<float>(pl));
+            hes = __fadd_rn(hes, static_cast<float>(ph));
+            local_sum -= 2 * pl;                    // every pair is counted once, by its earlier position
+          }
+        }
+      }
+      // keep the accumulators in the (now unused) raw-score slots until the normalisation factor is known
+      if (p < cnt) { reinterpret_cast<float*>(r_score)[2 * p] = lam; reinterpret_cast<float*>(r_score)[2 * p + 1] = hes; }
     }
-    atomicAdd(&s_sum_lambda, local_sum);
+    s_part[threadIdx.x] = local_sum;
     __syncthreads();
+    double sum_lambdas = 0.0;
+    if (norm) for (int t = 0; t < min(static_cast<int>(blockDim.x), cnt); ++t) sum_lambdas += s_part[t];      // fixed order: reproducible
     double nf = 1.0;
-    const double sum_lambdas = s_sum_lambda;
     const bool do_norm = norm && sum_lambdas > 0;
     if (do_norm) nf = log2(1 + sum_lambdas) / sum_lambdas;
     for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
-      float lam = s_lam[r], hes = s_hes[r];
+      float lam = reinterpret_cast<float*>(r_score)[2 * r], hes = reinterpret_cast<float*>(r_score)[2 * r + 1];
       if (do_norm) { lam = static_cast<float>(lam * nf); hes = static_cast<float>(hes * nf); }
-      int o = start + s_orig[r];
+      const int o = start + s_orig[r];
       if (weight) { lam = static_cast<float>(lam * weight[o]); hes = static_cast<float>(hes * weight[o]); }
       g[o] = lam; h[o] = hes;
     }
@@ -407,20 +435,22 @@ k_tree_init(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, Spl
 
 // Applies the split chosen in the previous round (Tree::Split + leaf bookkeeping, using the TRUE row
 // counts in the serial learner and the hessian-reconstructed global counts in the data-parallel one),
-// then runs SerialTreeLearner::BeforeFindBestSplit for the coming round.
-__global__ void __launch_bounds__(256)
-k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p,
-            int last) {
-  __shared__ int s_copy_from, s_copy_to;
+// then runs SerialTreeLearner::BeforeFindBestSplit for the coming round.  One block; thread 0 does the bookkeeping, all threads copy
+// the inherited is_splittable flags.  Runs as its own kernel before a tree's first round and, for every later round, in the last
+// block of the partition kernel of the previous round (k_partition) — one launch and one kernel boundary less per split.
+__device__ __forceinline__ void
+d_round_ctl(TreeCtrl* ctrl, LeafState* leaves, const TreeDev& tree, uint8_t* flags, const FeatMeta* __restrict__ meta, const SplitParams& p, int last,
+            int* s_copy) {       // s_copy: 2 shared ints
   if (threadIdx.x == 0) {
-    s_copy_from = -1; s_copy_to = -1;
+    s_copy[0] = -1; s_copy[1] = -1;
     if (ctrl->pending) {
       ctrl->pending = 0;
       const int leaf = ctrl->split_leaf, nl = ctrl->new_leaf;
       LeafState& L = leaves[leaf];
       LeafState& R = leaves[nl];
       LeafBest b = L.best;
-      const int true_left = ctrl->part_left_total, true_right = ctrl->part_count - true_left;
+      // written by another block of the same kernel when this runs as the tail of k_partition: read through L2
+      const int true_left = __ldcg(&ctrl->part_left_total), true_right = ctrl->part_count - true_left;
       if (!p.parallel) { b.left_count = true_left; b.right_count = true_right; }
       // Tree::Split
       const int node = ctrl->num_leaves - 1;
@@ -477,7 +507,7 @@ k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
           if (nl_cnt < nr_cnt) { smaller = ll; larger = rl; } else { smaller = rl; larger = ll; }
           // parent's histogram sits in the slot of `ll`; the larger child inherits it
           if (larger == rl) { int t = leaves[ll].hist_slot; leaves[ll].hist_slot = leaves[rl].hist_slot; leaves[rl].hist_slot = t; }
-          s_copy_from = ll; s_copy_to = rl;
+          s_copy[0] = ll; s_copy[1] = rl;
         }
         ctrl->smaller = smaller; ctrl->larger = larger; ctrl->go = 1;
         const LeafState& S = leaves[smaller];
@@ -490,8 +520,14 @@ k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     ctrl->round += 1;
   }
   __syncthreads();
-  if (s_copy_from >= 0)   // children inherit the parent's per-feature is_splittable flags
-    for (int u = threadIdx.x; u < p.nf_pad; u += blockDim.x) flags[static_cast<size_t>(s_copy_to) * p.nf_pad + u] = flags[static_cast<size_t>(s_copy_from) * p.nf_pad + u];
+  if (s_copy[0] >= 0)   // children inherit the parent's per-feature is_splittable flags
+    for (int u = threadIdx.x; u < p.nf_pad; u += blockDim.x) flags[static_cast<size_t>(s_copy[1]) * p.nf_pad + u] = flags[static_cast<size_t>(s_copy[0]) * p.nf_pad + u];
+}
+__global__ void __launch_bounds__(256)
+k_round_ctl(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p,
+            int last) {
+  __shared__ int s_copy[2];
+  d_round_ctl(ctrl, leaves, tree, flags, meta, p, last, s_copy);
 }
 
 // ---------------------------------------------------------------- K5/K6 split scan
@@ -1108,130 +1144,183 @@ k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, 
   if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
 }
 
-// ---------------------------------------------------------------- K7 row partition (stable)
+// ---------------------------------------------------------------- K7 row partition (stable), one cooperative kernel per split
+// Replaces [UPSTREAM] DataPartition::Split.  Round 1 ran three kernels (decision bits + per-chunk left counts, single-block scan of the
+// chunk counts, scatter) plus a memset of the scratch histogram and the next round's controller: five launches on the per-split
+// critical path.  They are now the phases of ONE cooperatively launched kernel separated by software grid barriers (all blocks are
+// resident; the arrive counter lives in TreeCtrl):
+//   phase 0  zero the scratch histogram H for the next K4 (the scan kernel consumed it; stream order)
+//   phase 1  decision bit per row (ballot words) and the left count of every 2048-row chunk
+//   ---- grid barrier
+//   phase 2  chunk prefix: leaves of <= 2048 chunks (4M rows) are scanned redundantly by every block in shared memory (no second
+//            barrier); larger ones by block 0 in place, followed by a second barrier
+//   phase 3  stable scatter into the other index buffer (lefts first, then rights, original order kept); the (g,h) words of the
+//            child K4 scans next go into partition order (qord)
+//   tail     the block that finishes last applies the split to the tree and prepares the next round (d_round_ctl)
 constexpr int kPartChunk = 2048;     // rows per chunk = 256 threads x 8
+constexpr int kPartLocalScan = 2048; // chunk counts a block scans by itself
 __device__ __forceinline__ bool d_goes_left(unsigned bin, const TreeCtrl* c) {
   if (c->split_is_cat) return (c->split_cat_bits[bin >> 5] >> (bin & 31u)) & 1u;
   if (c->split_missing_type == 2 && bin == static_cast<unsigned>(c->split_num_bin - 1)) return c->split_default_left != 0;
   return bin <= static_cast<unsigned>(c->split_threshold);
 }
-// pass 1: decision bit per row (ballot words) + left count per chunk
-__global__ void __launch_bounds__(256)
-k_part_count(const TreeCtrl* __restrict__ ctrl, const uint8_t* __restrict__ bins, size_t rows_stride, const int* __restrict__ idx0,
-             const int* __restrict__ idx1, unsigned* __restrict__ bits, int* __restrict__ chunk_left) {
-  const int n = ctrl->part_count;
-  if (n <= 0) return;
-  const int* src = ctrl->part_buf ? idx1 : idx0;
-  const int f = ctrl->split_feature;
-  const uint8_t* col = bins + (static_cast<size_t>(f >> 5) * rows_stride) * 32 + (f & 31);
-  const int chunks = (n + kPartChunk - 1) / kPartChunk;
-  __shared__ int s_cnt[8];
-  for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
-    int local = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = c * kPartChunk + k * 256 + threadIdx.x;
-      bool left = false;
-      if (i < n) {
-        const int r = ctrl->part_identity ? (ctrl->part_begin + i) : src[ctrl->part_begin + i];
-        left = d_goes_left(col[static_cast<size_t>(r) * 32], ctrl);
-      }
-      unsigned bal = __ballot_sync(0xffffffffu, left);
-      if ((threadIdx.x & 31) == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
-    }
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_cnt[w]; chunk_left[c] = t; }
-    __syncthreads();
-  }
-}
-// pass 2: exclusive scan of the chunk counts (single block)
-__global__ void __launch_bounds__(1024)
-k_part_scan(TreeCtrl* ctrl, const LeafState* __restrict__ leaves, int parallel, int* __restrict__ chunk_left) {
-  const int n = ctrl->part_count;
-  if (n <= 0) return;
-  const int chunks = (n + kPartChunk - 1) / kPartChunk;
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
+// all blocks of a cooperative launch: arrive on a monotone counter, spin until `target` arrivals
+__device__ __forceinline__ void d_grid_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
-  for (int base = 0; base < chunks; base += 1024) {
-    const int i = base + threadIdx.x;
-    int v = i < chunks ? chunk_left[i] : 0;
-    int inc = v;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane], winc = w;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-      s_warp[lane] = winc - w;
-    }
-    __syncthreads();
-    const int excl = s_carry + s_warp[warp] + inc - v;
-    if (i < chunks) chunk_left[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = excl + v;
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    ctrl->part_left_total = s_carry;
-    // the child K4 scans next is the one with fewer rows by the rule of k_round_ctl (global counts of the split in data-parallel
-    // mode, true counts otherwise; ties -> right): k_part_scatter puts that child's (g,h) words into partition order (qord)
-    const LeafBest& b = leaves[ctrl->split_leaf].best;
-    const int lc = parallel ? b.left_count : s_carry, rc = parallel ? b.right_count : n - s_carry;
-    ctrl->q_side = lc < rc ? 0 : 1;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) __nanosleep(32);
+    __threadfence();
   }
+  __syncthreads();
 }
-// pass 3: stable scatter into the other index buffer (lefts first, then rights, original order kept)
 __global__ void __launch_bounds__(256)
-k_part_scatter(const TreeCtrl* __restrict__ ctrl, int* __restrict__ idx0, int* __restrict__ idx1, const unsigned* __restrict__ bits,
-               const int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord) {
-  const int n = ctrl->part_count;
-  if (n <= 0) return;
-  const int* src = ctrl->part_buf ? idx1 : idx0;
-  int* dst = ctrl->part_identity ? idx0 : (ctrl->part_buf ? idx0 : idx1);
-  const int begin = ctrl->part_begin, total_left = ctrl->part_left_total;
-  const bool q_left = ctrl->q_side == 0;
-  const int chunks = (n + kPartChunk - 1) / kPartChunk;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p, int last,
+            const uint8_t* __restrict__ bins, size_t rows_stride, int* __restrict__ idx0, int* __restrict__ idx1, unsigned* __restrict__ bits,
+            int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems) {
+  __shared__ int s_pref[kPartLocalScan + 1];
   __shared__ int s_wl[64];
-  for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
-    // 64 ballot words per chunk; word w covers rows c*2048 + w*32 ..
-    const int wbase = c * (kPartChunk / 32);
-    if (threadIdx.x < 64) {
-      const int i0 = c * kPartChunk + threadIdx.x * 32;
-      s_wl[threadIdx.x] = i0 < n ? __popc(bits[wbase + threadIdx.x]) : 0;
-    }
-    __syncthreads();
-    if (warp == 0) {   // exclusive scan of the 64 word counts (two per lane)
-      int a = s_wl[lane * 2], b = s_wl[lane * 2 + 1];
-      int sum = a + b, inc = sum;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      int ex = inc - sum;
-      s_wl[lane * 2] = ex; s_wl[lane * 2 + 1] = ex + a;
-    }
-    __syncthreads();
-    const int left_base = chunk_left[c];
-    const int right_base = c * kPartChunk - left_base;
+  __shared__ int s_cnt[8];
+  __shared__ int s_copy[2];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- phase 0: H := 0 (16-byte stores; H is L2-resident)
+  {
+    longlong2* h2 = reinterpret_cast<longlong2*>(H);
+    const size_t n2 = h_elems / 2;
+    const longlong2 z = make_longlong2(0, 0);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += static_cast<size_t>(gridDim.x) * blockDim.x) h2[i] = z;
+  }
+  const int n = ctrl->part_count;
+  if (n > 0) {
+    const int* src = ctrl->part_buf ? idx1 : idx0;
+    int* dst = ctrl->part_identity ? idx0 : (ctrl->part_buf ? idx0 : idx1);
+    const int begin = ctrl->part_begin, identity = ctrl->part_identity;
+    const int f = ctrl->split_feature;
+    const uint8_t* col = bins + (static_cast<size_t>(f >> 5) * rows_stride) * 32 + (f & 31);
+    const int chunks = (n + kPartChunk - 1) / kPartChunk;
+    // ---- phase 1
+    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+      int local = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int w = k * 8 + warp;                 // word index inside the chunk
-      const int i = c * kPartChunk + w * 32 + lane;
-      if (i < n) {
-        const unsigned word = bits[wbase + w];
-        const bool left = (word >> lane) & 1u;
-        const int lefts_before = s_wl[w] + __popc(word & ((1u << lane) - 1u));
-        const int r = ctrl->part_identity ? (begin + i) : src[begin + i];
-        int pos;
-        if (left) pos = begin + left_base + lefts_before;
-        else pos = begin + total_left + right_base + (w * 32 + lane - lefts_before);
-        dst[pos] = r;
-        if (left == q_left) qord[pos] = qgh[r];      // replaces a separate gather pass before K4 (k_gather_q)
+      for (int k = 0; k < 8; ++k) {
+        const int i = c * kPartChunk + k * 256 + threadIdx.x;
+        bool left = false;
+        if (i < n) {
+          const int r = identity ? (begin + i) : src[begin + i];
+          left = d_goes_left(col[static_cast<size_t>(r) * 32], ctrl);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, left);
+        if (lane == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
       }
+      if (lane == 0) s_cnt[warp] = local;
+      __syncthreads();
+      if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_cnt[w]; chunk_left[c] = t; }
+      __syncthreads();
     }
-    __syncthreads();
+    d_grid_barrier(&ctrl->part_barrier, gridDim.x);
+    // ---- phase 2: exclusive prefix of the chunk counts + total
+    int total_left;
+    const bool local_scan = chunks <= kPartLocalScan;
+    if (local_scan) {
+      // 256 threads x 8 consecutive counts, warp scan of the per-thread sums, then the block total
+      int v[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int i = threadIdx.x * 8 + k; v[k] = i < chunks ? __ldcg(chunk_left + i) : 0; sum += v[k]; }
+      int inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_cnt[warp] = inc;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+      int run = woff + inc - sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s_pref[threadIdx.x * 8 + k] = run; run += v[k]; }
+      if (threadIdx.x == 255) s_pref[kPartLocalScan] = run;
+      __syncthreads();
+      total_left = s_pref[kPartLocalScan];
+    } else {
+      if (blockIdx.x == 0) {
+        __shared__ int s_carry;
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < chunks; base += 256) {
+          const int i = base + threadIdx.x;
+          const int v = i < chunks ? __ldcg(chunk_left + i) : 0;
+          int inc = v;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+          if (lane == 31) s_cnt[warp] = inc;
+          __syncthreads();
+          int woff = 0;
+          for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+          const int excl = s_carry + woff + inc - v;
+          if (i < chunks) chunk_left[i] = excl;
+          __syncthreads();
+          if (threadIdx.x == 255) s_carry = excl + v;
+          __syncthreads();
+        }
+        if (threadIdx.x == 0) ctrl->part_left_total = s_carry;
+      }
+      d_grid_barrier(&ctrl->part_barrier, 2 * gridDim.x);
+      total_left = *reinterpret_cast<volatile int*>(&ctrl->part_left_total);
+    }
+    // the child K4 scans next is the one with fewer rows by the rule of d_round_ctl (global counts of the split in data-parallel
+    // mode, true counts otherwise; ties -> right): its (g,h) words are written in partition order (qord)
+    const LeafBest& bsp = leaves[ctrl->split_leaf].best;
+    const int lc = p.parallel ? bsp.left_count : total_left, rc = p.parallel ? bsp.right_count : n - total_left;
+    const bool q_left = lc < rc;
+    // ---- phase 3
+    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+      const int wbase = c * (kPartChunk / 32);     // 64 ballot words per chunk; word w covers rows c*2048 + w*32 ..
+      if (threadIdx.x < 64) {
+        const int i0 = c * kPartChunk + threadIdx.x * 32;
+        s_wl[threadIdx.x] = i0 < n ? __popc(__ldcg(bits + wbase + threadIdx.x)) : 0;
+      }
+      __syncthreads();
+      if (warp == 0) {   // exclusive scan of the 64 word counts (two per lane)
+        const int a = s_wl[lane * 2], b = s_wl[lane * 2 + 1];
+        const int sum = a + b;
+        int inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int ex = inc - sum;
+        s_wl[lane * 2] = ex; s_wl[lane * 2 + 1] = ex + a;
+      }
+      __syncthreads();
+      const int left_base = local_scan ? s_pref[c] : __ldcg(chunk_left + c);
+      const int right_base = c * kPartChunk - left_base;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int w = k * 8 + warp;                 // word index inside the chunk
+        const int i = c * kPartChunk + w * 32 + lane;
+        if (i < n) {
+          const unsigned word = __ldcg(bits + wbase + w);
+          const bool left = (word >> lane) & 1u;
+          const int lefts_before = s_wl[w] + __popc(word & ((1u << lane) - 1u));
+          const int r = identity ? (begin + i) : src[begin + i];
+          int pos;
+          if (left) pos = begin + left_base + lefts_before;
+          else pos = begin + total_left + right_base + (w * 32 + lane - lefts_before);
+          dst[pos] = r;
+          if (left == q_left) qord[pos] = qgh[r];      // replaces a separate gather pass before K4 (k_gather_q)
+        }
+      }
+      __syncthreads();
+    }
+    if (local_scan && blockIdx.x == 0 && threadIdx.x == 0) ctrl->part_left_total = total_left;
+  }
+  // ---- tail: the last block to finish runs the controller of the next round
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctrl->part_ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x == 0) { ctrl->part_ticket = 0u; ctrl->part_barrier = 0u; }
+    d_round_ctl(ctrl, leaves, tree, flags, meta, p, last, s_copy);
   }
 }
 

@@ -225,7 +225,7 @@ def test_ranker_validation_rows_are_grouped_before_counting(built):
     m = Spy(groupCol="query", validationIndicatorCol="valid", numIterations=10, numTasks=1, minDataInLeaf=5, evalAt=[1, 3]).fit(df)
     assert len(seen) == 1
     assert seen[0] == [int(s) for s in sizes[0::4]]         # whole groups, in group-id order
-    assert m.getBoosterNumTotalIterations() == 10
+    assert 1 <= m.getBoosterNumTotalIterations() <= 10      # earlyStoppingRound = 0: trainCore stops at the first non-improving round (TrainUtils.scala:139-143)
 
 
 def test_batches_and_empty_partition_do_not_hang(built):

@@ -86,11 +86,12 @@ def test_push_rows_matches_from_mat_and_oracle(built, dtype, source):
     ds.free(); ref.free()
 
 
-def _random_csr(rng, n, F, density):
+def _random_csr(rng, n, F, density, nan_rate=0.02):
     mask = rng.random((n, F)) < density
     D = np.where(mask, rng.standard_normal((n, F)), 0.0)
     D[:, 3] = np.where(mask[:, 3], rng.integers(1, 9, n), 0.0)
-    D[mask & (rng.random((n, F)) < 0.02)] = np.nan          # explicit NaN entries
+    if nan_rate > 0:
+        D[mask & (rng.random((n, F)) < nan_rate)] = np.nan      # explicit NaN entries
     D[0, :] = 0.0                                            # an empty row
     stored = mask.copy()
     stored[0, :] = False
@@ -120,9 +121,16 @@ def test_from_csr_bins_and_training(built):
     vs = capi.Dataset.from_csr(ipv, ixv, dv, F, DS_PARAMS, reference=ds)
     vd = capi.Dataset.from_mat(Dv, DS_PARAMS, reference=dd)
     assert np.array_equal(vs.get_bins(), vd.get_bins())
+    # training on a CSR dataset.  No NaN entries here: a NaN-missing feature in a leaf without NaN rows has two mathematically equal
+    # scan directions whose winner is decided by fp64 rounding in any implementation (DESIGN.md, K5 "Ties"), which is not what this test is about
+    D2, ip2, ix2, d2 = _random_csr(rng, n, F, 0.15, nan_rate=0.0)
+    y2 = (D2[:, 0] * 2 - D2[:, 1] + D2[:, 2] * D2[:, 5] + 0.1 * rng.standard_normal(n) > 0).astype(np.float32)
+    ds2 = capi.Dataset.from_csr(ip2, ix2, d2, F, DS_PARAMS).set_field("label", y2)
+    ods2 = O.OracleDataset(D2, DS_PARAMS).set_field("label", y2)
+    assert np.array_equal(ds2.get_bins(), ods2.bins())
     params = _params("binary", "is_unbalance=false")
-    b = capi.Booster(ds, params)
-    ob = O.OracleBooster(ods, params)
+    b = capi.Booster(ds2, params)
+    ob = O.OracleBooster(ods2, params)
     for _ in range(8):
         assert b.update_one_iter() == ob.update()
     compare_models(parse_model(b.save_model_to_string()), parse_model(ob.model_string()))
