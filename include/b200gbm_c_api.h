@@ -162,7 +162,8 @@ int B200GBM_HostFreePinned(void* ptr);
 int B200GBM_Memcpy(void* dst, const void* src, size_t bytes);   /* cudaMemcpyDefault + sync */
 /* LightGBM's LCG row sampler (the rows that define the bins) */
 int B200GBM_SampleIndices(int num_total_row, int sample_cnt, int seed, int* out, int* out_len);
-/* counter-based synthetic generators: kind 0 = regression, 1 = binary, 2 = graded relevance 0..4 (ranking).
+/* counter-based synthetic generators: kind 0 = regression, 1 = binary, 2 = graded relevance 0..4 (ranking),
+ * 3 = 10 classes with the last ncol/16 columns categorical (log-uniform ids, cardinality 10^3..10^5) and a 70 %-zero first quarter.
  * x(row, col) and label(row) are pure functions of (seed, row, col). */
 int B200GBM_SyntheticFill(void* dev_x_f32, void* dev_label_f32, int64_t row_start, int32_t nrow, int32_t ncol,
                           uint64_t seed, int kind);
@@ -170,6 +171,8 @@ int B200GBM_SyntheticRows(const int* rows, int32_t nrows, int32_t ncol, uint64_t
                           float* host_label_out);
 /* dataset introspection for the bit-exact bin parity tests */
 int B200GBM_DatasetGetBins(DatasetHandle handle, uint8_t* out_row_major);          /* [num_data][num_feature] */
+int B200GBM_DatasetGetBins16(DatasetHandle handle, uint16_t* out_row_major);       /* same, uint16: datasets with features of more than 256 bins */
+int B200GBM_DatasetGetBinToCat(DatasetHandle handle, int feature, int* out, int* out_len);   /* categorical feature: bin -> category value (out: >= num_bin ints) */
 /* bins of the selected rows only, gathered on the device: out [nrows][num_feature] uint16 (trivial features 0).  Lets a test or
  * bench.py check rows of a dataset far too large to download (the 100M x 512 benchmark matrix) against host-side binning. */
 int B200GBM_DatasetGetBinsRows(DatasetHandle handle, const int32_t* rows, int32_t nrows, uint16_t* out);

@@ -232,6 +232,16 @@ class Dataset:
         check(load().B200GBM_DatasetGetBins(self.handle, _ptr(out)))
         return out
 
+    def get_bins16(self):
+        out = np.zeros((self.num_data(), self.num_feature()), dtype=np.uint16)
+        check(load().B200GBM_DatasetGetBins16(self.handle, _ptr(out)))
+        return out
+
+    def bin_to_cat(self, f):
+        out = np.zeros(65536, dtype=np.int32); k = C.c_int(0)
+        check(load().B200GBM_DatasetGetBinToCat(self.handle, C.c_int(f), _ptr(out), C.byref(k)))
+        return out[:k.value].copy()
+
     def get_bins_rows(self, rows):
         """bins of the selected rows only (device gather): [len(rows)][num_feature] uint16"""
         rows = np.ascontiguousarray(rows, dtype=np.int32)

@@ -443,8 +443,21 @@ __device__ __forceinline__ float syn_u(unsigned long long seed, long long row, i
   unsigned long long h = syn_mix(seed ^ syn_mix(static_cast<unsigned long long>(row) * 0x100000001B3ULL + static_cast<unsigned long long>(col)));
   return static_cast<float>(h >> 40) * (1.0f / 16777216.0f);
 }
-__device__ __forceinline__ float syn_x(unsigned long long seed, long long row, int col) {
-  return syn_u(seed, row, col) * (1.0f + static_cast<float>(col % 7)) - static_cast<float>(col % 5);
+// kind 3 (BASELINE.json configs[4]): the last ncol/16 columns are categorical with a log-uniform (Zipf-like) id distribution and
+// cardinalities from 10^3 to 10^5; the first quarter of the columns is 70 % zeros; the rest is dense numeric like the other kinds
+__device__ __forceinline__ int syn_ncat(int ncol, int kind) { return kind == 3 ? max(ncol / 16, 1) : 0; }
+__device__ __forceinline__ float syn_x(unsigned long long seed, long long row, int col, int ncol, int kind) {
+  const float u = syn_u(seed, row, col);
+  if (kind == 3) {
+    const int ncat = syn_ncat(ncol, kind);
+    if (col >= ncol - ncat) {
+      const int j = col - (ncol - ncat);
+      const float log10c = 3.0f + (ncat > 1 ? 2.0f * j / (ncat - 1) : 0.0f);
+      return floorf(__powf(10.0f, u * log10c)) - 1.0f;                       // ids 0 .. 10^log10c - 1, P(id) ~ 1/(id+1)
+    }
+    if (col < ncol / 4 && syn_u(seed ^ 0x5151515151ULL, row, col) < 0.7f) return 0.0f;
+  }
+  return u * (1.0f + static_cast<float>(col % 7)) - static_cast<float>(col % 5);
 }
 __device__ float syn_label(unsigned long long seed, long long row, int ncol, int kind) {
   const int m = ncol < 16 ? ncol : 16;
@@ -454,6 +467,12 @@ __device__ float syn_label(unsigned long long seed, long long row, int ncol, int
   const float noise = syn_u(seed ^ 0xABCDEF12345ULL, row, 1 << 20) + syn_u(seed ^ 0xABCDEF12345ULL, row, (1 << 20) + 1) - 1.0f;
   if (kind == 0) return s + 0.1f * noise * 2.449f;
   if (kind == 2) return fminf(fmaxf(floorf(2.0f + 0.6f * s + 1.5f * noise), 0.0f), 4.0f);      // graded relevance 0..4 (lambdarank, BASELINE cfg4)
+  if (kind == 3) {                                                                              // 10 ordinal classes, shifted by the first categorical column
+    const int ncat = syn_ncat(ncol, kind);
+    const float c0 = syn_x(seed, row, ncol - ncat, ncol, kind);
+    const float shift = (static_cast<int>(c0) % 3) - 1.0f;
+    return fminf(fmaxf(floorf(5.0f + 0.7f * s + 1.2f * shift + 1.5f * noise), 0.0f), 9.0f);
+  }
   const float p = 1.0f / (1.0f + __expf(-s));
   return syn_u(seed ^ 0x55AA55AA55ULL, row, 1 << 21) < p ? 1.0f : 0.0f;
 }
@@ -462,7 +481,7 @@ __global__ void k_syn_fill(float* x, float* label, long long row_start, int nrow
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = e / ncol;
     const int c = static_cast<int>(e % ncol);
-    x[e] = syn_x(seed, row_start + r, c);
+    x[e] = syn_x(seed, row_start + r, c, ncol, kind);
     if (c == 0 && label) label[r] = syn_label(seed, row_start + r, ncol, kind);
   }
 }
@@ -470,7 +489,7 @@ __global__ void k_syn_rows(const int* rows, int nrows, int ncol, unsigned long l
   const long long total = static_cast<long long>(nrows) * ncol;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(e / ncol), c = static_cast<int>(e % ncol);
-    out[e] = static_cast<double>(syn_x(seed, rows[i], c));
+    out[e] = static_cast<double>(syn_x(seed, rows[i], c, ncol, kind));
     if (c == 0 && label) label[i] = syn_label(seed, rows[i], ncol, kind);
   }
 }
@@ -501,6 +520,19 @@ int B200GBM_DatasetGetBins(DatasetHandle handle, uint8_t* out_row_major) {
   API_BEGIN();
   EnsureDevice();
   DS(handle)->GetBinsRowMajor(out_row_major);
+  API_END();
+}
+int B200GBM_DatasetGetBins16(DatasetHandle handle, uint16_t* out_row_major) {
+  API_BEGIN();
+  EnsureDevice();
+  DS(handle)->GetBinsRowMajor16(out_row_major);
+  API_END();
+}
+int B200GBM_DatasetGetBinToCat(DatasetHandle handle, int feature, int* out, int* out_len) {
+  API_BEGIN();
+  const FeatureBins& fb = DS(handle)->mappers.at(feature);
+  for (size_t i = 0; i < fb.bin_to_cat.size(); ++i) out[i] = fb.bin_to_cat[i];
+  *out_len = static_cast<int>(fb.bin_to_cat.size());
   API_END();
 }
 int B200GBM_DatasetGetBinsRows(DatasetHandle handle, const int32_t* rows, int32_t nrows, uint16_t* out) {

@@ -202,11 +202,10 @@ static bool IsDevicePointer(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-constexpr int kMapperRecord = 10 + 256;
-static void PackMapper(const FeatureBins& fb, double* r) {
+static void PackMapper(const FeatureBins& fb, double* r, int slots) {
   r[0] = fb.num_bin; r[1] = fb.missing_type; r[2] = fb.trivial; r[3] = fb.default_bin; r[4] = fb.most_freq_bin;
   r[5] = fb.sparse_rate; r[6] = fb.min_val; r[7] = fb.max_val; r[8] = fb.categorical; r[9] = 0;
-  for (int i = 0; i < 256; ++i) {
+  for (int i = 0; i < slots; ++i) {
     if (fb.categorical) r[10 + i] = i < static_cast<int>(fb.bin_to_cat.size()) ? fb.bin_to_cat[i] : 0.0;
     else r[10 + i] = i < static_cast<int>(fb.upper.size()) ? fb.upper[i] : 0.0;
   }
@@ -296,12 +295,17 @@ void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sam
                                       cfg.zero_as_missing);
   }
   for (int f = f0; f < f1; ++f)
-    if (mappers[f].num_bin > 256)
+    if (mappers[f].num_bin > kWideMaxBins)
       Fatal("categorical feature " + std::to_string(f) + " needs " + std::to_string(mappers[f].num_bin) +
-            " bins to cover 99% of its mass; this build stores bins as uint8 (<= 256 bins per feature)");
-  if (world > 1) {   // C5: all-gather the serialized mappers
+            " bins to cover 99% of its mass; this build supports at most " + std::to_string(kWideMaxBins) + " bins per feature");
+  if (world > 1) {   // C5: all-gather the serialized mappers (record = 10 header doubles + the largest bin count of any rank)
+    double maxbins = 256;
+    for (int f = f0; f < f1; ++f) maxbins = std::max(maxbins, static_cast<double>(mappers[f].num_bin));
+    AllReduceHost(&maxbins, 1, ncclMax, stream);
+    const int slots = static_cast<int>(maxbins);
+    const size_t kMapperRecord = 10 + static_cast<size_t>(slots);
     std::vector<double> send(static_cast<size_t>(step) * kMapperRecord, 0.0), recv(static_cast<size_t>(world) * step * kMapperRecord);
-    for (int f = f0; f < f1; ++f) PackMapper(mappers[f], &send[static_cast<size_t>(f - f0) * kMapperRecord]);
+    for (int f = f0; f < f1; ++f) PackMapper(mappers[f], &send[static_cast<size_t>(f - f0) * kMapperRecord], slots);
     DevBuf<double> ds, dr; ds.Alloc(send.size()); dr.Alloc(recv.size());
     ds.Upload(send.data(), send.size(), stream);
     B200_NCCL(ncclAllGather(ds.p, dr.p, send.size(), ncclDouble, Net().comm, stream));
@@ -315,23 +319,47 @@ void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sam
 }
 
 void Dataset::UploadMeta() {
+  // inner order: features with <= 256 bins first (uint8 tiles of 32), then the wide ones (uint16 columns), each group in real-index order
   used.clear();
   inner_of.assign(num_total_features, -1);
-  for (int f = 0; f < num_total_features; ++f)
-    if (!mappers[f].trivial) { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
+  std::vector<int> wide_real;
+  for (int f = 0; f < num_total_features; ++f) {
+    if (mappers[f].trivial) continue;
+    if (mappers[f].num_bin > 256) { if (!mappers[f].categorical) Fatal("numerical features with more than 256 bins are not supported"); wide_real.push_back(f); }
+    else { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
+  }
+  nfn = static_cast<int>(used.size());
+  for (int f : wide_real) { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
   nf = static_cast<int>(used.size());
-  num_tiles = std::max(1, (nf + 31) / 32);
-  nf_pad = num_tiles * 32;
+  nw = nf - nfn;
+  sample_order.clear();
+  for (int f = 0; f < num_total_features; ++f) if (inner_of[f] >= 0) sample_order.push_back(inner_of[f]);
+  num_tiles = std::max(1, (nfn + 31) / 32);
+  nf_pad = num_tiles * 32 + nw;
   meta_host.assign(nf_pad, FeatMeta{1, 0, 0, 0, 0, 0, 0, 0});
-  std::vector<double> ubh(static_cast<size_t>(nf_pad) * 256, 0.0);
-  std::vector<uint8_t> cbh(static_cast<size_t>(nf_pad) * 256, 0);
+  std::vector<double> ubh(static_cast<size_t>(num_tiles) * 32 * 256, 0.0);
+  std::vector<uint8_t> cbh(static_cast<size_t>(num_tiles) * 32 * 256, 0);
   has_categorical = false;
+  hist_pairs = static_cast<size_t>(num_tiles) * 32 * 256;
+  wide_host.clear();
+  std::vector<int> wcats;
+  std::vector<unsigned short> wbins;
   for (int u = 0; u < nf; ++u) {
     const FeatureBins& fb = mappers[used[u]];
+    int hist_off = u * 256;
+    if (u >= nfn) {
+      hist_off = static_cast<int>(hist_pairs);
+      WideMeta wm{fb.num_bin, hist_off, static_cast<int>(wcats.size()), static_cast<int>(fb.sorted_cats.size()), static_cast<int>(fb.default_bin), fb.missing_type, used[u], 0};
+      wide_host.push_back(wm);
+      for (size_t i = 0; i < fb.sorted_cats.size(); ++i) { wcats.push_back(fb.sorted_cats[i]); wbins.push_back(static_cast<unsigned short>(fb.sorted_bins[i])); }
+      hist_pairs += (static_cast<size_t>(fb.num_bin) + 255) / 256 * 256;
+      if (hist_pairs > (1u << 30)) Fatal("histogram of the wide features is too large");
+    }
     meta_host[u] = FeatMeta{fb.num_bin, fb.missing_type, static_cast<int>(fb.default_bin), fb.most_freq_bin == 0 ? 1 : 0, used[u],
-                            fb.categorical ? 1 : 0, static_cast<int>(fb.sorted_cats.size()), 0};
+                            fb.categorical ? 1 : 0, static_cast<int>(fb.sorted_cats.size()), hist_off};
+    if (fb.categorical) has_categorical = true;
+    if (u >= nfn) continue;
     if (fb.categorical) {
-      has_categorical = true;
       for (size_t i = 0; i < fb.sorted_cats.size(); ++i) {
         ubh[static_cast<size_t>(u) * 256 + i] = fb.sorted_cats[i];
         cbh[static_cast<size_t>(u) * 256 + i] = static_cast<uint8_t>(fb.sorted_bins[i]);
@@ -344,7 +372,18 @@ void Dataset::UploadMeta() {
   meta.Upload(meta_host.data(), nf_pad, stream);
   ub.Upload(ubh.data(), ubh.size(), stream);
   catbin.Upload(cbh.data(), cbh.size(), stream);
+  if (nw > 0) {
+    wide_meta.Alloc(nw); wide_meta.Upload(wide_host.data(), nw, stream);
+    wide_cats.Alloc(std::max<size_t>(wcats.size(), 1)); wide_catbin.Alloc(std::max<size_t>(wbins.size(), 1));
+    if (!wcats.empty()) { wide_cats.Upload(wcats.data(), wcats.size(), stream); wide_catbin.Upload(wbins.data(), wbins.size(), stream); }
+  }
   B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+// bins (tiles + wide columns) of a freshly created dataset
+static void AllocBins(Dataset* d) {
+  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  if (d->nw > 0) d->bins16.Alloc(static_cast<size_t>(d->nw) * d->rows_stride);
 }
 
 template <typename T>
@@ -353,7 +392,9 @@ static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long 
   B200_CUDA(cudaFuncSetAttribute(k_bin_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   dim3 grid(static_cast<unsigned>(std::min<long long>((nrow + 7) / 8, 148 * 8)), d.num_tiles);
   if (grid.x == 0) grid.x = 1;
-  k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.catbin.p, d.nf, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
+  k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.catbin.p, d.nfn, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
+  if (d.nw > 0)
+    k_bin_wide<T><<<148 * 8, 256, 0, s>>>(X, nrow, row_major, ld, d.wide_meta.p, d.nw, d.wide_cats.p, d.wide_catbin.p, d.bins16.p, d.rows_stride, row_offset);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -434,7 +475,7 @@ Dataset* Dataset::CreateFromSampledColumn(double** sample_data, int** sample_ind
   for (int f = 0; f < ncol; ++f) d->feature_names[f] = "Column_" + std::to_string(f);
   d->UploadMeta();
   d->rows_stride = static_cast<size_t>(num_total_row);
-  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  AllocBins(d.get());
   return d.release();
 }
 
@@ -455,22 +496,42 @@ void Dataset::PushRows(const void* data, int data_type, int nrow, int ncol, int 
 }
 
 void Dataset::GetBinsRowMajor(uint8_t* out) const {
+  if (nw > 0) Fatal("this dataset has features with more than 256 bins: use B200GBM_DatasetGetBins16");
   std::vector<uint8_t> h(bins.n);
   B200_CUDA(cudaMemcpy(h.data(), bins.p, bins.n, cudaMemcpyDeviceToHost));
   std::memset(out, 0, static_cast<size_t>(num_data) * num_total_features);
-  for (int u = 0; u < nf; ++u) {
+  for (int u = 0; u < nfn; ++u) {
     const int f = used[u];
     const uint8_t* src = h.data() + (static_cast<size_t>(u >> 5) * rows_stride) * 32 + (u & 31);
     for (int i = 0; i < num_data; ++i) out[static_cast<size_t>(i) * num_total_features + f] = src[static_cast<size_t>(i) * 32];
   }
 }
+void Dataset::GetBinsRowMajor16(uint16_t* out) const {
+  std::vector<uint8_t> h(bins.n);
+  B200_CUDA(cudaMemcpy(h.data(), bins.p, bins.n, cudaMemcpyDeviceToHost));
+  std::memset(out, 0, static_cast<size_t>(num_data) * num_total_features * sizeof(uint16_t));
+  for (int u = 0; u < nfn; ++u) {
+    const int f = used[u];
+    const uint8_t* src = h.data() + (static_cast<size_t>(u >> 5) * rows_stride) * 32 + (u & 31);
+    for (int i = 0; i < num_data; ++i) out[static_cast<size_t>(i) * num_total_features + f] = src[static_cast<size_t>(i) * 32];
+  }
+  if (nw > 0) {
+    std::vector<uint16_t> hw(bins16.n);
+    B200_CUDA(cudaMemcpy(hw.data(), bins16.p, bins16.n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < nw; ++w) {
+      const int f = used[nfn + w];
+      const uint16_t* src = hw.data() + static_cast<size_t>(w) * rows_stride;
+      for (int i = 0; i < num_data; ++i) out[static_cast<size_t>(i) * num_total_features + f] = src[i];
+    }
+  }
+}
 
-__global__ void k_gather_bin_rows(const uint8_t* __restrict__ bins, size_t rows_stride, int nf, const FeatMeta* __restrict__ meta, const int* __restrict__ rows,
-                                  int nrows, int F, uint16_t* __restrict__ out) {
+__global__ void k_gather_bin_rows(BinView bv, int nf, const FeatMeta* __restrict__ meta, const int* __restrict__ rows, int nrows, int F,
+                                  uint16_t* __restrict__ out) {
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < static_cast<long long>(nrows) * nf;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(e / nf), u = static_cast<int>(e % nf);
-    out[static_cast<size_t>(i) * F + meta[u].real_index] = bins[(static_cast<size_t>(u >> 5) * rows_stride + rows[i]) * 32 + (u & 31)];
+    out[static_cast<size_t>(i) * F + meta[u].real_index] = static_cast<uint16_t>(bv.at(u, static_cast<size_t>(rows[i])));
   }
 }
 void Dataset::GetBinsOfRows(const int32_t* rows, int nrows, uint16_t* out) const {
@@ -480,7 +541,7 @@ void Dataset::GetBinsOfRows(const int32_t* rows, int nrows, uint16_t* out) const
   DevBuf<uint16_t> dout; dout.Alloc(static_cast<size_t>(nrows) * num_total_features);
   dr.Upload(rows, nrows, stream);
   dout.Zero(stream);
-  if (nf > 0) k_gather_bin_rows<<<148 * 4, 256, 0, stream>>>(bins.p, rows_stride, nf, meta.p, dr.p, nrows, num_total_features, dout.p);
+  if (nf > 0) k_gather_bin_rows<<<148 * 4, 256, 0, stream>>>(View(), nf, meta.p, dr.p, nrows, num_total_features, dout.p);
   B200_CUDA(cudaGetLastError());
   dout.Download(out, dout.n, stream);
   B200_CUDA(cudaStreamSynchronize(stream));
@@ -496,7 +557,7 @@ void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx
   DevBuf<TreeCtrl> ctrl; ctrl.Alloc(1); ctrl.Zero(stream);
   DevBuf<int> didx; didx.Alloc(std::max(cnt, 1));
   if (idx) didx.Upload(idx, cnt, stream);
-  const size_t elems = static_cast<size_t>(nf_pad) * 512;
+  const size_t elems = static_cast<size_t>(num_tiles) * 32 * 512;      // tile features only (wide features are covered by the model-level tests)
   DevBuf<long long> H; H.Alloc(elems); H.Zero(stream);
   DevBuf<double> D; D.Alloc(elems);
   int sms = 148;
@@ -516,7 +577,7 @@ void Dataset::Histogram(const float* grad, const float* hess, const int32_t* idx
   D.Download(hd.data(), elems, stream);
   B200_CUDA(cudaStreamSynchronize(stream));
   std::memset(out, 0, sizeof(double) * static_cast<size_t>(num_total_features) * 512);
-  for (int u = 0; u < nf; ++u) std::memcpy(out + static_cast<size_t>(used[u]) * 512, hd.data() + static_cast<size_t>(u) * 512, sizeof(double) * 512);
+  for (int u = 0; u < nfn; ++u) std::memcpy(out + static_cast<size_t>(used[u]) * 512, hd.data() + static_cast<size_t>(u) * 512, sizeof(double) * 512);
 }
 
 Dataset* Dataset::CreateFromMat(const void* data, int data_type, int nrow, int ncol, int is_row_major, const char* params,
@@ -544,7 +605,7 @@ Dataset* Dataset::CreateFromMat(const void* data, int data_type, int nrow, int n
   }
   d->UploadMeta();
   d->rows_stride = static_cast<size_t>(nrow);
-  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
+  AllocBins(d.get());
   d->BinBlock(data, on_device, data_type, is_row_major, nrow, 0);
   B200_CUDA(cudaEventRecord(e1, d->stream));
   B200_CUDA(cudaEventSynchronize(e1));
@@ -558,6 +619,12 @@ Dataset* Dataset::CreateFromMat(const void* data, int data_type, int nrow, int n
 // ---- CSR ingestion without densifying (replaces LGBM_DatasetCreateFromCSR, reference call site DatasetAggregator.scala:438-459).
 // Bin finding walks the nonzeros of the sampled rows only; binning fills every row of a tile with the features' zero bins and then
 // scatters one thread per stored element.  Memory: O(nnz) + the uint8 bins, never nrow x num_col doubles.
+__global__ void k_fill_default_wide(const WideMeta* __restrict__ wm, int nw, uint16_t* __restrict__ bins16, size_t rows_stride, long long nrow) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < nrow * nw; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(e / nrow);
+    bins16[static_cast<size_t>(w) * rows_stride + (e - static_cast<long long>(w) * nrow)] = static_cast<uint16_t>(wm[w].default_bin);
+  }
+}
 __global__ void k_fill_default_bins(const FeatMeta* __restrict__ meta, int nf, uint8_t* __restrict__ bins, size_t rows_stride, long long nrow, int num_tiles) {
   const long long total = nrow * num_tiles * 32;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -572,7 +639,8 @@ __global__ void k_fill_default_bins(const FeatMeta* __restrict__ meta, int nf, u
 template <typename TI, typename TV>
 __global__ void k_bin_csr(const TI* __restrict__ indptr, const int* __restrict__ indices, const TV* __restrict__ vals, long long nrow, const int* __restrict__ inner_of,
                           const FeatMeta* __restrict__ meta, const double* __restrict__ ub, const uint8_t* __restrict__ catbin, uint8_t* __restrict__ bins,
-                          size_t rows_stride, long long elem_base) {
+                          size_t rows_stride, long long elem_base, int nfn, const WideMeta* __restrict__ wm, const int* __restrict__ wcats,
+                          const unsigned short* __restrict__ wcatbin, uint16_t* __restrict__ bins16) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5, nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = warp; r < nrow; r += nwarps) {
@@ -582,6 +650,21 @@ __global__ void k_bin_csr(const TI* __restrict__ indptr, const int* __restrict__
       if (u < 0) continue;
       const FeatMeta m = meta[u];
       double v = static_cast<double>(vals[k]);
+      if (u >= nfn) {           // wide categorical column
+        const WideMeta w = wm[u - nfn];
+        unsigned wb = 0;
+        if (!isnan(v)) {
+          const int iv = static_cast<int>(v);
+          if (iv >= 0) {
+            const int* c = wcats + w.cat_off;
+            int lo = 0, hi = w.num_cats;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] < iv) lo = mid + 1; else hi = mid; }
+            if (lo < w.num_cats && c[lo] == iv) wb = wcatbin[w.cat_off + lo];
+          }
+        }
+        bins16[static_cast<size_t>(u - nfn) * rows_stride + r] = static_cast<uint16_t>(wb);
+        continue;
+      }
       const double* myub = ub + static_cast<size_t>(u) * 256;
       unsigned bin = 0;
       if (m.is_categorical) {
@@ -662,8 +745,9 @@ Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32
   }
   d->UploadMeta();
   d->rows_stride = static_cast<size_t>(nrow);
-  d->bins.Alloc(static_cast<size_t>(d->num_tiles) * d->rows_stride * 32);
-  k_fill_default_bins<<<148 * 8, 256, 0, d->stream>>>(d->meta.p, d->nf, d->bins.p, d->rows_stride, nrow, d->num_tiles);
+  AllocBins(d.get());
+  k_fill_default_bins<<<148 * 8, 256, 0, d->stream>>>(d->meta.p, d->nfn, d->bins.p, d->rows_stride, nrow, d->num_tiles);
+  if (d->nw > 0) k_fill_default_wide<<<148 * 8, 256, 0, d->stream>>>(d->wide_meta.p, d->nw, d->bins16.p, d->rows_stride, nrow);
   B200_CUDA(cudaGetLastError());
   if (d->nf > 0) {
     DevBuf<int> d_inner; d_inner.Alloc(F); d_inner.Upload(d->inner_of.data(), F, d->stream);
@@ -690,7 +774,8 @@ Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32
 #define B200_CSR_LAUNCH(TI, TV)                                                                                                              \
         k_bin_csr<TI, TV><<<grid, 256, 0, d->stream>>>(reinterpret_cast<const TI*>(d_ip.p), reinterpret_cast<const int*>(d_ix.p),               \
                                                       reinterpret_cast<const TV*>(d_v.p), nr, d_inner.p, d->meta.p, d->ub.p, d->catbin.p, base,  \
-                                                      d->rows_stride, e0k)
+                                                      d->rows_stride, e0k, d->nfn, d->wide_meta.p, d->wide_cats.p, d->wide_catbin.p,               \
+                                                      d->bins16.p ? d->bins16.p + r0 : nullptr)
         if (indptr_type == 2 && data_type == 0) B200_CSR_LAUNCH(int32_t, float);
         else if (indptr_type == 2) B200_CSR_LAUNCH(int32_t, double);
         else if (data_type == 0) B200_CSR_LAUNCH(int64_t, float);
@@ -917,18 +1002,25 @@ void Booster::InitTraining() {
   sp_.l1 = cfg.lambda_l1; sp_.l2 = cfg.lambda_l2; sp_.max_delta_step = cfg.max_delta_step;
   sp_.min_gain_to_split = cfg.min_gain_to_split; sp_.min_sum_hessian = cfg.min_sum_hessian_in_leaf;
   sp_.min_data_in_leaf = cfg.min_data_in_leaf; sp_.max_depth = cfg.max_depth; sp_.num_leaves = L; sp_.parallel = parallel_ ? 1 : 0;
-  sp_.nf = train->nf; sp_.nf_pad = train->nf_pad; sp_.num_tiles = train->num_tiles; sp_.pad = 0;
+  sp_.nf = train->nf; sp_.nf_pad = train->nf_pad; sp_.num_tiles = train->num_tiles; sp_.nfn = train->nfn;
   {   // categorical split search parameters: native defaults unless given
     auto gd = [&](const char* k, double d) { auto it = cfg.raw.find(k); return (it != cfg.raw.end() && !it->second.empty()) ? std::atof(it->second.c_str()) : d; };
     sp_.cat_l2 = gd("cat_l2", 10.0); sp_.cat_smooth = gd("cat_smooth", 10.0);
     sp_.max_cat_threshold = static_cast<int>(gd("max_cat_threshold", 32)); sp_.max_cat_to_onehot = static_cast<int>(gd("max_cat_to_onehot", 4));
     sp_.min_data_per_group = static_cast<int>(gd("min_data_per_group", 100)); sp_.pad3 = 0;
+    if (train->nw > 0) {
+      if (sp_.max_cat_threshold > kCatListMax) Fatal("max_cat_threshold > " + std::to_string(kCatListMax) + " is not supported together with categorical features of more than 256 bins");
+      if (sp_.max_cat_to_onehot > 256) Fatal("max_cat_to_onehot > 256 is not supported together with categorical features of more than 256 bins");
+      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideMaxBins * 4));
+      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideMaxBins * 4));
+      B200_CUDA(cudaFuncSetAttribute(k_scan_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideMaxBins * 10));
+    }
   }
 
   score_.Alloc(static_cast<size_t>(K) * n); score_.Zero(stream_);
   grad_.Alloc(static_cast<size_t>(K) * n); hess_.Alloc(static_cast<size_t>(K) * n);
   qgh_.Alloc(n); qord_.Alloc(n); idx0_.Alloc(n); idx1_.Alloc(n);
-  slot_elems_ = static_cast<size_t>(train->nf_pad) * 512;
+  slot_elems_ = train->hist_pairs * 2;
   H_.Alloc(slot_elems_); H_.Zero(stream_); pool_.Alloc(slot_elems_ * L);
   {
     int per_sm = 0;
@@ -950,6 +1042,7 @@ void Booster::InitTraining() {
     size_t o_lc = take(4 * (L - 1)), o_rc = take(4 * (L - 1)), o_sf = take(4 * (L - 1)), o_tb = take(4 * (L - 1)), o_dt = take(4 * (L - 1));
     size_t o_sg = take(4 * (L - 1)), o_lv = take(8 * L), o_lw = take(8 * L), o_lcn = take(4 * L), o_iv = take(8 * (L - 1)), o_iw = take(8 * (L - 1));
     size_t o_ic = take(4 * (L - 1)), o_lp = take(4 * L), o_ld = take(4 * L), o_nl = take(16), o_cb = take(32 * (L - 1));
+    size_t o_cl = take(2 * kCatListMax * (L - 1)), o_cn = take(4 * (L - 1));
     tree_blob_bytes_ = off;
     tree_blob_.Alloc(off);
     unsigned char* b = tree_blob_.p;
@@ -962,6 +1055,9 @@ void Booster::InitTraining() {
     tree_dev_.leaf_parent = reinterpret_cast<int*>(b + o_lp); tree_dev_.leaf_depth = reinterpret_cast<int*>(b + o_ld);
     tree_dev_.num_leaves = reinterpret_cast<int*>(b + o_nl);
     tree_dev_.cat_bits = reinterpret_cast<unsigned*>(b + o_cb);
+    tree_dev_.cat_list = reinterpret_cast<unsigned short*>(b + o_cl);
+    tree_dev_.cat_list_len = reinterpret_cast<int*>(b + o_cn);
+    B200_CUDA(cudaMemsetAsync(b, 0, off, stream_));
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&tree_host_), off));
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctrl_host_), sizeof(TreeCtrl)));
     B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&leaves_host_), sizeof(LeafState) * L));
@@ -1140,7 +1236,7 @@ TreeDev Booster::RebasedTree(unsigned char* base) const {
   auto mv = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(base + (reinterpret_cast<unsigned char*>(p) - tree_blob_.p)); };
   mv(t.left_child); mv(t.right_child); mv(t.split_feature_inner); mv(t.threshold_bin); mv(t.decision_type); mv(t.split_gain);
   mv(t.leaf_value); mv(t.leaf_weight); mv(t.leaf_count); mv(t.internal_value); mv(t.internal_weight); mv(t.internal_count);
-  mv(t.leaf_parent); mv(t.leaf_depth); mv(t.num_leaves); mv(t.cat_bits);
+  mv(t.leaf_parent); mv(t.leaf_depth); mv(t.num_leaves); mv(t.cat_bits); mv(t.cat_list); mv(t.cat_list_len);
   return t;
 }
 // ScoreUpdater::AddScore(models_[tree], class): the tree's CURRENT host leaf values (after the Shrinkage calls) are pushed into
@@ -1162,10 +1258,10 @@ void Booster::AddStoredTree(int iter_index, int k, bool to_train, bool to_valid)
   TreeDev td = RebasedTree(blob.p);
   B200_CUDA(cudaMemcpyAsync(td.leaf_value, ht.leaf_value.data(), sizeof(double) * ht.num_leaves, cudaMemcpyHostToDevice, s));
   const int egrid = num_sms_ * 8;
-  if (to_train) k_add_tree_binned<<<egrid, 256, 0, s>>>(td, train->meta.p, train->bins.p, train->rows_stride, n, score_.p + static_cast<size_t>(k) * n, 1.0);
+  if (to_train) k_add_tree_binned<<<egrid, 256, 0, s>>>(td, train->meta.p, train->View(), n, score_.p + static_cast<size_t>(k) * n, 1.0);
   if (to_valid)
     for (auto* vs : valids_)
-      k_add_tree_binned<<<egrid, 256, 0, s>>>(td, vs->ds->meta.p, vs->ds->bins.p, vs->ds->rows_stride, vs->ds->num_data,
+      k_add_tree_binned<<<egrid, 256, 0, s>>>(td, vs->ds->meta.p, vs->ds->View(), vs->ds->num_data,
                                               vs->score.p + static_cast<size_t>(k) * vs->ds->num_data, 1.0);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaStreamSynchronize(s));        // the pageable host leaf values must stay put until the copy is done
@@ -1326,7 +1422,7 @@ void Booster::ResetFeaturesByTree() {
   const int total = train->nf;
   int cnt = std::max(static_cast<int>(total * cfg.feature_fraction + 0.5), std::min(2, total));
   std::fill(feature_used_host_.begin(), feature_used_host_.end(), 0);
-  for (int i : col_rand_.Sample(total, cnt)) feature_used_host_[i] = 1;
+  for (int i : col_rand_.Sample(total, cnt)) feature_used_host_[train->sample_order[i]] = 1;      // the draw indexes the used features in real-index order
   B200_CUDA(cudaStreamSynchronize(stream_));      // the previous tree must not still be reading the mask
   feature_used_.Upload(feature_used_host_.data(), train->nf_pad, stream_);
 }
@@ -1478,7 +1574,8 @@ void Booster::LaunchPartition(int grid, int last) {
   int4* qord = qord_.p;
   long long* H = H_.p;
   size_t h_elems = slot_elems_;
-  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems};
+  const uint16_t* bins16 = d.bins16.p;
+  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16};
   B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_partition), dim3(grid), dim3(256), args, 0, stream_));
 }
 
@@ -1505,7 +1602,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, use_bag_ ? bag_count_ : n, feature_used_.p, use_bag_ ? 1 : 0);
   timing.launches += 4;
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, part_max_blocks_));
-  const dim3 sgrid((d.nf + 7) / 8, 2);
+  const dim3 sgrid(std::max(1, (d.nfn + 7) / 8), 2);      // tile features; the pick step in its last block also sees the wide features' candidates
   std::vector<cudaEvent_t> evs;
   // B200GBM_SPLIT_TIMING=1 (debug): an event after every operation of a split; per-operation averages go to stderr when the booster is freed
   static const bool split_timing = getenv("B200GBM_SPLIT_TIMING") != nullptr;
@@ -1527,6 +1624,16 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     else
       k4_hist_build_ws<4><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
+    if (d.nw > 0) {      // the features with more than 256 bins: own sub-histogram layout (k4_hist_wide)
+      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 2 * num_sms_ / d.nw))), static_cast<unsigned>(d.nw));
+      if (const_hessian_)
+        k4_hist_wide<3><<<wgrid, kWideThreads, 4 * kWideMaxBins * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                         reinterpret_cast<unsigned long long*>(H_.p));
+      else
+        k4_hist_wide<4><<<wgrid, kWideThreads, 4 * kWideMaxBins * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+                                                                         reinterpret_cast<unsigned long long*>(H_.p));
+      timing.launches += 1;
+    }
     if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
     mark();
     if (fused_) {
@@ -1539,6 +1646,10 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     } else {
       if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
       mark();
+      if (d.nw > 0) {
+        k_scan_wide<<<dim3(d.nw, 2), 256, kWideMaxBins * 10, s>>>(ctrl, leaves_.p, d.wide_meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
+        timing.launches += 1;
+      }
       // scan + (last block) pick; the dynamic scratch is only touched by categorical features
       k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
     }
@@ -1552,11 +1663,11 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   const double bias = is_rf_ ? rf_init_scores_[k] : 0.0, pre = is_rf_ ? static_cast<double>(iter + num_init_iteration) : 1.0;
   const double post = is_rf_ ? 1.0 / (iter + num_init_iteration + 1) : 1.0;
   if (use_bag_ || is_rf_)      // out-of-bag rows are scored by walking the tree on the binned data, so walk it for every row
-    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, d.meta.p, d.bins.p, d.rows_stride, n, score_.p + static_cast<size_t>(k) * n, shrinkage_, bias, pre, post);
+    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, d.meta.p, d.View(), n, score_.p + static_cast<size_t>(k) * n, shrinkage_, bias, pre, post);
   else
     k_add_score<<<egrid, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, idx0_.p, idx1_.p, score_.p + static_cast<size_t>(k) * n, shrinkage_);
   for (auto* v : valids_)
-    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, v->ds->meta.p, v->ds->bins.p, v->ds->rows_stride, v->ds->num_data,
+    k_add_tree_binned<<<egrid, 256, 0, s>>>(tree_dev_, v->ds->meta.p, v->ds->View(), v->ds->num_data,
                                             v->score.p + static_cast<size_t>(k) * v->ds->num_data, shrinkage_, bias, pre, post);
   timing.launches += 2 + static_cast<long long>(valids_.size());
   B200_CUDA(cudaGetLastError());
@@ -1601,6 +1712,8 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     const int* ic = reinterpret_cast<const int*>(at(tree_dev_.internal_count));
     const int* ld = reinterpret_cast<const int*>(at(tree_dev_.leaf_depth));
     const unsigned* cb = reinterpret_cast<const unsigned*>(at(tree_dev_.cat_bits));
+    const unsigned short* cl = reinterpret_cast<const unsigned short*>(at(tree_dev_.cat_list));
+    const int* cln = reinterpret_cast<const int*>(at(tree_dev_.cat_list_len));
     for (int i = 0; i < nl - 1; ++i) {
       out->left_child[i] = lc[i]; out->right_child[i] = rc[i]; out->split_feature_inner[i] = sf[i];
       out->split_feature[i] = d.used[sf[i]]; out->threshold_in_bin[i] = static_cast<uint32_t>(tb[i]);
@@ -1608,7 +1721,8 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       const FeatureBins& fbm = d.mappers[d.used[sf[i]]];
       if (dt[i] & 1) {          // categorical node: bins of the inner bitset -> category values ([UPSTREAM] RealThreshold per bin)
         std::vector<int> cats;
-        for (int b = 0; b < fbm.num_bin; ++b) if ((cb[i * 8 + (b >> 5)] >> (b & 31)) & 1u) cats.push_back(fbm.bin_to_cat[b]);
+        if (sf[i] >= d.nfn) { for (int k = 0; k < cln[i]; ++k) cats.push_back(fbm.bin_to_cat[cl[i * kCatListMax + k]]); }
+        else for (int b = 0; b < fbm.num_bin; ++b) if ((cb[i * 8 + (b >> 5)] >> (b & 31)) & 1u) cats.push_back(fbm.bin_to_cat[b]);
         out->AddCategoricalNode(i, cats);
       } else {
         double thr = fbm.upper[tb[i]];

@@ -80,7 +80,8 @@ class Dataset {
   static Dataset* CreateFromSampledColumn(double** sample_data, int** sample_indices, int ncol, const int* num_per_col,
                                           int num_sample_row, int num_total_row, const char* params);
   void PushRows(const void* data, int data_type, int nrow, int ncol, int start_row);
-  void GetBinsRowMajor(uint8_t* out) const;
+  void GetBinsRowMajor(uint8_t* out) const;                 // fails when a feature has more than 256 bins
+  void GetBinsRowMajor16(uint16_t* out) const;
   void GetBinsOfRows(const int32_t* rows, int nrows, uint16_t* out) const;      // [nrows][num_total_features], gathered on the device
   // K4 on this dataset's bins for the given rows (kernel-level parity entry), fp64 [F][256][2]
   void Histogram(const float* grad, const float* hess, const int32_t* idx, int cnt, double* out) const;
@@ -96,8 +97,17 @@ class Dataset {
   std::vector<int> inner_of;                 // real -> inner or -1
   std::vector<FeatMeta> meta_host;
   int nf = 0, nf_pad = 0, num_tiles = 0;
+  int nfn = 0, nw = 0;                       // inner features [0, nfn) live in uint8 tiles, [nfn, nf) are wide (> 256 bins, uint16 columns)
+  size_t hist_pairs = 0;                     // (g,h) pairs of one histogram slot: num_tiles*32*256 for the tiles + the wide features' bins
+  std::vector<int> sample_order;             // used features in real-index order -> inner index (ColSampler draws in that order)
   size_t rows_stride = 0;
   DevBuf<uint8_t> bins;                      // [num_tiles][rows_stride][32]
+  DevBuf<uint16_t> bins16;                   // [nw][rows_stride]
+  std::vector<WideMeta> wide_host;
+  DevBuf<WideMeta> wide_meta;
+  DevBuf<int> wide_cats;                     // sorted category values of all wide features (slices per WideMeta)
+  DevBuf<unsigned short> wide_catbin;        // ... and their bins
+  BinView View() const { return BinView{bins.p, rows_stride, bins16.p, nfn}; }
   DevBuf<FeatMeta> meta;
   DevBuf<double> ub;                         // [nf][256] bin upper bounds (categorical: sorted category values)
   DevBuf<uint8_t> catbin;                    // [nf][256] categorical: bin of the i-th sorted category

@@ -19,13 +19,30 @@ struct FeatMeta {          // per inner (used) feature
   int real_index;
   int is_categorical;      // bins are category ranks; splits are bin bitsets
   int num_sorted_cats;     // categorical: entries of the sorted category table (ub row = categories, catbin row = their bins)
-  int pad2;
+  int hist_off;            // first (g,h) pair of the feature in a histogram slot: u * 256 for a tile feature, beyond the tiles for a wide one
+};
+
+// "Wide" features: more than 256 bins.  LightGBM does not cap a categorical feature at max_bin — it keeps categories until 99 % of the
+// sampled mass is covered (BinMapper::FindBin) — so a 10^3..10^5-cardinality column (BASELINE.json configs[4]) needs thousands of bins.
+// They live outside the uint8 feature tiles: one uint16 column per feature, their own histogram kernel (k4_hist_wide) and scan
+// (k_scan_wide); inner index = nfn + w.  A categorical split on one sends at most max_cat_threshold bins left, carried as a bin list.
+constexpr int kWideMaxBins = 8192;       // 4 planes x 8192 x 4 B = 128 KB of shared memory per CTA
+constexpr int kCatListMax = 64;          // >= max_cat_threshold (default 32) when wide features exist
+struct WideMeta {
+  int num_bin, hist_off, cat_off, num_cats;      // hist_off in (g,h) pairs; cat_off/num_cats: slice of the sorted category table
+  int default_bin, missing_type, real_index, pad;
+};
+struct BinView {                         // where a row's bin of inner feature u is stored
+  const uint8_t* bins; size_t rows_stride; const uint16_t* bins16; int nfn;
+  __device__ __forceinline__ unsigned at(int u, size_t row) const {
+    return u < nfn ? bins[(static_cast<size_t>(u >> 5) * rows_stride + row) * 32 + (u & 31)] : bins16[static_cast<size_t>(u - nfn) * rows_stride + row];
+  }
 };
 
 struct SplitParams {
   double l1, l2, max_delta_step, min_gain_to_split, min_sum_hessian;
   int min_data_in_leaf, max_depth, num_leaves, parallel;
-  int nf, nf_pad, num_tiles, pad;
+  int nf, nf_pad, num_tiles, nfn;                              // nfn: features stored in uint8 tiles; [nfn, nf) are wide
   double cat_l2, cat_smooth;                                   // categorical split search ([UPSTREAM] defaults 10, 10)
   int max_cat_threshold, max_cat_to_onehot, min_data_per_group, pad3;   // 32, 4, 100
 };
@@ -36,7 +53,8 @@ struct SplitCand {         // best threshold of one (leaf, feature)
   int threshold, left_count, default_left, feature;   // feature = inner index
   double l2_extra;         // cat_l2 for a many-vs-many categorical split (leaf outputs use lambda_l2 + l2_extra)
   unsigned cat_bits[8];    // categorical: bins that go LEFT
-  int is_cat, pad;
+  int is_cat, cat_list_len;
+  unsigned short cat_list[kCatListMax];      // wide categorical feature: the bins that go LEFT (cat_bits unused)
 };
 
 struct LeafBest {
@@ -45,6 +63,8 @@ struct LeafBest {
   double left_out, right_out;
   int feature, threshold, default_left, left_count, right_count, is_cat;
   unsigned cat_bits[8];
+  int cat_list_len, pad;
+  unsigned short cat_list[kCatListMax];
 };
 
 struct LeafState {
@@ -69,6 +89,9 @@ struct TreeCtrl {
   int q_side;                  // (unused since the fused partition kernel decides the side itself)
   unsigned part_barrier;       // k_partition: grid-barrier arrive counter (reset by its last block)
   unsigned part_ticket;        // k_partition: finished-block ticket (the last block runs the next round's controller)
+  int split_wide;              // wide index (inner feature - nfn) of the split feature, or -1
+  int split_cat_list_len;
+  unsigned short split_cat_list[kCatListMax];
 };
 
 struct TreeDev {               // SoA tree under construction (sizes: num_leaves / num_leaves-1)
@@ -76,6 +99,8 @@ struct TreeDev {               // SoA tree under construction (sizes: num_leaves
   float* split_gain; double* leaf_value; double* leaf_weight; int* leaf_count; double* internal_value;
   double* internal_weight; int* internal_count; int* leaf_parent; int* leaf_depth; int* num_leaves;
   unsigned* cat_bits;          // [num_leaves-1][8] inner (bin) bitset of categorical nodes
+  unsigned short* cat_list;    // [num_leaves-1][kCatListMax] bins going left at a categorical node on a wide feature
+  int* cat_list_len;           // [num_leaves-1] 0 for every other node
 };
 
 // ---------------------------------------------------------------- helpers
@@ -479,6 +504,8 @@ d_round_ctl(TreeCtrl* ctrl, LeafState* leaves, const TreeDev& tree, uint8_t* fla
         tree.threshold_bin[node] = b.threshold;
       }
       for (int wd = 0; wd < 8; ++wd) tree.cat_bits[node * 8 + wd] = b.is_cat ? b.cat_bits[wd] : 0u;
+      tree.cat_list_len[node] = b.is_cat ? b.cat_list_len : 0;
+      if (b.is_cat) for (int k = 0; k < b.cat_list_len && k < kCatListMax; ++k) tree.cat_list[node * kCatListMax + k] = b.cat_list[k];
       ctrl->num_leaves += 1; *tree.num_leaves = ctrl->num_leaves;
       // data partition bookkeeping: children live in the other index buffer
       const int dst_buf = L.identity ? 0 : (L.buf ^ 1);
@@ -816,6 +843,9 @@ __device__ __forceinline__ void d_choose_leaf(TreeCtrl* ctrl, LeafState* leaves,
     ctrl->split_missing_type = fm.missing_type; ctrl->split_num_bin = fm.num_bin;
     ctrl->split_is_cat = b.is_cat;
     for (int wd = 0; wd < 8; ++wd) ctrl->split_cat_bits[wd] = b.cat_bits[wd];
+    ctrl->split_wide = b.feature >= p.nfn ? b.feature - p.nfn : -1;
+    ctrl->split_cat_list_len = b.cat_list_len;
+    for (int k = 0; k < b.cat_list_len && k < kCatListMax; ++k) ctrl->split_cat_list[k] = b.cat_list[k];
     ctrl->part_begin = L.begin; ctrl->part_count = L.count; ctrl->part_buf = L.buf; ctrl->part_identity = L.identity;
     ctrl->part_left_total = 0;
   }
@@ -861,10 +891,12 @@ d_pick_block(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ met
         LeafState& L = leaves[leaf];
         LeafBest b;
         b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
+        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0; b.cat_list_len = 0; b.pad = 0;
         for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
         if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
           const SplitCand c = d_load_cand(&cands[which * p.nf_pad + s_idx[0]]);
+          b.cat_list_len = c.cat_list_len;
+          for (int k = 0; k < c.cat_list_len && k < kCatListMax; ++k) b.cat_list[k] = c.cat_list[k];
           const double sum_h = L.sum_h + 2 * kEpsD;
           b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
           b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
@@ -902,7 +934,7 @@ k_scan(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta,
   const int leaf = which ? ctrl->larger : ctrl->smaller;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u = blockIdx.x * 8 + warp;
-  if (ctrl->go && leaf >= 0 && u < p.nf) d_scan_one(ctrl, leaves, meta, H, pool, slot_elems, flags, cands, p, which, leaf, u, lane, warp);
+  if (ctrl->go && leaf >= 0 && u < p.nfn) d_scan_one(ctrl, leaves, meta, H, pool, slot_elems, flags, cands, p, which, leaf, u, lane, warp);
   // the block that finishes last picks the best candidate per leaf and the next leaf to split (was a separate kernel)
   __shared__ int s_last;
   __syncthreads();
@@ -924,7 +956,7 @@ d_scan_one(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta,
            size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* cands, const SplitParams& p, int which, int leaf, int u, int lane, int warp) {
   SplitCand out;
   out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
-  out.l2_extra = 0; out.is_cat = 0; out.pad = 0;
+  out.l2_extra = 0; out.is_cat = 0; out.cat_list_len = 0;
   for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
   uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
   if (!*flag) { if (lane == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); } return; }
@@ -1007,7 +1039,7 @@ k_scan_dp(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leave
   if (u >= pt.feat1 || u >= p.nf) return;
   SplitCand out;
   out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
-  out.l2_extra = 0; out.is_cat = 0; out.pad = 0;
+  out.l2_extra = 0; out.is_cat = 0; out.cat_list_len = 0;
   for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
   uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
   if (!*flag) { if (lane == 0) cands[which * p.nf_pad + u] = out; return; }
@@ -1126,7 +1158,7 @@ k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, 
       LeafState& L = leaves[leaf];
       LeafBest b;
       b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-      b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0;
+      b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0; b.cat_list_len = 0; b.pad = 0;
       for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
       if (best.feature >= 0 && best.gain > kNegInf) {
         const double sum_h = L.sum_h + 2 * kEpsD;
@@ -1178,8 +1210,10 @@ __device__ __forceinline__ void d_grid_barrier(unsigned* counter, unsigned targe
 __global__ void __launch_bounds__(256)
 k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p, int last,
             const uint8_t* __restrict__ bins, size_t rows_stride, int* __restrict__ idx0, int* __restrict__ idx1, unsigned* __restrict__ bits,
-            int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems) {
+            int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems,
+            const uint16_t* __restrict__ bins16) {
   __shared__ int s_pref[kPartLocalScan + 1];
+  __shared__ unsigned short s_list[kCatListMax];
   __shared__ int s_wl[64];
   __shared__ int s_cnt[8];
   __shared__ int s_copy[2];
@@ -1198,7 +1232,13 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     int* dst = ctrl->part_identity ? idx0 : (ctrl->part_buf ? idx0 : idx1);
     const int begin = ctrl->part_begin, identity = ctrl->part_identity;
     const int f = ctrl->split_feature;
-    const uint8_t* col = bins + (static_cast<size_t>(f >> 5) * rows_stride) * 32 + (f & 31);
+    const int wide = ctrl->split_wide;
+    const uint8_t* col = bins + (static_cast<size_t>((wide >= 0 ? 0 : f) >> 5) * rows_stride) * 32 + ((wide >= 0 ? 0 : f) & 31);
+    const uint16_t* wcol = wide >= 0 ? bins16 + static_cast<size_t>(wide) * rows_stride : nullptr;
+    const bool wide_cat = wide >= 0 && ctrl->split_is_cat;
+    const int list_len = wide_cat ? ctrl->split_cat_list_len : 0;
+    if (threadIdx.x < list_len) s_list[threadIdx.x] = ctrl->split_cat_list[threadIdx.x];
+    __syncthreads();
     const int chunks = (n + kPartChunk - 1) / kPartChunk;
     // ---- phase 1
     for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
@@ -1209,7 +1249,9 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
         bool left = false;
         if (i < n) {
           const int r = identity ? (begin + i) : src[begin + i];
-          left = d_goes_left(col[static_cast<size_t>(r) * 32], ctrl);
+          const unsigned bin = wide >= 0 ? static_cast<unsigned>(wcol[r]) : static_cast<unsigned>(col[static_cast<size_t>(r) * 32]);
+          if (wide_cat) { for (int k = 0; k < list_len; ++k) left |= (bin == s_list[k]); }
+          else left = d_goes_left(bin, ctrl);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, left);
         if (lane == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
@@ -1324,6 +1366,191 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
   }
 }
 
+// ---------------------------------------------------------------- wide features (> 256 bins): binning, histogram, categorical scan
+// value -> bin of the wide columns of a row block (categorical lookup: binary search in the feature's sorted category table)
+template <typename T>
+__global__ void k_bin_wide(const T* __restrict__ X, long long nrow, int row_major, long long ld, const WideMeta* __restrict__ wm, int nw,
+                           const int* __restrict__ cats, const unsigned short* __restrict__ catbin, uint16_t* __restrict__ bins16, size_t rows_stride,
+                           long long row_offset) {
+  const long long total = nrow * nw;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(e / nrow);
+    const long long r = e - static_cast<long long>(w) * nrow;
+    const WideMeta m = wm[w];
+    const double v = row_major ? static_cast<double>(X[r * ld + m.real_index]) : static_cast<double>(X[static_cast<long long>(m.real_index) * ld + r]);
+    unsigned bin = 0;
+    if (!isnan(v)) {
+      const int iv = static_cast<int>(v);
+      if (iv >= 0) {
+        const int* c = cats + m.cat_off;
+        int lo = 0, hi = m.num_cats;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] < iv) lo = mid + 1; else hi = mid; }
+        if (lo < m.num_cats && c[lo] == iv) bin = catbin[m.cat_off + lo];
+      }
+    }
+    bins16[static_cast<size_t>(w) * rows_stride + row_offset + r] = static_cast<uint16_t>(bin);
+  }
+}
+
+// K4 for wide features.  One CTA = (wide feature, row range of the leaf): the sub-histogram is [NATOM planes][num_bin] in shared memory
+// with the same fixed-point fields as the tile kernel; lanes read consecutive rows of the uint16 column (or gather through the leaf's
+// index list), so the atomics of a warp fall on data-dependent banks — these features are a few percent of a wide table's columns and
+// run at a fraction of the tile kernel's rate, which is acceptable.  Flush every 2^14 rows (field headroom) into the int64 histogram.
+constexpr int kWideThreads = 512;
+template <int NATOM>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const WideMeta* __restrict__ wm, const int4* __restrict__ qgh,
+             const int4* __restrict__ qord, const int* __restrict__ idx0, const int* __restrict__ idx1, const HistWork* __restrict__ work,
+             unsigned long long* __restrict__ hist) {
+  extern __shared__ __align__(16) unsigned wplane[];        // [NATOM][nb_pad]
+  const HistWork w = *work;
+  const int n = w.count;
+  if (n <= 0) return;
+  const int active = min(static_cast<int>(gridDim.x), (n + 4095) / 4096);
+  if (static_cast<int>(blockIdx.x) >= active) return;
+  const WideMeta m = wm[blockIdx.y];
+  const int nb = m.num_bin;
+  const int p0 = static_cast<int>(static_cast<long long>(n) * blockIdx.x / active), p1 = static_cast<int>(static_cast<long long>(n) * (blockIdx.x + 1) / active);
+  const int* __restrict__ idx = w.buf ? idx1 : idx0;
+  const uint16_t* __restrict__ col = bins16 + static_cast<size_t>(blockIdx.y) * rows_stride;
+  unsigned* pl0 = wplane; unsigned* pl1 = wplane + kWideMaxBins; unsigned* pl2 = wplane + 2 * kWideMaxBins; unsigned* pl3 = wplane + 3 * kWideMaxBins;
+  for (int e = threadIdx.x; e < nb; e += kWideThreads) { pl0[e] = 0u; pl1[e] = 0u; pl2[e] = 0u; if (NATOM == 4) pl3[e] = 0u; }
+  __syncthreads();
+  for (int c0 = p0; c0 < p1; c0 += kFlushRows) {
+    const int c1 = min(c0 + kFlushRows, p1);
+    for (int p = c0 + threadIdx.x; p < c1; p += kWideThreads) {
+      int4 q; unsigned b;
+      if (w.use_idx) { const int r = idx[w.begin + p]; b = col[r]; q = qord[w.begin + p]; }
+      else { const size_t r = static_cast<size_t>(w.begin + p); b = col[r]; q = qgh[r]; }
+      atomicAdd(&pl0[b], static_cast<unsigned>(q.x));
+      atomicAdd(&pl1[b], static_cast<unsigned>(q.y));
+      atomicAdd(&pl2[b], static_cast<unsigned>(q.z));
+      if (NATOM == 4) atomicAdd(&pl3[b], static_cast<unsigned>(q.w));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb; e += kWideThreads) {
+      const unsigned ghi = pl0[e], glo = pl1[e], hhi = pl2[e], hlo = (NATOM == 4) ? pl3[e] : 0u;
+      if (ghi | glo | hhi | hlo) {
+        const long long g = (static_cast<long long>(static_cast<int>(ghi)) << kLoBits) + static_cast<long long>(glo);
+        const long long h = (NATOM == 4) ? (static_cast<long long>(static_cast<int>(hhi)) << kLoBits) + static_cast<long long>(hlo) : static_cast<long long>(hhi);
+        const size_t o = (static_cast<size_t>(m.hist_off) + e) * 2;
+        if (g) atomicAdd(&hist[o], static_cast<unsigned long long>(g));
+        if (h) atomicAdd(&hist[o + 1], static_cast<unsigned long long>(h));
+        pl0[e] = 0u; pl1[e] = 0u; pl2[e] = 0u; if (NATOM == 4) pl3[e] = 0u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Split search of a WIDE categorical feature (FeatureHistogram::FindBestThresholdCategoricalInner, many-vs-many branch): one block per
+// (smaller|larger, feature).  The histogram is reduced into the leaf's pool slot (parent - smaller for the larger child), the bins that
+// hold >= cat_smooth rows are sorted by g / (h + cat_smooth) with a block-wide bitonic sort over (ctr, bin) keys — the stable order of
+// the reference — and thread 0 accumulates from both ends exactly like the sequential code (at most max_cat_threshold bins each).
+__global__ void __launch_bounds__(256)
+k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const WideMeta* __restrict__ wm, const long long* __restrict__ H,
+            long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* __restrict__ cands, SplitParams p) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  double* s_key = reinterpret_cast<double*>(sw_smem);                          // [P]
+  unsigned short* s_id = reinterpret_cast<unsigned short*>(s_key + kWideMaxBins);   // [P]
+  __shared__ int s_used;
+  const int which = blockIdx.y, w = blockIdx.x, u = p.nfn + w;
+  const int leaf = which ? ctrl->larger : ctrl->smaller;
+  if (!ctrl->go || leaf < 0) return;
+  SplitCand out;
+  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 0; out.feature = u;
+  out.l2_extra = 0; out.is_cat = 1; out.cat_list_len = 0;
+  for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
+  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
+  if (!*flag) { if (threadIdx.x == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); } return; }
+  const WideMeta m = wm[w];
+  const LeafState& L = leaves[leaf];
+  const double inv_g = ctrl->inv_g, inv_h = ctrl->inv_h;
+  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(m.hist_off) * 2;
+  const long long* src = H + static_cast<size_t>(m.hist_off) * 2;
+  const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
+  const int num_data = L.global_count;
+  const double cnt_factor = num_data / sum_h;
+  int P = 1;
+  while (P < m.num_bin) P <<= 1;
+  if (threadIdx.x == 0) s_used = 0;
+  __syncthreads();
+  int my_used = 0;
+  for (int b = threadIdx.x; b < P; b += blockDim.x) {
+    double key = __longlong_as_double(0x7ff0000000000000LL);      // +inf: unused bins and padding sort last
+    if (b < m.num_bin) {
+      longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
+      if (which) { const longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2); s.x = pr.x - s.x; s.y = pr.y - s.y; }
+      *reinterpret_cast<longlong2*>(dst + b * 2) = s;
+      const double g = static_cast<double>(s.x) * inv_g, h = static_cast<double>(s.y) * inv_h;
+      const int cnt = static_cast<int>(h * cnt_factor + 0.5);
+      if (b >= 1 && cnt >= p.cat_smooth) { key = g / (h + p.cat_smooth); ++my_used; }
+    }
+    s_key[b] = key; s_id[b] = static_cast<unsigned short>(b);
+  }
+  if (my_used) atomicAdd(&s_used, my_used);
+  __syncthreads();
+  // bitonic sort ascending by (key, bin)
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const double a = s_key[i], c = s_key[ixj];
+          const unsigned short ia = s_id[i], ic = s_id[ixj];
+          const bool a_gt_c = (a > c) || (a == c && ia > ic);
+          const bool up = (i & k) == 0;
+          if (up ? a_gt_c : !a_gt_c) { s_key[i] = c; s_key[ixj] = a; s_id[i] = ic; s_id[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x != 0) return;
+  const int used_bin = s_used;
+  SplitParams pshift = p;
+  if (!(p.max_delta_step > 0)) pshift.max_delta_step = 0;
+  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, pshift) + p.min_gain_to_split;
+  SplitParams pc = p;
+  pc.l2 += p.cat_l2;
+  const int max_num_cat = min(p.max_cat_threshold, (used_bin + 1) / 2);
+  bool any_valid = false;
+  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
+  int best_i = -1, best_dir = 1, best_lc = 0;
+  for (int d = 0; d < 2; ++d) {
+    const int dir = d == 0 ? 1 : -1;
+    int pos = d == 0 ? 0 : used_bin - 1;
+    int cnt_cur_group = 0, left_count = 0;
+    double slg = 0.0, slh = kEpsD;
+    for (int i = 0; i < used_bin && i < max_num_cat; ++i) {
+      const int t = s_id[pos];
+      pos += dir;
+      const double g = static_cast<double>(dst[t * 2]) * inv_g, h = static_cast<double>(dst[t * 2 + 1]) * inv_h;
+      const int cnt = static_cast<int>(h * cnt_factor + 0.5);
+      slg += g; slh += h; left_count += cnt; cnt_cur_group += cnt;
+      if (left_count < p.min_data_in_leaf || slh < p.min_sum_hessian) continue;
+      const int right_count = num_data - left_count;
+      if (right_count < p.min_data_in_leaf || right_count < p.min_data_per_group) break;
+      const double srh = sum_h - slh;
+      if (srh < p.min_sum_hessian) break;
+      if (cnt_cur_group < p.min_data_per_group) continue;
+      cnt_cur_group = 0;
+      const double gain = d_leaf_gain(slg, slh, pc) + d_leaf_gain(sum_g - slg, srh, pc);
+      if (gain <= min_gain_shift) continue;
+      any_valid = true;
+      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_lc = left_count; best_i = i; best_dir = dir; }
+    }
+  }
+  *flag = any_valid ? 1 : 0;
+  if (any_valid) {
+    out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = 0; out.left_count = best_lc;
+    out.default_left = 0; out.is_cat = 1; out.l2_extra = p.cat_l2;
+    out.cat_list_len = best_i + 1;
+    for (int i = 0; i <= best_i && i < kCatListMax; ++i) out.cat_list[i] = best_dir == 1 ? s_id[i] : s_id[used_bin - 1 - i];
+  }
+  cands[which * p.nf_pad + u] = out;
+  __threadfence();
+}
+
 // ---------------------------------------------------------------- K8/K9 leaf values -> scores
 // score[row] += shrinkage * leaf_value[leaf(row)], via the final data partition
 __global__ void __launch_bounds__(256)
@@ -1347,7 +1574,7 @@ __global__ void k_add_const(double* __restrict__ score, int n, double v) {
 }
 // score of a (validation) dataset += shrinkage * tree(row), traversing by bin thresholds
 __global__ void __launch_bounds__(256)
-k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t* __restrict__ bins, size_t rows_stride, int n,
+k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, BinView bv, int n,
                   double* __restrict__ score, double shrinkage, double bias = 0.0, double pre_mul = 1.0, double post_mul = 1.0) {
   const int nl = *tree.num_leaves;
   if (nl <= 1) return;
@@ -1355,10 +1582,18 @@ k_add_tree_binned(TreeDev tree, const FeatMeta* __restrict__ meta, const uint8_t
     int node = 0;
     while (node >= 0) {
       const int f = tree.split_feature_inner[node];
-      const unsigned bin = bins[(static_cast<size_t>(f >> 5) * rows_stride + i) * 32 + (f & 31)];
+      const unsigned bin = bv.at(f, static_cast<size_t>(i));
       const int dt = tree.decision_type[node];
       bool left;
-      if (dt & 1) left = (tree.cat_bits[node * 8 + (bin >> 5)] >> (bin & 31u)) & 1u;
+      if (dt & 1) {
+        if (f >= bv.nfn) {      // wide feature: short list of bins
+          left = false;
+          const int len = tree.cat_list_len[node];
+          for (int k = 0; k < len; ++k) left |= (bin == tree.cat_list[node * kCatListMax + k]);
+        } else {
+          left = (tree.cat_bits[node * 8 + (bin >> 5)] >> (bin & 31u)) & 1u;
+        }
+      }
       else if (((dt >> 2) & 3) == 2 && bin == static_cast<unsigned>(meta[f].num_bin - 1)) left = dt & 2;
       else left = bin <= static_cast<unsigned>(tree.threshold_bin[node]);
       node = left ? tree.left_child[node] : tree.right_child[node];

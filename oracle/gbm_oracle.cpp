@@ -478,7 +478,16 @@ struct Dataset {
   std::vector<BinMapper> mappers;         // [F]
   std::vector<int> used;                  // inner -> real feature index
   std::vector<int> inner_of;              // real -> inner (-1 if trivial)
-  std::vector<uint8_t> bins;              // col-major [n_used][n]
+  std::vector<uint8_t> bins;              // col-major [n_used][n]  (all features <= 256 bins)
+  std::vector<uint16_t> bins16;           // col-major [n_used][n]  (used instead of `bins` when some feature needs more than 256 bins:
+                                          //  categorical features are not capped at max_bin — they keep categories until 99 % of the mass)
+  bool wide = false;
+  inline uint32_t bin_at(size_t u, size_t i) const { return wide ? bins16[u * static_cast<size_t>(n) + i] : bins[u * static_cast<size_t>(n) + i]; }
+  void alloc_bins() {
+    wide = false;
+    for (int f : used) if (mappers[f].num_bin > 256) wide = true;
+    if (wide) bins16.resize(used.size() * static_cast<size_t>(n)); else bins.resize(used.size() * static_cast<size_t>(n));
+  }
   std::vector<float> label, weight;
   std::vector<double> init_score;
   std::vector<int> query_boundaries;      // ngroup+1
@@ -525,12 +534,12 @@ struct Dataset {
     }
     inner_of.assign(F, -1);
     for (int f = 0; f < F; ++f) if (!mappers[f].is_trivial) { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
-    bins.resize(used.size() * static_cast<size_t>(n));
+    alloc_bins();
 #pragma omp parallel for schedule(static)
     for (int u = 0; u < static_cast<int>(used.size()); ++u) {
       int f = used[u];
-      uint8_t* col = &bins[static_cast<size_t>(u) * n];
-      for (int i = 0; i < n; ++i) col[i] = static_cast<uint8_t>(mappers[f].ValueToBin(X[static_cast<size_t>(i) * F + f]));
+      if (wide) { uint16_t* col = &bins16[static_cast<size_t>(u) * n]; for (int i = 0; i < n; ++i) col[i] = static_cast<uint16_t>(mappers[f].ValueToBin(X[static_cast<size_t>(i) * F + f])); }
+      else { uint8_t* col = &bins[static_cast<size_t>(u) * n]; for (int i = 0; i < n; ++i) col[i] = static_cast<uint8_t>(mappers[f].ValueToBin(X[static_cast<size_t>(i) * F + f])); }
     }
     feature_names.resize(F);
     for (int f = 0; f < F; ++f) feature_names[f] = "Column_" + std::to_string(f);
@@ -1475,7 +1484,8 @@ struct TreeLearner {
   std::vector<int> idx, tmp_left, tmp_right;          // data partition
   std::vector<int> leaf_begin, leaf_cnt;
   std::vector<int> global_cnt;                         // counts used for decisions
-  std::vector<std::vector<double>> pool;               // per-leaf hist [nf][256][2]
+  std::vector<std::vector<double>> pool;               // per-leaf hist: feature u at hoff[u], max(256, num_bin) (g,h) pairs
+  std::vector<size_t> hoff;                            // [nf+1] offsets in doubles
   std::vector<std::vector<uint8_t>> splittable;        // per-leaf per-feature flag
   std::vector<SplitInfo> best;
   std::vector<double> leaf_sum_g, leaf_sum_h;
@@ -1490,6 +1500,8 @@ struct TreeLearner {
   void Init(const Dataset* d, const Config& c, bool par) {
     ds = d; cfg = c; parallel = par;
     nf = static_cast<int>(d->used.size());
+    hoff.assign(nf + 1, 0);
+    for (int u = 0; u < nf; ++u) hoff[u + 1] = hoff[u] + 2 * static_cast<size_t>(std::max(256, d->mappers[d->used[u]].num_bin));
     sc = {c.lambda_l1, c.lambda_l2, c.max_delta_step, c.min_gain_to_split, c.min_sum_hessian_in_leaf, c.min_data_in_leaf};
     sc.max_cat_threshold = c.max_cat_threshold; sc.max_cat_to_onehot = c.max_cat_to_onehot; sc.min_data_per_group = c.min_data_per_group;
     sc.cat_l2 = c.cat_l2; sc.cat_smooth = c.cat_smooth;
@@ -1520,7 +1532,7 @@ struct TreeLearner {
   }
   void BuildHist(int leaf, const float* g, const float* h, std::vector<double>& out, const std::vector<uint8_t>& use) {
     double t0 = now();
-    out.assign(static_cast<size_t>(nf) * 512, 0.0);
+    out.assign(hoff[nf], 0.0);
     const int b = leaf_begin[leaf], cnt = leaf_cnt[leaf];
     const int* rows = idx.data() + b;
     const bool root = (cnt == ds->n) && rows[0] == 0 && rows[cnt - 1] == cnt - 1;
@@ -1534,7 +1546,13 @@ struct TreeLearner {
 #pragma omp parallel for schedule(dynamic, 1)
     for (int u = 0; u < nf; ++u) {
       if (!use[u]) continue;
-      double* o = &out[static_cast<size_t>(u) * 512];
+      double* o = &out[hoff[u]];
+      if (ds->wide) {
+        const uint16_t* col = &ds->bins16[static_cast<size_t>(u) * n];
+        if (root) { for (int i = 0; i < cnt; ++i) { int ti = col[i] << 1; o[ti] += gg[i]; o[ti + 1] += hh[i]; } }
+        else { for (int i = 0; i < cnt; ++i) { int ti = col[rows[i]] << 1; o[ti] += gg[i]; o[ti + 1] += hh[i]; } }
+        continue;
+      }
       const uint8_t* col = &ds->bins[static_cast<size_t>(u) * n];
       if (root) {
         for (int i = 0; i < cnt; ++i) { int ti = col[i] << 1; o[ti] += gg[i]; o[ti + 1] += hh[i]; }
@@ -1555,8 +1573,8 @@ struct TreeLearner {
       const BinMapper& bm = ds->mappers[ds->used[u]];
       ScanMeta m{bm.num_bin, bm.missing_type, static_cast<int>(bm.default_bin), bm.most_freq_bin == 0 ? 1 : 0};
       bool ok = false;
-      if (bm.is_categorical) FindBestThresholdCategorical(&hist[static_cast<size_t>(u) * 512], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
-      else FindBestThresholdNumerical(&hist[static_cast<size_t>(u) * 512], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
+      if (bm.is_categorical) FindBestThresholdCategorical(&hist[hoff[u]], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
+      else FindBestThresholdNumerical(&hist[hoff[u]], m, sc, leaf_sum_g[leaf], leaf_sum_h[leaf], num_data, &cand[u], &ok);
       cand[u].feature = ds->used[u];
       flag[u] = ok ? 1 : 0;
     }
@@ -1618,7 +1636,7 @@ struct TreeLearner {
 #pragma omp parallel for schedule(static)
           for (int u = 0; u < nf; ++u) {
             if (!splittable[larger][u]) continue;
-            for (int k = 0; k < 512; ++k) ph[static_cast<size_t>(u) * 512 + k] -= shist[static_cast<size_t>(u) * 512 + k];
+            for (size_t k = hoff[u]; k < hoff[u + 1]; ++k) ph[k] -= shist[k];
           }
           FindForLeaf(larger, ph, global_cnt[larger]);
         }
@@ -1631,14 +1649,13 @@ struct TreeLearner {
       // Split
       const int inner = ds->inner_of[bs.feature];
       const BinMapper& bm = ds->mappers[bs.feature];
-      const uint8_t* col = &ds->bins[static_cast<size_t>(inner) * n];
       int b0 = leaf_begin[best_leaf], c0 = leaf_cnt[best_leaf];
       int nl = 0, nr = 0;
       std::vector<uint32_t> bits_inner;
       if (bm.is_categorical) { std::vector<int> v(bs.cat_threshold.begin(), bs.cat_threshold.end()); bits_inner = ConstructBitset(v); }
       for (int i = 0; i < c0; ++i) {
         int r = idx[b0 + i];
-        uint32_t bin = col[r];
+        uint32_t bin = ds->bin_at(static_cast<size_t>(inner), static_cast<size_t>(r));
         bool left;
         if (bm.is_categorical) left = FindInBitset(bits_inner.data(), static_cast<int>(bits_inner.size()), static_cast<int>(bin));
         else if (bm.missing_type == kMissNaN && bin == static_cast<uint32_t>(bm.num_bin - 1)) left = bs.default_left;
@@ -1826,7 +1843,7 @@ struct Booster {
     if (t.num_leaves <= 1) { if (t.leaf_value[0] != 0.0) for (int i = 0; i < n; ++i) sp[i] += t.leaf_value[0]; return; }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
-      int leaf = t.LeafByBins([&](int f) { return static_cast<uint32_t>(ds->bins[static_cast<size_t>(f) * n + i]); }, nan_bin_of_inner);
+      int leaf = t.LeafByBins([&](int f) { return ds->bin_at(static_cast<size_t>(f), static_cast<size_t>(i)); }, nan_bin_of_inner);
       sp[i] += t.leaf_value[leaf];
     }
   }
@@ -1904,7 +1921,7 @@ struct Booster {
     }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
-      int leaf = t.LeafByBins([&](int f) { return static_cast<uint32_t>(ds->bins[static_cast<size_t>(f) * n + i]); }, nan_bin_of_inner);
+      int leaf = t.LeafByBins([&](int f) { return ds->bin_at(static_cast<size_t>(f), static_cast<size_t>(i)); }, nan_bin_of_inner);
       sp[i] += t.leaf_value[leaf];
     }
   }
@@ -2055,7 +2072,7 @@ void* orc_dataset_create_from_bins(const uint8_t* bins_rm, int n, int F, const i
   }
   d->inner_of.assign(F, -1);
   for (int f = 0; f < F; ++f) if (!d->mappers[f].is_trivial) { d->inner_of[f] = static_cast<int>(d->used.size()); d->used.push_back(f); }
-  d->bins.resize(d->used.size() * static_cast<size_t>(n));
+  d->alloc_bins();
 #pragma omp parallel for schedule(static)
   for (int u = 0; u < static_cast<int>(d->used.size()); ++u) {
     const int f = d->used[u];
@@ -2068,15 +2085,28 @@ void* orc_dataset_create_from_bins(const uint8_t* bins_rm, int n, int F, const i
 }
 
 int orc_dataset_num_used(void* h) { return static_cast<int>(static_cast<Dataset*>(h)->used.size()); }
-// bins out: row-major uint8 [n][F]; trivial features are written as 0
+// bins out: row-major uint8 [n][F]; trivial features are written as 0 (bins above 255 are truncated: use orc_dataset_bins16 for wide datasets)
 void orc_dataset_bins(void* h, uint8_t* out) {
   Dataset* d = static_cast<Dataset*>(h);
   std::memset(out, 0, static_cast<size_t>(d->n) * d->F);
   for (size_t u = 0; u < d->used.size(); ++u) {
     int f = d->used[u];
-    const uint8_t* col = &d->bins[u * static_cast<size_t>(d->n)];
-    for (int i = 0; i < d->n; ++i) out[static_cast<size_t>(i) * d->F + f] = col[i];
+    for (int i = 0; i < d->n; ++i) out[static_cast<size_t>(i) * d->F + f] = static_cast<uint8_t>(d->bin_at(u, i));
   }
+}
+void orc_dataset_bins16(void* h, uint16_t* out) {
+  Dataset* d = static_cast<Dataset*>(h);
+  std::memset(out, 0, static_cast<size_t>(d->n) * d->F * sizeof(uint16_t));
+  for (size_t u = 0; u < d->used.size(); ++u) {
+    int f = d->used[u];
+    for (int i = 0; i < d->n; ++i) out[static_cast<size_t>(i) * d->F + f] = static_cast<uint16_t>(d->bin_at(u, i));
+  }
+}
+// categorical feature: bin -> category value (bin 0 = -1); returns num_bin
+int orc_dataset_bin_to_cat(void* h, int f, int* out) {
+  const BinMapper& m = static_cast<Dataset*>(h)->mappers[f];
+  for (size_t i = 0; i < m.bin_2_cat.size(); ++i) out[i] = m.bin_2_cat[i];
+  return static_cast<int>(m.bin_2_cat.size());
 }
 // info: {num_bin, missing_type, default_bin, most_freq_bin, is_trivial}
 void orc_dataset_feature_info(void* h, int f, int* info) {

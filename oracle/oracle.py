@@ -53,6 +53,8 @@ def lib():
         L.orc_dataset_free.argtypes = [C.c_void_p]
         L.orc_dataset_num_used.argtypes = [C.c_void_p]
         L.orc_dataset_bins.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_dataset_bins16.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_dataset_bin_to_cat.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_dataset_feature_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_dataset_upper_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_dataset_set_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
@@ -134,6 +136,16 @@ class OracleDataset:
         out = np.zeros((self.n, self.F), dtype=np.uint8)
         lib().orc_dataset_bins(self.h, _p(out))
         return out
+
+    def bins16(self):
+        out = np.zeros((self.n, self.F), dtype=np.uint16)
+        lib().orc_dataset_bins16(self.h, _p(out))
+        return out
+
+    def bin_to_cat(self, f):
+        out = np.zeros(65536, dtype=np.int32)
+        k = lib().orc_dataset_bin_to_cat(self.h, f, _p(out))
+        return out[:k].copy()
 
     def feature_info(self, f):
         info = np.zeros(5, dtype=np.int32)

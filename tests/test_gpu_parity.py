@@ -242,8 +242,10 @@ def test_lambdarank(built):
     ds, ods = _make(X, rel, group=sizes)
     params = _classifier_params("lambdarank", "max_position=20 eval_at=1,2,3,4,5", leaves=15).replace("boost_from_average=true", "")
     b, ob, m, om = _train_both(ds, ods, params, 10)
-    # per-document lambdas are fp32 sums whose order differs on the GPU => gains/values to 1e-4, structure identical
-    compare_models(m, om, value_tol=1e-4, gain_tol=1e-4)
+    # per-document lambdas are accumulated by one thread per document in the reference's own pair order (same fp32 additions), so the
+    # general 1e-5 bar holds (round 1 needed 1e-4 with shared-memory float atomics)
+    compare_models(m, om)
+    np.testing.assert_allclose(b.get_scores(), ob.scores(), rtol=1e-7, atol=1e-9)
 
 
 def test_custom_objective_and_init_score(built):
