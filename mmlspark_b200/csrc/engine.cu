@@ -4,6 +4,8 @@
 #include "renew_kernel.cuh"
 #include "metric_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
+
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/in.h>
@@ -23,6 +25,12 @@
 #include <thread>
 
 namespace b200gbm {
+
+// NVTX ranges named after the kernel / collective numbering of SURVEY.md §2.5 (K1..K9, C1..C5): `nsys`/`ncu --nvtx` can filter on them
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // =============================================================================== device / network
 static thread_local int t_device = -1;
@@ -278,6 +286,7 @@ void Dataset::FindBins(const void* data, bool on_device, int data_type, int is_r
 
 // nz[f] = sampled values of feature f with |v| > 1e-35 or NaN (only this rank's slice needs filling)
 void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sample_cnt) {
+  NvtxRange nvtx("b200gbm:find bins (host) + C5 mapper all-gather");
   std::vector<std::vector<double>>& nz = *nzp;
   const int n = num_data, F = num_total_features;
   const int filter_cnt = static_cast<int>(static_cast<double>(cfg.min_data_in_leaf) * sample_cnt / n);
@@ -399,6 +408,7 @@ static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long 
 }
 
 void Dataset::BinBlock(const void* data, bool on_device, int data_type, int is_row_major, long long n, long long start_row) {
+  NvtxRange nvtx("b200gbm:K0 bin rows (H2D + value->bin)");
   const int F = num_total_features;
   const size_t esz = data_type == 0 ? 4 : 8;
   if (start_row < 0 || start_row + n > num_data) Fatal("row block out of range");
@@ -1011,8 +1021,8 @@ void Booster::InitTraining() {
     if (train->nw > 0) {
       if (sp_.max_cat_threshold > kCatListMax) Fatal("max_cat_threshold > " + std::to_string(kCatListMax) + " is not supported together with categorical features of more than 256 bins");
       if (sp_.max_cat_to_onehot > 256) Fatal("max_cat_to_onehot > 256 is not supported together with categorical features of more than 256 bins");
-      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideMaxBins * 4));
-      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideMaxBins * 4));
+      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideHistSeg * 4));
+      B200_CUDA(cudaFuncSetAttribute(k4_hist_wide<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kWideHistSeg * 4));
       B200_CUDA(cudaFuncSetAttribute(k_scan_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideMaxBins * 10));
     }
   }
@@ -1034,7 +1044,7 @@ void Booster::InitTraining() {
   cands_.Alloc(2 * static_cast<size_t>(train->nf_pad));
   leaves_.Alloc(L); ctrl_.Alloc(1); ctrl_.Zero(stream_);
   const int chunks = n / kPartChunk + 2;
-  part_bits_.Alloc(static_cast<size_t>(chunks) * (kPartChunk / 32)); part_chunks_.Alloc(chunks);
+  part_bits_.Alloc(static_cast<size_t>(chunks) * (kPartChunk / 32)); part_chunks_.Alloc(chunks); part_chunks_.Zero(stream_);
   // SoA tree blob
   {
     size_t off = 0;
@@ -1490,6 +1500,7 @@ double Booster::BoostFromAverage(int k) {
 
 void Booster::ComputeGradients() { ComputeGradientsAt(score_.p); }
 void Booster::ComputeGradientsAt(const double* score_p) {
+  NvtxRange nvtx("b200gbm:K1/K2 gradients");
   const int n = train->num_data;
   const int grid = num_sms_ * 8;
   const float* w = train->weight.empty() ? nullptr : train->d_weight.p;
@@ -1582,6 +1593,7 @@ void Booster::LaunchPartition(int grid, int last) {
 // One tree: the whole leaf-wise growth is enqueued without a host sync; leaf choice, smaller/larger
 // selection, partition sizes all live in TreeCtrl / LeafState on the device.
 void Booster::TrainOneTree(int k, HostTree* out) {
+  NvtxRange nvtx_tree("b200gbm:tree");
   const Dataset& d = *train;
   const int n = d.num_data;
   const int L = cfg.num_leaves;
@@ -1590,6 +1602,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   TreeCtrl* ctrl = ctrl_.p;
   cudaStream_t s = stream_;
   const int egrid = num_sms_ * 8;
+  nvtxRangePushA("b200gbm:K3 quantize + C1 root sums");
   B200_CUDA(cudaMemsetAsync(&ctrl->absmax_bits[0], 0, 8, s));
   k_absmax<<<egrid, 256, 0, s>>>(g, h, n, ctrl);
   if (parallel_) B200_NCCL(ncclAllReduce(&ctrl->absmax_bits[0], &ctrl->absmax_bits[0], 2, ncclUint32, ncclMax, Net().comm, s));
@@ -1600,6 +1613,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   if (use_bag_)      // the root leaf is the ascending in-bag row list (SetBaggingData); partitions then ping-pong idx0/idx1 as usual
     B200_CUDA(cudaMemcpyAsync(idx0_.p, bag_idx_.p, static_cast<size_t>(bag_count_) * sizeof(int), cudaMemcpyDeviceToDevice, s));
   k_tree_init<<<1, 256, 0, s>>>(ctrl, leaves_.p, tree_dev_, flags_.p, sp_, use_bag_ ? bag_count_ : n, feature_used_.p, use_bag_ ? 1 : 0);
+  nvtxRangePop();
   timing.launches += 4;
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, part_max_blocks_));
   const dim3 sgrid(std::max(1, (d.nfn + 7) / 8), 2);      // tile features; the pick step in its last block also sees the wide features' candidates
@@ -1618,6 +1632,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     if (split == 0 && use_bag_) k_gather_q<<<egrid, 256, 0, s>>>(&ctrl->hist_work, idx0_.p, idx1_.p, qgh_.p, qord_.p);
     mark();
     // the scratch histogram H is zero here: zeroed at set-up and by every partition kernel after the scan consumed it
+    nvtxRangePushA("b200gbm:K4 histogram");
     if (const_hessian_)
       k4_hist_build_ws<3><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
@@ -1625,17 +1640,22 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k4_hist_build_ws<4><<<num_sms_, kWsThreads, kWsSmemBytes, s>>>(d.bins.p, d.rows_stride, d.num_tiles, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                      reinterpret_cast<unsigned long long*>(H_.p));
     if (d.nw > 0) {      // the features with more than 256 bins: own sub-histogram layout (k4_hist_wide)
-      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 2 * num_sms_ / d.nw))), static_cast<unsigned>(d.nw));
+      int max_nb = 0;
+      for (const WideMeta& wm : d.wide_host) max_nb = std::max(max_nb, wm.num_bin);
+      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 2 * num_sms_ / d.nw))), static_cast<unsigned>(d.nw),
+                       static_cast<unsigned>((max_nb + kWideHistSeg - 1) / kWideHistSeg));      // z: 8192-bin segments of the largest feature
       if (const_hessian_)
-        k4_hist_wide<3><<<wgrid, kWideThreads, 4 * kWideMaxBins * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+        k4_hist_wide<3><<<wgrid, kWideThreads, 4 * kWideHistSeg * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                          reinterpret_cast<unsigned long long*>(H_.p));
       else
-        k4_hist_wide<4><<<wgrid, kWideThreads, 4 * kWideMaxBins * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
+        k4_hist_wide<4><<<wgrid, kWideThreads, 4 * kWideHistSeg * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                          reinterpret_cast<unsigned long long*>(H_.p));
       timing.launches += 1;
     }
+    nvtxRangePop();
     if (profile_hist) B200_CUDA(cudaEventRecord(evs.back(), s));
     mark();
+    nvtxRangePushA(parallel_ ? "b200gbm:C2 histogram reduce + K5 scan + pick" : "b200gbm:K5 scan + pick");
     if (fused_) {
       // C2+K5+C3 fused over NVLink peer memory: signal "histogram ready", then the scan reduces its owned slice from all peers
       ++epoch_;
@@ -1653,8 +1673,11 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       // scan + (last block) pick; the dynamic scratch is only touched by categorical features
       k_scan<<<sgrid, 256, d.has_categorical ? kScanSmem : 0, s>>>(ctrl, leaves_.p, d.meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
     }
+    nvtxRangePop();
     mark();
+    nvtxRangePushA("b200gbm:K7 partition + controller");
     LaunchPartition(pgrid, split == L - 2 ? 1 : 0);
+    nvtxRangePop();
     mark();
     timing.launches += fused_ ? 4 : 3; timing.hist_launches += 1;
   }
@@ -1738,6 +1761,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
 }
 
 bool Booster::TrainTrees(const float* custom_g, const float* custom_h) {
+  NvtxRange nvtx("b200gbm:iteration (LGBM_BoosterUpdateOneIter)");
   if (!train) Fatal("this booster was loaded from a model string and cannot be trained");
   EnsureDevice();
   cudaStream_t s = stream_;
@@ -1860,13 +1884,25 @@ std::string Booster::DumpModelJson(int start_iteration, int num_iteration) const
   auto num = [&](double v) { snprintf(buf, sizeof(buf), "%.17g", v); return std::string(buf); };
   for (int t = t0; t < t1; ++t) {
     const HostTree& tr = *model.trees[t];
-    s << (t > t0 ? "," : "") << "{\"tree_index\":" << (t - t0) << ",\"num_leaves\":" << tr.num_leaves << ",\"num_cat\":0,\"shrinkage\":" << num(tr.shrinkage)
+    s << (t > t0 ? "," : "") << "{\"tree_index\":" << (t - t0) << ",\"num_leaves\":" << tr.num_leaves << ",\"num_cat\":" << (tr.cat_boundaries.empty() ? 0 : static_cast<int>(tr.cat_boundaries.size()) - 1)
+      << ",\"shrinkage\":" << num(tr.shrinkage)
       << ",\"tree_structure\":";
     struct Rec { static void node(std::ostringstream& o, const HostTree& tr, int idx, const std::function<std::string(double)>& num) {
       if (idx >= 0) {
         int mt = (tr.decision_type[idx] >> 2) & 3;
+        const bool is_cat = (tr.decision_type[idx] & 1) != 0;
+        std::string thr = num(tr.threshold[idx]);
+        if (is_cat) {       // [UPSTREAM Tree::NodeToJSON]: the categories that go left, joined by "||"
+          const int ci = static_cast<int>(tr.threshold[idx]);
+          thr = "\"";
+          bool first = true;
+          for (int wd = tr.cat_boundaries[ci]; wd < tr.cat_boundaries[ci + 1]; ++wd)
+            for (int bit = 0; bit < 32; ++bit)
+              if ((tr.cat_threshold[wd] >> bit) & 1u) { thr += (first ? "" : "||") + std::to_string((wd - tr.cat_boundaries[ci]) * 32 + bit); first = false; }
+          thr += "\"";
+        }
         o << "{\"split_index\":" << idx << ",\"split_feature\":" << tr.split_feature[idx] << ",\"split_gain\":" << num(tr.split_gain[idx])
-          << ",\"threshold\":" << num(tr.threshold[idx]) << ",\"decision_type\":\"<=\",\"default_left\":" << ((tr.decision_type[idx] & 2) ? "true" : "false")
+          << ",\"threshold\":" << thr << ",\"decision_type\":\"" << (is_cat ? "==" : "<=") << "\",\"default_left\":" << ((tr.decision_type[idx] & 2) ? "true" : "false")
           << ",\"missing_type\":\"" << (mt == 0 ? "None" : mt == 1 ? "Zero" : "NaN") << "\",\"internal_value\":" << num(tr.internal_value[idx])
           << ",\"internal_weight\":" << num(tr.internal_weight[idx]) << ",\"internal_count\":" << tr.internal_count[idx] << ",\"left_child\":";
         node(o, tr, tr.left_child[idx], num);
@@ -1942,6 +1978,7 @@ void Booster::ValidateMetrics() const {
 }
 
 std::vector<double> Booster::GetEval(int data_idx) {
+  NvtxRange nvtx("b200gbm:eval metrics (LGBM_BoosterGetEval)");
   if (!train) Fatal("this booster was loaded from a model string: it holds no training/validation data to evaluate");
   EnsureDevice();
   if (is_dart_ && data_idx == 0 && !dart_dropped_this_iter_) DroppingTrees();      // DART::GetTrainingScore

@@ -479,4 +479,5 @@ k4_hist_build_ws(const uint8_t* __restrict__ bins, size_t rows_stride, int num_t
   }
 }
 
+
 }  // namespace b200gbm

@@ -26,7 +26,8 @@ struct FeatMeta {          // per inner (used) feature
 // sampled mass is covered (BinMapper::FindBin) — so a 10^3..10^5-cardinality column (BASELINE.json configs[4]) needs thousands of bins.
 // They live outside the uint8 feature tiles: one uint16 column per feature, their own histogram kernel (k4_hist_wide) and scan
 // (k_scan_wide); inner index = nfn + w.  A categorical split on one sends at most max_cat_threshold bins left, carried as a bin list.
-constexpr int kWideMaxBins = 8192;       // 4 planes x 8192 x 4 B = 128 KB of shared memory per CTA
+constexpr int kWideHistSeg = 8192;       // bins one k4_hist_wide CTA accumulates: 4 planes x 8192 x 4 B = 128 KB of shared memory
+constexpr int kWideMaxBins = 16384;      // per feature (k_scan_wide sorts (ctr, bin) keys in 160 KB of shared memory); more fails loudly
 constexpr int kCatListMax = 64;          // >= max_cat_threshold (default 32) when wide features exist
 struct WideMeta {
   int num_bin, hist_off, cat_off, num_cats;      // hist_off in (g,h) pairs; cat_off/num_cats: slice of the sorted category table
@@ -114,7 +115,10 @@ __device__ __forceinline__ double d_calc_output(double g, double h, const SplitP
   if (p.max_delta_step > 0 && fabs(ret) > p.max_delta_step) ret = d_sign(ret) * p.max_delta_step;
   return ret;
 }
-__device__ __forceinline__ double d_leaf_gain(double g, double h, const SplitParams& p) {
+// NOT inlined on purpose: the split scan evaluates it ~40 times per lane; inlined and unrolled (each call holds a software fp64 division)
+// k_scan grew to 15.8K SASS instructions that every warp ran through once, and ncu showed 55 % of its stall samples in stall_no_inst
+// (instruction-cache misses), 39 us per launch.  As a function its body is fetched once.
+__device__ __noinline__ double d_leaf_gain(double g, double h, const SplitParams& p) {
   if (!(p.max_delta_step > 0)) {
     if (p.l1 > 0) { double sg = d_threshold_l1(g, p.l1); return (sg * sg) / (h + p.l2); }
     return (g * g) / (h + p.l2);
@@ -572,6 +576,8 @@ __device__ __forceinline__ long long warp_prefix_excl(long long v, int lane) {  
 }
 
 // the per-feature scan shared by k_scan and k_scan_dp: qg/qh = this lane's 8 bins of the (global) histogram
+// The bin loops are deliberately NOT unrolled (qg/qh/cnt are then indexed dynamically and live in L1-cached local memory): unrolled, the two
+// scan directions alone were ~5K instructions of straight-line fp64 code per warp and the kernel was bound by instruction fetch.
 __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
                                                double inv_g, double inv_h, const SplitParams& p, uint8_t* flag, SplitCand* outp) {
   SplitCand& out = *outp;
@@ -583,7 +589,7 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
   const int na = two_way ? 1 : 0;
 
   int cnt[8];
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 8; ++j) cnt[j] = static_cast<int>(static_cast<double>(qh[j]) * inv_h * cnt_factor + 0.5);
 
   // ---- reverse pass: bins num_bin-1-na .. 1, candidate threshold = b-1
@@ -593,10 +599,10 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
   {
     const int hi = m.num_bin - 1 - na;
     long long lg = 0, lh = 0, lc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) { const int b = lane * 8 + j; if (b >= 1 && b <= hi) { lg += qg[j]; lh += qh[j]; lc += cnt[j]; } }
     long long rg = warp_suffix_excl(lg, lane), rh = warp_suffix_excl(lh, lane), rc = warp_suffix_excl(lc, lane);
-#pragma unroll
+#pragma unroll 1
     for (int j = 7; j >= 0; --j) {
       const int b = lane * 8 + j;
       if (b < 1 || b > hi) continue;
@@ -629,7 +635,7 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
     const int hi = m.num_bin - 2;
     long long ag = 0, ah = 0, ac = 0;     // everything stored except bin 0 (incl. the NaN bin)
     long long lg = 0, lh = 0, lc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       const int b = lane * 8 + j;
       if (b >= 1 && b < m.num_bin) { ag += qg[j]; ah += qh[j]; ac += cnt[j]; }
@@ -644,7 +650,7 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
       base_c = num_data - static_cast<int>(ac);
     }
     double f_gain = kNegInf, f_lg = 0, f_lh = 0; int f_thr = 1 << 30, f_lc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       const int b = lane * 8 + j;
       if (b > hi) continue;
@@ -688,7 +694,7 @@ __device__ __forceinline__ void d_scan_feature(const long long (&qg)[8], const l
 // one-hot when num_bin <= max_cat_to_onehot; otherwise the bins holding >= cat_smooth rows are ranked by g/(h+cat_smooth)
 // (stable, ties by bin) and accumulated from both ends, at most max_cat_threshold bins, lambda_l2 += cat_l2.
 // ws = this warp's shared scratch: g[256], h[256], ctr[256] doubles + order[256] + used[256] bytes.
-__device__ __forceinline__ void d_scan_feature_cat(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
+__device__ __noinline__ void d_scan_feature_cat(const long long (&qg)[8], const long long (&qh)[8], int lane, const FeatMeta m, const LeafState& L,
                                                    double inv_g, double inv_h, const SplitParams& p, uint8_t* flag, SplitCand* outp, double* ws) {
   SplitCand& out = *outp;
   double* sg = ws; double* sh = ws + 256; double* sc = ws + 512;
@@ -862,7 +868,7 @@ __device__ __forceinline__ SplitCand d_load_cand(const SplitCand* c) {
   return out;
 }
 // best candidate per leaf (argmax over features, ties -> smaller real feature index), then the leaf to split; one 256-thread block
-__device__ void
+__device__ __noinline__ void
 d_pick_block(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* cands, const SplitParams& p) {
   __shared__ double s_gain[256];
   __shared__ int s_feat[256], s_idx[256];
@@ -1240,7 +1246,8 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     if (threadIdx.x < list_len) s_list[threadIdx.x] = ctrl->split_cat_list[threadIdx.x];
     __syncthreads();
     const int chunks = (n + kPartChunk - 1) / kPartChunk;
-    // ---- phase 1
+    // ---- phase 1 (no block-wide barrier: every warp adds the left count of its 256 rows to the chunk's counter, which the tail of
+    // the previous partition kernel left at zero)
     for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
       int local = 0;
 #pragma unroll
@@ -1250,16 +1257,13 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
         if (i < n) {
           const int r = identity ? (begin + i) : src[begin + i];
           const unsigned bin = wide >= 0 ? static_cast<unsigned>(wcol[r]) : static_cast<unsigned>(col[static_cast<size_t>(r) * 32]);
-          if (wide_cat) { for (int k = 0; k < list_len; ++k) left |= (bin == s_list[k]); }
+          if (wide_cat) { for (int kk = 0; kk < list_len; ++kk) left |= (bin == s_list[kk]); }
           else left = d_goes_left(bin, ctrl);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, left);
         if (lane == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
       }
-      if (lane == 0) s_cnt[warp] = local;
-      __syncthreads();
-      if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_cnt[w]; chunk_left[c] = t; }
-      __syncthreads();
+      if (lane == 0 && local) atomicAdd(&chunk_left[c], local);
     }
     d_grid_barrier(&ctrl->part_barrier, gridDim.x);
     // ---- phase 2: exclusive prefix of the chunk counts + total
@@ -1362,6 +1366,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
   if (s_last) {
     __threadfence();
     if (threadIdx.x == 0) { ctrl->part_ticket = 0u; ctrl->part_barrier = 0u; }
+    if (n > 0) for (int c = threadIdx.x; c < (n + kPartChunk - 1) / kPartChunk; c += blockDim.x) chunk_left[c] = 0;      // phase 1 of the next launch accumulates into zeros
     d_round_ctl(ctrl, leaves, tree, flags, meta, p, last, s_copy);
   }
 }
@@ -1409,11 +1414,13 @@ k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const Wide
   const int active = min(static_cast<int>(gridDim.x), (n + 4095) / 4096);
   if (static_cast<int>(blockIdx.x) >= active) return;
   const WideMeta m = wm[blockIdx.y];
-  const int nb = m.num_bin;
+  const unsigned lo = blockIdx.z * kWideHistSeg;              // this CTA accumulates bins [lo, lo + nb) of the feature
+  if (static_cast<int>(lo) >= m.num_bin) return;
+  const int nb = min(kWideHistSeg, m.num_bin - static_cast<int>(lo));
   const int p0 = static_cast<int>(static_cast<long long>(n) * blockIdx.x / active), p1 = static_cast<int>(static_cast<long long>(n) * (blockIdx.x + 1) / active);
   const int* __restrict__ idx = w.buf ? idx1 : idx0;
   const uint16_t* __restrict__ col = bins16 + static_cast<size_t>(blockIdx.y) * rows_stride;
-  unsigned* pl0 = wplane; unsigned* pl1 = wplane + kWideMaxBins; unsigned* pl2 = wplane + 2 * kWideMaxBins; unsigned* pl3 = wplane + 3 * kWideMaxBins;
+  unsigned* pl0 = wplane; unsigned* pl1 = wplane + kWideHistSeg; unsigned* pl2 = wplane + 2 * kWideHistSeg; unsigned* pl3 = wplane + 3 * kWideHistSeg;
   for (int e = threadIdx.x; e < nb; e += kWideThreads) { pl0[e] = 0u; pl1[e] = 0u; pl2[e] = 0u; if (NATOM == 4) pl3[e] = 0u; }
   __syncthreads();
   for (int c0 = p0; c0 < p1; c0 += kFlushRows) {
@@ -1422,6 +1429,8 @@ k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const Wide
       int4 q; unsigned b;
       if (w.use_idx) { const int r = idx[w.begin + p]; b = col[r]; q = qord[w.begin + p]; }
       else { const size_t r = static_cast<size_t>(w.begin + p); b = col[r]; q = qgh[r]; }
+      b -= lo;
+      if (b >= static_cast<unsigned>(nb)) continue;           // another segment's bin
       atomicAdd(&pl0[b], static_cast<unsigned>(q.x));
       atomicAdd(&pl1[b], static_cast<unsigned>(q.y));
       atomicAdd(&pl2[b], static_cast<unsigned>(q.z));
@@ -1433,7 +1442,7 @@ k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const Wide
       if (ghi | glo | hhi | hlo) {
         const long long g = (static_cast<long long>(static_cast<int>(ghi)) << kLoBits) + static_cast<long long>(glo);
         const long long h = (NATOM == 4) ? (static_cast<long long>(static_cast<int>(hhi)) << kLoBits) + static_cast<long long>(hlo) : static_cast<long long>(hhi);
-        const size_t o = (static_cast<size_t>(m.hist_off) + e) * 2;
+        const size_t o = (static_cast<size_t>(m.hist_off) + lo + e) * 2;
         if (g) atomicAdd(&hist[o], static_cast<unsigned long long>(g));
         if (h) atomicAdd(&hist[o + 1], static_cast<unsigned long long>(h));
         pl0[e] = 0u; pl1[e] = 0u; pl2[e] = 0u; if (NATOM == 4) pl3[e] = 0u;

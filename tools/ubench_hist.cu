@@ -10,6 +10,7 @@
 #include <vector>
 #include <cmath>
 #include "../mmlspark_b200/csrc/hist_kernel.cuh"
+#include "k4_direct_load_experiment.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -183,7 +184,11 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(k4_hist_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
   CK(cudaFuncSetAttribute(k4_hist_build_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
   CK(cudaFuncSetAttribute(k4_hist_build_ws<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
-  const bool use_ws = argc > 2 && atoi(argv[2]) == 1;
+  const int variant = argc > 2 ? atoi(argv[2]) : 0;      // 0 = v2, 1 = v3/v4 warp-specialised (production in round 1), 2 = v5 direct-load
+  const bool use_ws = variant == 1;
+  const bool use_dl = variant == 2;
+  CK(cudaFuncSetAttribute(k4_hist_build_dl<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmemBytes));
+  CK(cudaFuncSetAttribute(k4_hist_build_dl<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmemBytes));
 
   // correctness on the first 1M rows (contiguous) and on a strided index list
   {
@@ -192,7 +197,11 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_work, hw, sizeof(hw), cudaMemcpyHostToDevice));
     gen_idx<<<nsm, 256>>>(d_idx, n_chk / 3, 3);
     CK(cudaMemset(d_hist, 0, slot_elems * 8 * 2));
-    if (use_ws) {
+    if (use_dl) {
+      k4_hist_build_dl<4><<<nsm, kDlThreads, kDlSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
+      k_gather_q<<<nsm * 8, 256>>>(d_work + 1, d_idx, d_idx, d_q, d_qord);
+      k4_hist_build_dl<4><<<nsm, kDlThreads, kDlSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
+    } else if (use_ws) {
       k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
       k_gather_q<<<nsm * 8, 256>>>(d_work + 1, d_idx, d_idx, d_q, d_qord);
       k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work + 1, d_hist + slot_elems);
@@ -232,8 +241,11 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 2; ++r) {
       CK(cudaMemsetAsync(d_hist, 0, slot_elems * 8));
       CK(cudaEventRecord(e0));
-      if (use_ws && use_idx) k_gather_q<<<nsm * 8, 256>>>(d_work, d_idx, d_idx, d_q, d_qord);     // part of a leaf pass: timed
-      if (use_ws) {
+      if ((use_ws || use_dl) && use_idx) k_gather_q<<<nsm * 8, 256>>>(d_work, d_idx, d_idx, d_q, d_qord);     // part of a leaf pass: timed
+      if (use_dl) {
+        if (natom == 4) k4_hist_build_dl<4><<<nsm, kDlThreads, kDlSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
+        else k4_hist_build_dl<3><<<nsm, kDlThreads, kDlSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
+      } else if (use_ws) {
         if (natom == 4) k4_hist_build_ws<4><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
         else k4_hist_build_ws<3><<<nsm, kWsThreads, kWsSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_qord, d_idx, d_idx, d_work, d_hist);
       } else if (natom == 4) k4_hist_build<4><<<nsm, kHistThreads, kHistSmemBytes>>>(d_bins, rows_stride, num_tiles, d_q, d_idx, d_idx, d_work, d_hist);
