@@ -896,6 +896,10 @@ static float LabelWeightedPercentile(const float* y, const float* w, int cnt, do
 }
 
 // =============================================================================== booster
+// dynamic shared memory of k_grad_lambdarank: per-document arrays + the pair matrix of one j-tile
+static size_t LambdarankSmem(int max_q, int truncation) {
+  return static_cast<size_t>(max_q) * (8 + 8 + 4 + 4 + 4 + 4) + 8 + static_cast<size_t>(truncation) * (lr_tile(truncation) + 1) * 8;
+}
 static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 constexpr int kScanSmem = 8 * (768 + 64) * 8;     // k_scan: per-warp scratch of the categorical split search
 
@@ -1198,7 +1202,8 @@ void Booster::InitTraining() {
     for (size_t i = 0; i < disc.size(); ++i) disc[i] = 1.0 / std::log2(2.0 + i);
     lr_discount_.Alloc(disc.size()); lr_discount_.Upload(disc.data(), disc.size(), stream_);
     B200_CUDA(cudaStreamSynchronize(stream_));
-    size_t smem = static_cast<size_t>(lr_max_q_) * (8 + 8 + 4 + 4);
+    if (cfg.lambdarank_truncation_level < 1 || cfg.lambdarank_truncation_level > 180) Fatal("lambdarank_truncation_level should be in [1, 180]");
+    size_t smem = LambdarankSmem(lr_max_q_, cfg.lambdarank_truncation_level);
     if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
     B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
   }
@@ -1523,8 +1528,8 @@ void Booster::ComputeGradientsAt(const double* score_p) {
     k_grad_xent<<<grid, 256, 0, stream_>>>(score_p, train->d_label.p, w, grad_.p, hess_.p, n);
   } else if (cfg.objective == "lambdarank") {
     const int nq = static_cast<int>(train->query_boundaries.size()) - 1;
-    size_t smem = std::max<size_t>(static_cast<size_t>(lr_max_q_) * (8 + 8 + 4 + 4), 1024);
-    k_grad_lambdarank<<<std::min(nq, num_sms_ * 16), 128, smem, stream_>>>(
+    size_t smem = std::max<size_t>(LambdarankSmem(lr_max_q_, cfg.lambdarank_truncation_level), 1024);
+    k_grad_lambdarank<<<std::min(nq, num_sms_ * 16), kLrThreads, smem, stream_>>>(
         score_p, train->d_label.p, w, train->d_qb.p, nq, lr_inv_max_dcg_.p, lr_label_gain_.p, lr_discount_.p, lr_sig_table_.p, 1024 * 1024, lr_min_in_,
         lr_max_in_, lr_idx_factor_, cfg.sigmoid, cfg.lambdarank_truncation_level, cfg.lambdarank_norm ? 1 : 0, grad_.p, hess_.p, lr_max_q_);
   }

@@ -286,13 +286,21 @@ __global__ void k_grad_softmax(const double* __restrict__ score, const float* __
 
 // [UPSTREAM LambdarankNDCG::GetGradientsForOneQuery] — one block per query (K2).
 // Sorting: stable rank by score descending (rank counting out of shared memory; queries are ~100 docs).
-// Accumulation: one thread per DOCUMENT adds the pairs it takes part in, in the reference's own (i, j) pair order — pairs (i, p) with
-// i < min(p, truncation) ascending, then pairs (p, j), j > p, when p < truncation — with the reference's fp32 `+=` / `-=` on a score_t
-// accumulator.  Every pair is evaluated twice (once per side) but there are no atomics (shared-memory float atomicAdd is a CAS loop on
-// sm_100a) and each document's lambda / hessian is the same sequence of fp32 additions as the sequential reference, so gradients are
-// reproducible run to run and equal to the oracle's up to the fp64 rounding of the normalisation factor.  discount[] = 1 / log2(2 + pos)
-// is the host-computed table the reference uses (DCGCalculator::GetDiscount), not a device log2.
-__global__ void __launch_bounds__(128)
+// Pairs (i, j), i < min(truncation, cnt-1), j > i, are evaluated ONCE, tile by tile over j, by all threads (balanced) into a
+// shared-memory matrix M[i][j] = (+-p_lambda, p_hessian) as fp32; then one thread per DOCUMENT adds its entries in the reference's own
+// pair order — for document p: (0,p), (1,p) .. (p-1,p), then (p,p+1) .. (p,cnt-1) — with fp32 adds on a score_t accumulator.  No atomics
+// (shared-memory float atomicAdd is a CAS loop on sm_100a), no double evaluation (the pair math is fp64 with a software division and a
+// table look-up: the first version of this kernel, which evaluated every pair once per side, was FP64-bound at 2.4 ms per 50k queries),
+// and every document's lambda / hessian is the same sequence of fp32 additions as the sequential reference: gradients are reproducible
+// and equal to the oracle's up to the fp64 rounding of the normalisation factor.  discount[] = 1 / log2(2 + pos) is the host-computed
+// table the reference uses (DCGCalculator), not a device log2.
+constexpr int kLrThreads = 128;
+__host__ __device__ inline int lr_tile(int truncation) {          // j-tile width: M = truncation x (tile + 1) float2 within 48 KB
+  int t = (48 * 1024 / 8) / max(truncation, 1) - 1;
+  t = min(t, 128);                 // queries are ~100 documents: one tile, and 20 KB per block keeps 8+ blocks per SM
+  return max(t & ~31, 32);
+}
+__global__ void __launch_bounds__(kLrThreads)
 k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ label, const float* __restrict__ weight,
                   const int* __restrict__ qb, int nq, const double* __restrict__ inv_max_dcg, const double* __restrict__ label_gain,
                   const double* __restrict__ discount, const float* __restrict__ sig_table, int sig_bins, double min_in, double max_in,
@@ -302,7 +310,11 @@ k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ la
   double* s_score = r_score + max_q;                                     // [max_q] scores by sorted position
   int* s_lab = reinterpret_cast<int*>(s_score + max_q);                  // label by sorted position
   int* s_orig = s_lab + max_q;                                           // document index by sorted position
-  __shared__ double s_part[128];
+  float* s_lam = reinterpret_cast<float*>(s_orig + max_q);               // accumulators by sorted position
+  float* s_hes = s_lam + max_q;
+  float2* M = reinterpret_cast<float2*>(s_hes + max_q);                  // [truncation][T + 1]; 32 * max_q bytes precede it: 8-byte aligned
+  __shared__ double s_part[kLrThreads];
+  const int T = lr_tile(truncation), TS = T + 1;
   for (int q = blockIdx.x; q < nq; q += gridDim.x) {
     const int start = qb[q], cnt = qb[q + 1] - start;
     __syncthreads();
@@ -316,6 +328,7 @@ k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ la
         rank += (sj > si) || (sj == si && j < i);
       }
       s_score[rank] = si; s_lab[rank] = static_cast<int>(label[start + i]); s_orig[rank] = i;
+      s_lam[rank] = 0.f; s_hes[rank] = 0.f;
     }
     __syncthreads();
     const double imd = inv_max_dcg[q];
@@ -324,63 +337,65 @@ k_grad_lambdarank(const double* __restrict__ score, const float* __restrict__ la
     if (worst_idx > 0 && s_score[worst_idx] == kNegInf) worst_idx -= 1;
     const double worst_score = s_score[worst_idx];
     const bool do_div = norm && best_score != worst_score;
-    // pair (i, j), i < j (sorted positions): returns p_lambda / p_hessian and whether position i is the higher-labelled one
-    auto pair = [&](int i, int j, double* p_lambda, double* p_hessian, bool* i_high) -> bool {
-      const double sci = s_score[i], scj = s_score[j];
-      if (sci == kNegInf || scj == kNegInf) return false;
-      const int li = s_lab[i], lj = s_lab[j];
-      if (li == lj) return false;
-      const bool ih = li > lj;
-      const int hr = ih ? i : j, lr = ih ? j : i;
-      const double delta_score = ih ? sci - scj : scj - sci;
-      const double dcg_gap = label_gain[ih ? li : lj] - label_gain[ih ? lj : li];
-      const double paired_discount = fabs(discount[hr] - discount[lr]);
-      double delta = dcg_gap * paired_discount * imd;
-      if (do_div) delta /= (0.01f + fabs(delta_score));
-      double pl;
-      if (delta_score <= min_in) pl = sig_table[0];
-      else if (delta_score >= max_in) pl = sig_table[sig_bins - 1];
-      else pl = sig_table[static_cast<size_t>((delta_score - min_in) * idx_factor)];
-      double ph = pl * (1.0f - pl);
-      pl *= -sigmoid * delta;
-      ph *= sigmoid * sigmoid * delta;
-      *p_lambda = pl; *p_hessian = ph; *i_high = ih;
-      return true;
-    };
+    const int teff = min(truncation, cnt - 1);          // pairs exist for i < teff
     double local_sum = 0.0;
-    for (int pbase = 0; pbase < cnt; pbase += blockDim.x) {
-      const int p = pbase + threadIdx.x;
-      float lam = 0.f, hes = 0.f;
-      if (p < cnt) {
-        const int ilim = min(p, min(truncation, cnt - 1));
-        for (int i = 0; i < ilim; ++i) {            // this document is the later position j of the pair
-          double pl, ph; bool ih;
-          if (!pair(i, p, &pl, &ph, &ih)) continue;
-          lam = ih ? __fsub_rn(lam, static_cast<float>(pl)) : __fadd_rn(lam, static_cast<float>(pl));      // low: -=, high: +=
-          hes = __fadd_rn(hes, static_cast<float>(ph));
-        }
-        if (p < truncation && p < cnt - 1) {
-          for (int j = p + 1; j < cnt; ++j) {       // this document is the earlier position i of the pair
-            double pl, ph; bool ih;
-            if (!pair(p, j, &pl, &ph, &ih)) continue;
-            lam = ih ? __fadd_rn(lam, static_cast<float>(pl)) : __fsub_rn(lam, static_cast<float>(pl));
-            hes = __fadd_rn(hes, static_cast<float>(ph));
-            local_sum -= 2 * pl;                    // every pair is counted once, by its earlier position
+    for (int j0 = 0; j0 < cnt; j0 += T) {
+      const int tcnt = min(T, cnt - j0);
+      // ---- phase A: every pair of the tile once
+      for (int e = threadIdx.x; e < teff * tcnt; e += blockDim.x) {
+        const int i = e / tcnt, jj = e - i * tcnt, j = j0 + jj;
+        float2 m = make_float2(0.f, 0.f);
+        if (j > i) {
+          const double sci = s_score[i], scj = s_score[j];
+          const int li = s_lab[i], lj = s_lab[j];
+          if (sci != kNegInf && scj != kNegInf && li != lj) {
+            const bool ih = li > lj;                     // position i holds the higher label
+            const int hr = ih ? i : j, lr = ih ? j : i;
+            const double delta_score = ih ? sci - scj : scj - sci;
+            const double dcg_gap = label_gain[ih ? li : lj] - label_gain[ih ? lj : li];
+            const double paired_discount = fabs(discount[hr] - discount[lr]);
+            double delta = dcg_gap * paired_discount * imd;
+            if (do_div) delta /= (0.01f + fabs(delta_score));
+            double pl;
+            if (delta_score <= min_in) pl = sig_table[0];
+            else if (delta_score >= max_in) pl = sig_table[sig_bins - 1];
+            else pl = sig_table[static_cast<size_t>((delta_score - min_in) * idx_factor)];
+            double ph = pl * (1.0f - pl);
+            pl *= -sigmoid * delta;
+            ph *= sigmoid * sigmoid * delta;
+            local_sum -= 2 * pl;
+            const float fl = static_cast<float>(pl);
+            m = make_float2(ih ? fl : -fl, static_cast<float>(ph));      // lambdas[i] += m.x, lambdas[j] -= m.x (x - y == x + (-y) exactly)
           }
         }
+        M[i * TS + jj] = m;
       }
-      // keep the accumulators in the (now unused) raw-score slots until the normalisation factor is known
-      if (p < cnt) { reinterpret_cast<float*>(r_score)[2 * p] = lam; reinterpret_cast<float*>(r_score)[2 * p + 1] = hes; }
+      __syncthreads();
+      // ---- phase B: one thread per document, the reference's order of additions
+      for (int p = threadIdx.x; p < cnt; p += blockDim.x) {
+        const bool as_j = p >= j0 && p < j0 + tcnt, as_i = p < teff && p + 1 < j0 + tcnt;
+        if (!as_j && !as_i) continue;
+        float lam = s_lam[p], hes = s_hes[p];
+        if (as_j) {
+          const int ilim = min(p, teff);
+          for (int i = 0; i < ilim; ++i) { const float2 m = M[i * TS + (p - j0)]; lam = __fsub_rn(lam, m.x); hes = __fadd_rn(hes, m.y); }
+        }
+        if (as_i) {
+          for (int j = max(j0, p + 1); j < j0 + tcnt; ++j) { const float2 m = M[p * TS + (j - j0)]; lam = __fadd_rn(lam, m.x); hes = __fadd_rn(hes, m.y); }
+        }
+        s_lam[p] = lam; s_hes[p] = hes;
+      }
+      __syncthreads();
     }
     s_part[threadIdx.x] = local_sum;
     __syncthreads();
     double sum_lambdas = 0.0;
-    if (norm) for (int t = 0; t < min(static_cast<int>(blockDim.x), cnt); ++t) sum_lambdas += s_part[t];      // fixed order: reproducible
+    if (norm) for (int t = 0; t < static_cast<int>(blockDim.x); ++t) sum_lambdas += s_part[t];      // fixed order: reproducible
     double nf = 1.0;
     const bool do_norm = norm && sum_lambdas > 0;
     if (do_norm) nf = log2(1 + sum_lambdas) / sum_lambdas;
     for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
-      float lam = reinterpret_cast<float*>(r_score)[2 * r], hes = reinterpret_cast<float*>(r_score)[2 * r + 1];
+      float lam = s_lam[r], hes = s_hes[r];
       if (do_norm) { lam = static_cast<float>(lam * nf); hes = static_cast<float>(hes * nf); }
       const int o = start + s_orig[r];
       if (weight) { lam = static_cast<float>(lam * weight[o]); hes = static_cast<float>(hes * weight[o]); }
