@@ -260,7 +260,7 @@ class Dataset:
         return dict(num_bin=int(info[0]), missing_type=int(info[1]), default_bin=int(info[2]), most_freq_bin=int(info[3]), is_trivial=bool(info[4]))
 
     def upper_bounds(self, f):
-        out = np.zeros(512, dtype=np.float64); k = C.c_int(0)
+        out = np.zeros(32768, dtype=np.float64); k = C.c_int(0)
         check(load().B200GBM_DatasetGetUpperBounds(self.handle, C.c_int(f), _ptr(out), C.byref(k)))
         return out[:k.value].copy()
 

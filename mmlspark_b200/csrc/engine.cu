@@ -237,7 +237,7 @@ static FeatureBins UnpackMapper(const double* r) {
 
 void Dataset::FindBins(const void* data, bool on_device, int data_type, int is_row_major) {
   const int n = num_data, F = num_total_features;
-  if (cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+  if (cfg.max_bin >= kWideMaxBins) Fatal("max_bin >= " + std::to_string(kWideMaxBins) + " is not supported");
   if (cfg.max_bin < 2) Fatal("max_bin should be >= 2");
   if (cfg.zero_as_missing) Fatal("zero_as_missing=true is not supported by this build");
   LcgRandom rnd(cfg.data_random_seed);
@@ -306,7 +306,7 @@ void Dataset::FindBinsFromColumns(std::vector<std::vector<double>>* nzp, int sam
   for (int f = f0; f < f1; ++f)
     if (mappers[f].num_bin > kWideMaxBins)
       Fatal("categorical feature " + std::to_string(f) + " needs " + std::to_string(mappers[f].num_bin) +
-            " bins to cover 99% of its mass; this build supports at most " + std::to_string(kWideMaxBins) + " bins per feature");
+            " bins (a categorical feature keeps categories until 99% of its mass is covered); this build supports at most " + std::to_string(kWideMaxBins) + " bins per feature");
   if (world > 1) {   // C5: all-gather the serialized mappers (record = 10 header doubles + the largest bin count of any rank)
     double maxbins = 256;
     for (int f = f0; f < f1; ++f) maxbins = std::max(maxbins, static_cast<double>(mappers[f].num_bin));
@@ -334,7 +334,7 @@ void Dataset::UploadMeta() {
   std::vector<int> wide_real;
   for (int f = 0; f < num_total_features; ++f) {
     if (mappers[f].trivial) continue;
-    if (mappers[f].num_bin > 256) { if (!mappers[f].categorical) Fatal("numerical features with more than 256 bins are not supported"); wide_real.push_back(f); }
+    if (mappers[f].num_bin > 256) wide_real.push_back(f);
     else { inner_of[f] = static_cast<int>(used.size()); used.push_back(f); }
   }
   nfn = static_cast<int>(used.size());
@@ -353,14 +353,17 @@ void Dataset::UploadMeta() {
   wide_host.clear();
   std::vector<int> wcats;
   std::vector<unsigned short> wbins;
+  std::vector<double> wub;
   for (int u = 0; u < nf; ++u) {
     const FeatureBins& fb = mappers[used[u]];
     int hist_off = u * 256;
     if (u >= nfn) {
       hist_off = static_cast<int>(hist_pairs);
-      WideMeta wm{fb.num_bin, hist_off, static_cast<int>(wcats.size()), static_cast<int>(fb.sorted_cats.size()), static_cast<int>(fb.default_bin), fb.missing_type, used[u], 0};
+      WideMeta wm{fb.num_bin, hist_off, static_cast<int>(fb.categorical ? wcats.size() : wub.size()), static_cast<int>(fb.sorted_cats.size()),
+                  static_cast<int>(fb.default_bin), fb.missing_type, used[u], fb.categorical ? 1 : 0, fb.most_freq_bin == 0 ? 1 : 0, 0, 0, 0};
       wide_host.push_back(wm);
-      for (size_t i = 0; i < fb.sorted_cats.size(); ++i) { wcats.push_back(fb.sorted_cats[i]); wbins.push_back(static_cast<unsigned short>(fb.sorted_bins[i])); }
+      if (fb.categorical) for (size_t i = 0; i < fb.sorted_cats.size(); ++i) { wcats.push_back(fb.sorted_cats[i]); wbins.push_back(static_cast<unsigned short>(fb.sorted_bins[i])); }
+      else wub.insert(wub.end(), fb.upper.begin(), fb.upper.end());
       hist_pairs += (static_cast<size_t>(fb.num_bin) + 255) / 256 * 256;
       if (hist_pairs > (1u << 30)) Fatal("histogram of the wide features is too large");
     }
@@ -385,6 +388,8 @@ void Dataset::UploadMeta() {
     wide_meta.Alloc(nw); wide_meta.Upload(wide_host.data(), nw, stream);
     wide_cats.Alloc(std::max<size_t>(wcats.size(), 1)); wide_catbin.Alloc(std::max<size_t>(wbins.size(), 1));
     if (!wcats.empty()) { wide_cats.Upload(wcats.data(), wcats.size(), stream); wide_catbin.Upload(wbins.data(), wbins.size(), stream); }
+    wide_ub.Alloc(std::max<size_t>(wub.size(), 1));
+    if (!wub.empty()) wide_ub.Upload(wub.data(), wub.size(), stream);
   }
   B200_CUDA(cudaStreamSynchronize(stream));
 }
@@ -403,7 +408,7 @@ static void LaunchBin(const T* X, long long nrow, int ncol, int row_major, long 
   if (grid.x == 0) grid.x = 1;
   k_bin_rows<T><<<grid, 256, 65536, s>>>(X, nrow, ncol, row_major, ld, d.meta.p, d.ub.p, d.catbin.p, d.nfn, d.bins.p, static_cast<long long>(d.rows_stride), row_offset);
   if (d.nw > 0)
-    k_bin_wide<T><<<148 * 8, 256, 0, s>>>(X, nrow, row_major, ld, d.wide_meta.p, d.nw, d.wide_cats.p, d.wide_catbin.p, d.bins16.p, d.rows_stride, row_offset);
+    k_bin_wide<T><<<148 * 8, 256, 0, s>>>(X, nrow, row_major, ld, d.wide_meta.p, d.nw, d.wide_cats.p, d.wide_catbin.p, d.wide_ub.p, d.bins16.p, d.rows_stride, row_offset);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -477,7 +482,7 @@ Dataset* Dataset::CreateFromSampledColumn(double** sample_data, int** sample_ind
   B200_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   d->num_data = num_total_row; d->num_total_features = ncol;
   d->cfg.Parse(params);
-  if (d->cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+  if (d->cfg.max_bin >= kWideMaxBins) Fatal("max_bin >= " + std::to_string(kWideMaxBins) + " is not supported");
   std::vector<std::vector<double>> nz(ncol);
   for (int f = 0; f < ncol; ++f) nz[f].assign(sample_data[f], sample_data[f] + num_per_col[f]);
   d->FindBinsFromColumns(&nz, num_sample_row);
@@ -650,7 +655,7 @@ template <typename TI, typename TV>
 __global__ void k_bin_csr(const TI* __restrict__ indptr, const int* __restrict__ indices, const TV* __restrict__ vals, long long nrow, const int* __restrict__ inner_of,
                           const FeatMeta* __restrict__ meta, const double* __restrict__ ub, const uint8_t* __restrict__ catbin, uint8_t* __restrict__ bins,
                           size_t rows_stride, long long elem_base, int nfn, const WideMeta* __restrict__ wm, const int* __restrict__ wcats,
-                          const unsigned short* __restrict__ wcatbin, uint16_t* __restrict__ bins16) {
+                          const unsigned short* __restrict__ wcatbin, const double* __restrict__ wub, uint16_t* __restrict__ bins16) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5, nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = warp; r < nrow; r += nwarps) {
@@ -660,19 +665,8 @@ __global__ void k_bin_csr(const TI* __restrict__ indptr, const int* __restrict__
       if (u < 0) continue;
       const FeatMeta m = meta[u];
       double v = static_cast<double>(vals[k]);
-      if (u >= nfn) {           // wide categorical column
-        const WideMeta w = wm[u - nfn];
-        unsigned wb = 0;
-        if (!isnan(v)) {
-          const int iv = static_cast<int>(v);
-          if (iv >= 0) {
-            const int* c = wcats + w.cat_off;
-            int lo = 0, hi = w.num_cats;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] < iv) lo = mid + 1; else hi = mid; }
-            if (lo < w.num_cats && c[lo] == iv) wb = wcatbin[w.cat_off + lo];
-          }
-        }
-        bins16[static_cast<size_t>(u - nfn) * rows_stride + r] = static_cast<uint16_t>(wb);
+      if (u >= nfn) {           // wide column (categorical with > 256 bins, or numerical with max_bin > 255)
+        bins16[static_cast<size_t>(u - nfn) * rows_stride + r] = static_cast<uint16_t>(d_wide_bin(v, wm[u - nfn], wcats, wcatbin, wub));
         continue;
       }
       const double* myub = ub + static_cast<size_t>(u) * 256;
@@ -736,7 +730,7 @@ Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32
     d->mappers = reference->mappers;
     d->feature_names = reference->feature_names;
   } else {
-    if (d->cfg.max_bin > 255) Fatal("max_bin > 255 is not supported (bins are stored as uint8)");
+    if (d->cfg.max_bin >= kWideMaxBins) Fatal("max_bin >= " + std::to_string(kWideMaxBins) + " is not supported");
     if (d->cfg.max_bin < 2) Fatal("max_bin should be >= 2");
     if (d->cfg.zero_as_missing) Fatal("zero_as_missing=true is not supported by this build");
     LcgRandom rnd(d->cfg.data_random_seed);
@@ -784,7 +778,7 @@ Dataset* Dataset::CreateFromCSR(const void* indptr, int indptr_type, const int32
 #define B200_CSR_LAUNCH(TI, TV)                                                                                                              \
         k_bin_csr<TI, TV><<<grid, 256, 0, d->stream>>>(reinterpret_cast<const TI*>(d_ip.p), reinterpret_cast<const int*>(d_ix.p),               \
                                                       reinterpret_cast<const TV*>(d_v.p), nr, d_inner.p, d->meta.p, d->ub.p, d->catbin.p, base,  \
-                                                      d->rows_stride, e0k, d->nfn, d->wide_meta.p, d->wide_cats.p, d->wide_catbin.p,               \
+                                                      d->rows_stride, e0k, d->nfn, d->wide_meta.p, d->wide_cats.p, d->wide_catbin.p, d->wide_ub.p,  \
                                                       d->bins16.p ? d->bins16.p + r0 : nullptr)
         if (indptr_type == 2 && data_type == 0) B200_CSR_LAUNCH(int32_t, float);
         else if (indptr_type == 2) B200_CSR_LAUNCH(int32_t, double);

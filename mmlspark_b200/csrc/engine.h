@@ -107,6 +107,7 @@ class Dataset {
   DevBuf<WideMeta> wide_meta;
   DevBuf<int> wide_cats;                     // sorted category values of all wide features (slices per WideMeta)
   DevBuf<unsigned short> wide_catbin;        // ... and their bins
+  DevBuf<double> wide_ub;                    // bin upper bounds of the wide numerical features (max_bin > 255)
   BinView View() const { return BinView{bins.p, rows_stride, bins16.p, nfn}; }
   DevBuf<FeatMeta> meta;
   DevBuf<double> ub;                         // [nf][256] bin upper bounds (categorical: sorted category values)

@@ -30,8 +30,10 @@ constexpr int kWideHistSeg = 8192;       // bins one k4_hist_wide CTA accumulate
 constexpr int kWideMaxBins = 16384;      // per feature (k_scan_wide sorts (ctr, bin) keys in 160 KB of shared memory); more fails loudly
 constexpr int kCatListMax = 64;          // >= max_cat_threshold (default 32) when wide features exist
 struct WideMeta {
-  int num_bin, hist_off, cat_off, num_cats;      // hist_off in (g,h) pairs; cat_off/num_cats: slice of the sorted category table
-  int default_bin, missing_type, real_index, pad;
+  int num_bin, hist_off, cat_off, num_cats;      // hist_off in (g,h) pairs; categorical: slice of the sorted category table (cat_off, num_cats);
+                                                 // numerical (max_bin > 255): cat_off = first entry of the feature's upper bounds in the wide ub table
+  int default_bin, missing_type, real_index, is_cat;
+  int offset, pad0, pad1, pad2;                  // offset: 1 iff most_freq_bin == 0 (as FeatMeta::offset)
 };
 struct BinView {                         // where a row's bin of inner feature u is stored
   const uint8_t* bins; size_t rows_stride; const uint16_t* bins16; int nfn;
@@ -1388,17 +1390,11 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
 
 // ---------------------------------------------------------------- wide features (> 256 bins): binning, histogram, categorical scan
 // value -> bin of the wide columns of a row block (categorical lookup: binary search in the feature's sorted category table)
-template <typename T>
-__global__ void k_bin_wide(const T* __restrict__ X, long long nrow, int row_major, long long ld, const WideMeta* __restrict__ wm, int nw,
-                           const int* __restrict__ cats, const unsigned short* __restrict__ catbin, uint16_t* __restrict__ bins16, size_t rows_stride,
-                           long long row_offset) {
-  const long long total = nrow * nw;
-  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(e / nrow);
-    const long long r = e - static_cast<long long>(w) * nrow;
-    const WideMeta m = wm[w];
-    const double v = row_major ? static_cast<double>(X[r * ld + m.real_index]) : static_cast<double>(X[static_cast<long long>(m.real_index) * ld + r]);
-    unsigned bin = 0;
+// value -> bin of one wide feature (shared by the dense and CSR ingestion kernels)
+__device__ __forceinline__ unsigned d_wide_bin(double v, const WideMeta& m, const int* __restrict__ cats, const unsigned short* __restrict__ catbin,
+                                               const double* __restrict__ wub) {
+  unsigned bin = 0;
+  if (m.is_cat) {
     if (!isnan(v)) {
       const int iv = static_cast<int>(v);
       if (iv >= 0) {
@@ -1408,7 +1404,25 @@ __global__ void k_bin_wide(const T* __restrict__ X, long long nrow, int row_majo
         if (lo < m.num_cats && c[lo] == iv) bin = catbin[m.cat_off + lo];
       }
     }
-    bins16[static_cast<size_t>(w) * rows_stride + row_offset + r] = static_cast<uint16_t>(bin);
+    return bin;
+  }
+  if (isnan(v)) { if (m.missing_type == 2) return static_cast<unsigned>(m.num_bin - 1); v = 0.0; }
+  const double* ub = wub + m.cat_off;
+  int lo = 0, hi = m.num_bin - 1 - (m.missing_type == 2 ? 1 : 0);
+  while (lo < hi) { const int mid = (hi + lo - 1) / 2; if (v <= ub[mid]) hi = mid; else lo = mid + 1; }
+  return static_cast<unsigned>(lo);
+}
+template <typename T>
+__global__ void k_bin_wide(const T* __restrict__ X, long long nrow, int row_major, long long ld, const WideMeta* __restrict__ wm, int nw,
+                           const int* __restrict__ cats, const unsigned short* __restrict__ catbin, const double* __restrict__ wub,
+                           uint16_t* __restrict__ bins16, size_t rows_stride, long long row_offset) {
+  const long long total = nrow * nw;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(e / nrow);
+    const long long r = e - static_cast<long long>(w) * nrow;
+    const WideMeta m = wm[w];
+    const double v = row_major ? static_cast<double>(X[r * ld + m.real_index]) : static_cast<double>(X[static_cast<long long>(m.real_index) * ld + r]);
+    bins16[static_cast<size_t>(w) * rows_stride + row_offset + r] = static_cast<uint16_t>(d_wide_bin(v, m, cats, catbin, wub));
   }
 }
 
@@ -1467,6 +1481,161 @@ k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const Wide
   }
 }
 
+// exclusive prefix (reverse == 0: over threads < t) or suffix (reverse == 1: over threads > t) sums of three int64 values across a 256-thread
+// block, plus nothing else; sm = 3 * 8 long longs of shared scratch.  Exact integers: any association order gives the same result.
+__device__ __forceinline__ void d_block_excl3(long long& a, long long& b, long long& c, int reverse, long long* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long ia = a, ib = b, ic = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    long long ta, tb, tc;
+    if (reverse) { ta = __shfl_down_sync(0xffffffffu, ia, o); tb = __shfl_down_sync(0xffffffffu, ib, o); tc = __shfl_down_sync(0xffffffffu, ic, o); if (lane + o < 32) { ia += ta; ib += tb; ic += tc; } }
+    else { ta = __shfl_up_sync(0xffffffffu, ia, o); tb = __shfl_up_sync(0xffffffffu, ib, o); tc = __shfl_up_sync(0xffffffffu, ic, o); if (lane >= o) { ia += ta; ib += tb; ic += tc; } }
+  }
+  __syncthreads();
+  if (lane == (reverse ? 0 : 31)) { sm[warp] = ia; sm[8 + warp] = ib; sm[16 + warp] = ic; }
+  __syncthreads();
+  long long oa = 0, ob = 0, oc = 0;
+  for (int w2 = 0; w2 < 8; ++w2) if (reverse ? w2 > warp : w2 < warp) { oa += sm[w2]; ob += sm[8 + w2]; oc += sm[16 + w2]; }
+  a = oa + ia - a; b = ob + ib - b; c = oc + ic - c;
+  __syncthreads();
+}
+
+// FeatureHistogram::FindBestThresholdSequentially for a WIDE numerical feature (max_bin > 255): the same two passes as d_scan_feature with the
+// bins spread over a 256-thread block — thread t owns the contiguous bins [t*S, (t+1)*S) — exclusive block scans of the per-thread
+// (g, h, count) sums, and a block argmax with the sequential scan's tie-breaks (reverse pass: the highest threshold wins, forward pass: the
+// lowest).  hist = the leaf's reduced histogram of the feature in its pool slot.  Returns through *outp (thread 0) and *flag.
+__device__ __noinline__ void d_scan_wide_numeric(const long long* __restrict__ hist, const WideMeta m, const LeafState& L, double inv_g, double inv_h,
+                                                  const SplitParams& p, uint8_t* flag, SplitCand* outp) {
+  __shared__ long long s_sc[24];
+  __shared__ double s_bg[8], s_blg[8], s_blh[8];
+  __shared__ int s_bt[8], s_blc[8], s_any;
+  __shared__ long long s_tot[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
+  const int num_data = L.global_count;
+  const double cnt_factor = num_data / sum_h;
+  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, p) + p.min_gain_to_split;
+  const bool two_way = (m.num_bin > 2 && m.missing_type == 2);
+  const int na = two_way ? 1 : 0;
+  const int S = (m.num_bin + 255) / 256;
+  const int b0 = threadIdx.x * S, b1 = min(b0 + S, m.num_bin);
+  if (threadIdx.x == 0) s_any = 0;
+  bool any_valid = false;
+  // ---- reverse pass: bins hi .. 1, candidate threshold = b - 1
+  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
+  int best_thr = -1, best_lc = 0, best_dl = 1;
+  {
+    const int hi = m.num_bin - 1 - na;
+    long long lg = 0, lh = 0, lc = 0;
+    for (int b = b0; b < b1; ++b)
+      if (b >= 1 && b <= hi) { const long long qh = hist[b * 2 + 1]; lg += hist[b * 2]; lh += qh; lc += static_cast<int>(static_cast<double>(qh) * inv_h * cnt_factor + 0.5); }
+    long long rg = lg, rh = lh, rc = lc;
+    d_block_excl3(rg, rh, rc, 1, s_sc);
+    for (int b = b1 - 1; b >= b0; --b) {
+      if (b < 1 || b > hi) continue;
+      const long long qg = hist[b * 2], qh = hist[b * 2 + 1];
+      rg += qg; rh += qh; rc += static_cast<int>(static_cast<double>(qh) * inv_h * cnt_factor + 0.5);
+      const double srg = static_cast<double>(rg) * inv_g;
+      const double srh = kEpsD + static_cast<double>(rh) * inv_h;
+      const int right_count = static_cast<int>(rc);
+      if (right_count < p.min_data_in_leaf || srh < p.min_sum_hessian) continue;
+      const int left_count = num_data - right_count;
+      if (left_count < p.min_data_in_leaf) continue;
+      const double slh = sum_h - srh;
+      if (slh < p.min_sum_hessian) continue;
+      const double slg = sum_g - srg;
+      const double gain = d_leaf_gain(slg, slh, p) + d_leaf_gain(srg, srh, p);
+      if (gain <= min_gain_shift) continue;
+      any_valid = true;
+      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_thr = b - 1; best_lc = left_count; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, best_thr, o);
+      const double olg = __shfl_xor_sync(0xffffffffu, best_lg, o), olh = __shfl_xor_sync(0xffffffffu, best_lh, o);
+      const int olc = __shfl_xor_sync(0xffffffffu, best_lc, o);
+      if (og > best_gain || (og == best_gain && ot > best_thr)) { best_gain = og; best_thr = ot; best_lg = olg; best_lh = olh; best_lc = olc; }
+    }
+    if (lane == 0) { s_bg[warp] = best_gain; s_bt[warp] = best_thr; s_blg[warp] = best_lg; s_blh[warp] = best_lh; s_blc[warp] = best_lc; }
+    __syncthreads();
+    for (int w2 = 0; w2 < 8; ++w2)
+      if (s_bg[w2] > best_gain || (s_bg[w2] == best_gain && s_bt[w2] > best_thr)) { best_gain = s_bg[w2]; best_thr = s_bt[w2]; best_lg = s_blg[w2]; best_lh = s_blh[w2]; best_lc = s_blc[w2]; }
+    __syncthreads();
+  }
+  // ---- forward pass (NaN-as-missing features only): bins 0 .. num_bin-2, threshold = b, NaN goes right
+  if (two_way) {
+    const int hi = m.num_bin - 2;
+    long long ag = 0, ah = 0, ac = 0, lg = 0, lh = 0, lc = 0;
+    for (int b = b0; b < b1; ++b) {
+      const long long qg = hist[b * 2], qh = hist[b * 2 + 1];
+      const int c = static_cast<int>(static_cast<double>(qh) * inv_h * cnt_factor + 0.5);
+      if (b >= 1 && b < m.num_bin) { ag += qg; ah += qh; ac += c; }
+      if (b >= m.offset && b <= hi) { lg += qg; lh += qh; lc += c; }
+    }
+    {   // block totals of (ag, ah, ac)
+      long long ta = ag, tb = ah, tc = ac;
+      for (int o = 16; o; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tb += __shfl_xor_sync(0xffffffffu, tb, o); tc += __shfl_xor_sync(0xffffffffu, tc, o); }
+      if (lane == 0) { s_sc[warp] = ta; s_sc[8 + warp] = tb; s_sc[16 + warp] = tc; }
+      __syncthreads();
+      if (threadIdx.x == 0) { long long x = 0, y = 0, z = 0; for (int w2 = 0; w2 < 8; ++w2) { x += s_sc[w2]; y += s_sc[8 + w2]; z += s_sc[16 + w2]; } s_tot[0] = x; s_tot[1] = y; s_tot[2] = z; }
+      __syncthreads();
+      ag = s_tot[0]; ah = s_tot[1]; ac = s_tot[2];
+    }
+    long long pg = lg, ph = lh, pc = lc;
+    d_block_excl3(pg, ph, pc, 0, s_sc);
+    double base_g = 0.0, base_h = kEpsD; int base_c = 0;
+    if (m.offset == 1) {   // implicit bin 0 = leaf total - everything stored  [UPSTREAM NA_AS_MISSING && offset==1]
+      base_g = sum_g - static_cast<double>(ag) * inv_g;
+      base_h = (sum_h - kEpsD) - static_cast<double>(ah) * inv_h;
+      base_c = num_data - static_cast<int>(ac);
+    }
+    double f_gain = kNegInf, f_lg = 0, f_lh = 0; int f_thr = 1 << 30, f_lc = 0;
+    for (int b = b0; b < b1; ++b) {
+      if (b > hi) continue;
+      if (b >= m.offset) { const long long qh = hist[b * 2 + 1]; pg += hist[b * 2]; ph += qh; pc += static_cast<int>(static_cast<double>(qh) * inv_h * cnt_factor + 0.5); }
+      const double slg = base_g + static_cast<double>(pg) * inv_g;
+      const double slh = base_h + static_cast<double>(ph) * inv_h;
+      const int left_count = base_c + static_cast<int>(pc);
+      if (left_count < p.min_data_in_leaf || slh < p.min_sum_hessian) continue;
+      const int right_count = num_data - left_count;
+      if (right_count < p.min_data_in_leaf) continue;
+      const double srh = sum_h - slh;
+      if (srh < p.min_sum_hessian) continue;
+      const double srg = sum_g - slg;
+      const double gain = d_leaf_gain(slg, slh, p) + d_leaf_gain(srg, srh, p);
+      if (gain <= min_gain_shift) continue;
+      any_valid = true;
+      if (gain > f_gain) { f_gain = gain; f_lg = slg; f_lh = slh; f_thr = b; f_lc = left_count; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, f_gain, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, f_thr, o);
+      const double olg = __shfl_xor_sync(0xffffffffu, f_lg, o), olh = __shfl_xor_sync(0xffffffffu, f_lh, o);
+      const int olc = __shfl_xor_sync(0xffffffffu, f_lc, o);
+      if (og > f_gain || (og == f_gain && ot < f_thr)) { f_gain = og; f_thr = ot; f_lg = olg; f_lh = olh; f_lc = olc; }
+    }
+    if (lane == 0) { s_bg[warp] = f_gain; s_bt[warp] = f_thr; s_blg[warp] = f_lg; s_blh[warp] = f_lh; s_blc[warp] = f_lc; }
+    __syncthreads();
+    for (int w2 = 0; w2 < 8; ++w2)
+      if (s_bg[w2] > f_gain || (s_bg[w2] == f_gain && s_bt[w2] < f_thr)) { f_gain = s_bg[w2]; f_thr = s_bt[w2]; f_lg = s_blg[w2]; f_lh = s_blh[w2]; f_lc = s_blc[w2]; }
+    __syncthreads();
+    if (f_gain > best_gain) { best_gain = f_gain; best_thr = f_thr; best_lg = f_lg; best_lh = f_lh; best_lc = f_lc; best_dl = 0; }
+  } else if (m.missing_type == 2) {
+    best_dl = 0;
+  }
+  if (any_valid) atomicOr(&s_any, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SplitCand& out = *outp;
+    *flag = s_any ? 1 : 0;
+    out.is_cat = 0; out.default_left = 1;
+    if (s_any && best_gain > min_gain_shift) {
+      out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = best_thr;
+      out.left_count = best_lc; out.default_left = best_dl;
+    }
+  }
+}
+
 // Split search of a WIDE categorical feature (FeatureHistogram::FindBestThresholdCategoricalInner, many-vs-many branch): one block per
 // (smaller|larger, feature).  The histogram is reduced into the leaf's pool slot (parent - smaller for the larger child), the bins that
 // hold >= cat_smooth rows are sorted by g / (h + cat_smooth) with a block-wide bitonic sort over (ctr, bin) keys — the stable order of
@@ -1495,6 +1664,17 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
   const double sum_g = L.sum_g, sum_h = L.sum_h + 2 * kEpsD;
   const int num_data = L.global_count;
   const double cnt_factor = num_data / sum_h;
+  if (!m.is_cat) {        // wide numerical feature (max_bin > 255): reduce into the pool slot, then the block-wide two-pass scan
+    for (int b = threadIdx.x; b < m.num_bin; b += blockDim.x) {
+      longlong2 sv = *reinterpret_cast<const longlong2*>(src + b * 2);
+      if (which) { const longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2); sv.x = pr.x - sv.x; sv.y = pr.y - sv.y; }
+      *reinterpret_cast<longlong2*>(dst + b * 2) = sv;
+    }
+    __syncthreads();      // every thread reads bins other threads reduced (same block: visible after the barrier)
+    d_scan_wide_numeric(dst, m, L, inv_g, inv_h, p, flag, &out);
+    if (threadIdx.x == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); }
+    return;
+  }
   int P = 1;
   while (P < m.num_bin) P <<= 1;
   if (threadIdx.x == 0) s_used = 0;

@@ -154,7 +154,7 @@ class OracleDataset:
                     most_freq_bin=int(info[3]), is_trivial=bool(info[4]))
 
     def upper_bounds(self, f):
-        out = np.zeros(512, dtype=np.float64)
+        out = np.zeros(32768, dtype=np.float64)
         k = lib().orc_dataset_upper_bounds(self.h, f, _p(out))
         return out[:k].copy()
 

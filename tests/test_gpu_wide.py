@@ -175,3 +175,42 @@ def test_wide_categorical_two_ranks(built):
         assert np.array_equal(res[r]["bins"], want[offs[r]:offs[r + 1]])
     assert res[0]["model"] == res[1]["model"]
     compare_models(parse_model(res[0]["model"]), parse_model(ob.model_string()))
+
+
+@pytest.mark.parametrize("max_bin", [1023, 4000])
+def test_numerical_max_bin_above_255(built, max_bin):
+    """maxBin is a plain estimator parameter (LightGBMParams.scala:136-137): numerical features with more than 256 bins take the wide path
+    (uint16 columns, block-wide two-pass scan).  Bins bit-exact, trees identical, incl. the NaN two-way scan and a mostly-zero column."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(50 + max_bin)
+    n = 150_000
+    X = rng.standard_normal((n, 8))
+    X[:, 1] = np.where(rng.random(n) < 0.3, np.nan, X[:, 1])            # NaN bin + forward pass
+    X[:, 2] = np.where(rng.random(n) < 0.8, 0.0, rng.exponential(1.0, n))  # most_freq_bin is the zero bin
+    X[:, 3] = rng.integers(0, 200, n)                                    # <= 256 distinct values: stays a tile feature
+    X[:, 4] = np.round(X[:, 4], 2)                                       # ~800 distinct values
+    s = X[:, 0] + np.where(np.isnan(X[:, 1]), 0.7, np.sin(3 * X[:, 1])) + 0.5 * X[:, 2] + 0.01 * X[:, 3] + X[:, 4] * X[:, 5] + 0.3 * rng.standard_normal(n)
+    y = (s > 0.5).astype(np.float32)
+    dsp = "max_bin=%d is_pre_partition=True bin_construct_sample_cnt=200000 num_threads=0" % max_bin
+    ds = capi.Dataset.from_mat(X, dsp).set_field("label", y)
+    ods = O.OracleDataset(X, dsp).set_field("label", y)
+    infos = [ds.feature_info(f) for f in range(8)]
+    assert max(i["num_bin"] for i in infos) > 256 and infos[3]["num_bin"] <= 256
+    for f in range(8):
+        assert infos[f] == ods.feature_info(f)
+        assert ds.upper_bounds(f).tobytes() == ods.upper_bounds(f).tobytes()
+    assert np.array_equal(ds.get_bins16(), ods.bins16())
+    params = ("objective=binary boosting_type=gbdt num_leaves=31 learning_rate=0.1 min_data_in_leaf=20 min_sum_hessian_in_leaf=0.001 verbosity=-1 "
+              "max_bin=%d is_unbalance=false" % max_bin)
+    b = capi.Booster(ds, params)
+    ob = O.OracleBooster(ods, params)
+    for _ in range(8):
+        assert b.update_one_iter() == ob.update()
+    m = parse_model(b.save_model_to_string())
+    compare_models(m, parse_model(ob.model_string()))
+    used = np.concatenate([t["split_feature"] for t in m["trees"] if t["num_leaves"] > 1])
+    assert {0, 1, 2} <= set(used.tolist()), "wide numerical features must actually be split on"
+    np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(b.predict_device(X[:300], predict_type=capi.PREDICT_RAW_SCORE)[:, 0], ob.predict_raw(X[:300])[:, 0], rtol=1e-9, atol=1e-9)
