@@ -544,8 +544,9 @@ def main():
             "dtype": "int64 fixed-point histograms over u8 bins%s (fp32 gradients, fp64 split gains)" % (" + u16 bins of the wide categorical features" if cfg["kind"] == KIND_MULTI else ""),
             "data": "synthetic", "config": config,
             "hist_rows_x_feats_per_sec": hist_rows_all * F / (hist_ms / 1000.0) if hist_ms > 0 else None,
-            "histogram_reduce": ("fused reduce-scatter+scan over NVLink peer memory (k_scan_dp)" if binfo["fused_peer_reduce"] else
-                                 ("ncclAllReduce int64" if world > 1 else "none (1 rank)")),
+            "histogram_reduce": ("none (1 rank)" if world == 1 else
+                                 {0: "ncclAllReduce int64", 1: "fused reduce-scatter+scan over NVLink peer memory (k_scan_dp)",
+                                  2: "two-shot all-reduce kernel over NVLink peer memory (k_allreduce_p2p)"}[binfo["reduce_mode"]]),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"], "clocks": clocks,
             "dataset_build_s": build_s}
     line.update(checks)

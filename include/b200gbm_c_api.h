@@ -195,7 +195,8 @@ int B200GBM_BoosterGetScores(BoosterHandle handle, int data_idx, double* out);  
  * NULL) = CUDA-event time.  Replaces the per-row UDF calls of LightGBMBooster.scala:390-423,528-545 for whole partitions. */
 int B200GBM_BoosterPredictForMatDevice(BoosterHandle handle, const void* data, int data_type, int64_t nrow, int32_t ncol, int predict_type,
                                        int start_iteration, int num_iteration, int64_t* out_len, double* out_result, double* elapsed_ms);
-/* out = {num_machines, rank, fused_peer_reduce (1 = K5 reduces over NVLink peer memory, 0 = NCCL allreduce), constant_hessian} */
+/* out = {num_machines, rank, histogram reduce mode (0 = ncclAllReduce, 1 = reduce-scatter + scan of the owned feature slice over NVLink
+ * peer memory, 2 = two-shot all-reduce kernel over peer memory + replicated scan), constant_hessian} */
 int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4);
 
 #ifdef __cplusplus

@@ -1201,7 +1201,7 @@ void Booster::InitTraining() {
     if (smem > 200 * 1024) Fatal("a query group is too large for the lambdarank kernel");
     B200_CUDA(cudaFuncSetAttribute(k_grad_lambdarank, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem, 1024))));
   }
-  if (parallel_ && !train->has_categorical) SetupPeerReduce();
+  if (parallel_) SetupPeerReduce();
   // ColSampler: one draw at init, then one per tree ([UPSTREAM] ColSampler::SetTrainingData / ResetByTree)
   col_rand_ = LcgRandom(cfg.feature_fraction_seed);
   feature_used_host_.assign(train->nf_pad, 0);
@@ -1367,14 +1367,16 @@ void Booster::SetupPeerReduce() {
   const char* env = std::getenv("B200GBM_FUSED_REDUCE");
   const int R = Net().world, me = Net().rank;
   mailbox_.Alloc(static_cast<size_t>(kMaxPeers) * 2); mailbox_.Zero(stream_);
-  peer_flags_.Alloc(32); peer_flags_.Zero(stream_);
+  peer_flags_.Alloc(64); peer_flags_.Zero(stream_);      // [0,16) "histogram ready" epochs by rank, [16,32) "second barrier" epochs, [48] block ticket
   peer_error_.Alloc(1); peer_error_.Zero(stream_);
   B200_CUDA(cudaStreamSynchronize(stream_));
   PeerInfo mine{};
   mine.pid = static_cast<long long>(getpid()); mine.device = device_;
   // Default = NCCL: measured on 8xB200 (100M x 512, profiles/r01_fused_vs_nccl_8gpu.md) the in-switch ncclAllReduce of the 2 MB
   // histogram is ~3 % faster end to end than the fused peer-memory reduce-scatter (two cross-GPU flag barriers per split).
-  mine.ok = (R <= kMaxPeers && env && std::atoi(env) == 1) ? 1 : 0;
+  int mode = env ? std::atoi(env) : 0;      // 0 NCCL, 1 fused reduce-scatter + scan of the owned slice, 2 two-shot P2P all-reduce + replicated scan
+  if (mode == 1 && train->has_categorical) mode = 0;      // the fused scan handles numerical tile features only (same decision on every rank)
+  mine.ok = (R <= kMaxPeers && (mode == 1 || mode == 2)) ? 1 : 0;
   void* bufs[3] = {H_.p, mailbox_.p, peer_flags_.p};
   for (int i = 0; i < 3; ++i) {
     mine.ptr[i] = reinterpret_cast<unsigned long long>(bufs[i]);
@@ -1416,7 +1418,10 @@ void Booster::SetupPeerReduce() {
   // every rank must take the same path: agree on `ok`
   double okd = ok ? 1.0 : 0.0;
   AllReduceHost(&okd, 1, ncclMin, stream_);
-  fused_ = okd > 0.5;
+  const bool peers_ok = okd > 0.5;
+  fused_ = peers_ok && mode == 1;
+  p2p_allreduce_ = peers_ok && mode == 2;
+  if (p2p_allreduce_) { pt.rank = me; pt.world = R; pt.feat0 = 0; pt.feat1 = 0; pt.error = peer_error_.p; peers_ = pt; return; }
   if (!fused_) return;
   const int tiles_per_rank = (train->num_tiles + R - 1) / R;
   pt.rank = me; pt.world = R;
@@ -1663,7 +1668,14 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       k_pick_dp<<<1, 256, 0, s>>>(ctrl, leaves_.p, d.meta.p, cands_.p, sp_, peers_, epoch_);
       mark();
     } else {
-      if (parallel_) B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
+      if (p2p_allreduce_) {       // C2 as one kernel over NVLink peer memory (k_allreduce_p2p)
+        ++epoch_;
+        const int agrid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(64, slot_elems_ / 2 / Net().world / 256 + 1)));
+        k_allreduce_p2p<<<agrid, 256, 0, s>>>(ctrl, peers_, slot_elems_, epoch_, peer_flags_.p + 48);
+        timing.launches += 1;
+      } else if (parallel_) {
+        B200_NCCL(ncclAllReduce(H_.p, H_.p, slot_elems_, ncclInt64, ncclSum, Net().comm, s));   // C2
+      }
       mark();
       if (d.nw > 0) {
         k_scan_wide<<<dim3(d.nw, 2), 256, kWideMaxBins * 10, s>>>(ctrl, leaves_.p, d.wide_meta.p, H_.p, pool_.p, slot_elems_, flags_.p, cands_.p, sp_);
@@ -1709,7 +1721,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     for (auto e : evs) cudaEventDestroy(e);
   }
   timing.hist_rows += ctrl_host_->trace_rows;
-  if (fused_) {
+  if (fused_ || p2p_allreduce_) {
     int err = 0;
     B200_CUDA(cudaMemcpy(&err, peer_error_.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (err) Fatal("data-parallel training: a peer rank stopped responding (peer-memory barrier timed out)");

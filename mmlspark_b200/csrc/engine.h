@@ -162,7 +162,7 @@ class Booster {
   // Returns the number of doubles written to `out` (host).  last_predict_ms = kernel time (CUDA events), incl. H2D for host input.
   int64_t PredictBatch(const void* data, int data_type, int64_t nrow, int ncol, int predict_type, int start_iteration, int num_iteration, double* out);
   double last_predict_ms = 0.0;
-  void GetInfo(int* out4) const { out4[0] = parallel_ ? Net().world : 1; out4[1] = parallel_ ? Net().rank : 0; out4[2] = fused_ ? 1 : 0; out4[3] = const_hessian_ ? 1 : 0; }
+  void GetInfo(int* out4) const { out4[0] = parallel_ ? Net().world : 1; out4[1] = parallel_ ? Net().rank : 0; out4[2] = fused_ ? 1 : (p2p_allreduce_ ? 2 : 0); out4[3] = const_hessian_ ? 1 : 0; }
   std::string SaveModelToString(int start_iteration, int num_iteration, int importance_type) const;
   std::string DumpModelJson(int start_iteration, int num_iteration) const;
 
@@ -270,6 +270,7 @@ class Booster {
   int lr_max_q_ = 0;
   // fused data-parallel reduce (peer memory over NVLink); falls back to NCCL when peers cannot map each other
   bool fused_ = false;
+  bool p2p_allreduce_ = false;          // B200GBM_FUSED_REDUCE=2: the per-split histogram all-reduce is k_allreduce_p2p instead of ncclAllReduce
   PeerTables peers_{};
   DevBuf<SplitCand> mailbox_;
   DevBuf<unsigned> peer_flags_;

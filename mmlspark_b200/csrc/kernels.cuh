@@ -1106,6 +1106,54 @@ k_scan_dp(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leave
   if (lane == 0) cands[which * p.nf_pad + u] = out;
 }
 
+// ---------------------------------------------------------------- C2 as ONE kernel: two-shot all-reduce over NVLink peer memory
+// B200GBM_FUSED_REDUCE=2.  The histogram all-reduce of a split is 2-4 MB of int64 — far below the size where NCCL's ring / tree protocols
+// pay off; ncclAllReduce costs ~50 us of launch + protocol latency per split at 8 ranks.  Here every rank runs this kernel on its own stream:
+//   barrier A  "my scratch histogram is complete" -> flag in every peer's flag block; wait for all peers
+//   shot 1     rank r sums slice r (1/world of the histogram) over all peers' scratch histograms with 16-byte P2P loads ...
+//   shot 2     ... and stores the sums into slice r of EVERY peer's scratch histogram (nobody else touches slice r)
+//   barrier B  raised by the block that finishes last; the kernel does not return before all peers raised theirs, so the scan that follows
+//              in stream order sees the complete reduced histogram.  Exact int64 sums: identical bits on every rank.
+__global__ void __launch_bounds__(256)
+k_allreduce_p2p(const TreeCtrl* __restrict__ ctrl, PeerTables pt, size_t elems, unsigned epoch, unsigned* __restrict__ ticket) {
+  __shared__ int s_last;
+  if (!ctrl->go) return;                 // same decision on every rank (global counts); nothing was built
+  if (blockIdx.x == 0 && threadIdx.x < pt.world) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(&pt.flags[threadIdx.x][pt.rank]) = epoch;
+  }
+  if (threadIdx.x == 0) peer_wait(pt.flags[pt.rank], pt.world, epoch, pt.error);
+  __syncthreads();
+  const size_t n2 = elems / 2;                                   // longlong2 units
+  const size_t per = (n2 + pt.world - 1) / pt.world;
+  const size_t lo = per * pt.rank, hi = min(lo + per, n2);
+  for (size_t i = lo + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < hi; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    long long sx = 0, sy = 0;
+    for (int r0 = 0; r0 < pt.world; r0 += 4) {                   // 4 peers in flight: the NVLink round trips overlap
+      long long vx[4], vy[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = min(r0 + rr, pt.world - 1);
+        asm volatile("ld.volatile.global.v2.s64 {%0, %1}, [%2];\n" : "=l"(vx[rr]), "=l"(vy[rr]) : "l"(pt.H[r] + i * 2));
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) if (r0 + rr < pt.world) { sx += vx[rr]; sy += vy[rr]; }
+    }
+    for (int r = 0; r < pt.world; ++r)
+      asm volatile("st.volatile.global.v2.s64 [%0], {%1, %2};\n" ::"l"(const_cast<long long*>(pt.H[r]) + i * 2), "l"(sx), "l"(sy) : "memory");
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence_system();
+  if (threadIdx.x < pt.world) *reinterpret_cast<volatile unsigned*>(&pt.flags[threadIdx.x][16 + pt.rank]) = epoch;
+  if (threadIdx.x == 0) peer_wait(pt.flags[pt.rank] + 16, pt.world, epoch, pt.error);
+  __syncthreads();
+}
+
 // leaf choice by warp 0: ArgMax over leaves with SplitInfo::operator> (gain desc, real feature asc, first index), stop on gain <= 0
 
 // argmax over features per leaf (gain desc, real feature index asc), then over leaves

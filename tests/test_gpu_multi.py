@@ -76,9 +76,11 @@ def run_ranks(X, y, rank_rows, params, iters, base_port, weight=None, push_chunk
     return out
 
 
-@pytest.mark.parametrize("objective,R,fused", [("regression", 2, 0), ("binary", 2, 0), ("binary", 2, 1), ("binary", 4, 0), ("regression", 4, 1)])
+@pytest.mark.parametrize("objective,R,fused", [("regression", 2, 0), ("binary", 2, 0), ("binary", 2, 1), ("binary", 2, 2), ("regression", 2, 2),
+                                               ("binary", 4, 0), ("regression", 4, 1), ("binary", 4, 2)])
 def test_data_parallel_matches_oracle_emulation(built, objective, R, fused, monkeypatch):
-    """fused=1 selects the reduce-scatter + scan over NVLink peer memory (k_scan_dp / k_pick_dp) instead of ncclAllReduce."""
+    """fused=1 selects the reduce-scatter + scan over NVLink peer memory (k_scan_dp / k_pick_dp) instead of ncclAllReduce, fused=2 the
+    two-shot all-reduce kernel over peer memory (k_allreduce_p2p) followed by the replicated scan."""
     if _ngpu() < R:
         pytest.skip("needs %d GPUs" % R)
     monkeypatch.setenv("B200GBM_FUSED_REDUCE", str(fused))
@@ -92,7 +94,7 @@ def test_data_parallel_matches_oracle_emulation(built, objective, R, fused, monk
     y = (s > 0).astype(np.float32) if objective == "binary" else s.astype(np.float32)
     rank_rows = [n // R + (7 if r == 0 else 0) - (7 if r == R - 1 else 0) for r in range(R)]     # unequal shards
     params = _params(objective, R, "is_unbalance=false" if objective == "binary" else "")
-    res = run_ranks(X, y, rank_rows, params, 15, 23000 + 20 * R + 7 * fused + (0 if objective == "binary" else 3))
+    res = run_ranks(X, y, rank_rows, params, 15, 23000 + 40 * R + 9 * fused + (0 if objective == "binary" else 3))
     ods = O.OracleDataset(X, DS_PARAMS, rank_rows=rank_rows).set_field("label", y)
     ob = O.OracleBooster(ods, params)
     ob.train(15)
