@@ -92,6 +92,7 @@ struct TreeCtrl {
   int q_side;                  // (unused since the fused partition kernel decides the side itself)
   unsigned part_barrier;       // k_partition: grid-barrier arrive counter (reset by its last block)
   unsigned part_ticket;        // k_partition: finished-block ticket (the last block runs the next round's controller)
+  unsigned part_next[2];       // k_partition: next chunk of phase 1 / phase 3 (dynamic hand-out; reset by its last block)
   int split_wide;              // wide index (inner feature - nfn) of the split feature, or -1
   int split_cat_list_len;
   unsigned short split_cat_list[kCatListMax];
@@ -1289,6 +1290,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
   __shared__ int s_cnt[8];
   __shared__ int s_copy[2];
   __shared__ int s_last;
+  __shared__ int s_chunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ---- phase 0: H := 0 (16-byte stores; H is L2-resident)
   {
@@ -1313,7 +1315,13 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     const int chunks = (n + kPartChunk - 1) / kPartChunk;
     // ---- phase 1 (no block-wide barrier: every warp adds the left count of its 256 rows to the chunk's counter, which the tail of
     // the previous partition kernel left at zero)
-    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+    // chunks are handed out dynamically (one atomic per chunk): the rows' DRAM latency varies, and the grid barrier waits for the slowest block
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_chunk = static_cast<int>(atomicAdd(&ctrl->part_next[0], 1u));
+      __syncthreads();
+      const int c = s_chunk;
+      if (c >= chunks) break;
       int local = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -1382,7 +1390,12 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     const int lc = p.parallel ? bsp.left_count : total_left, rc = p.parallel ? bsp.right_count : n - total_left;
     const bool q_left = lc < rc;
     // ---- phase 3
-    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_chunk = static_cast<int>(atomicAdd(&ctrl->part_next[1], 1u));
+      __syncthreads();
+      const int c = s_chunk;
+      if (c >= chunks) break;
       const int wbase = c * (kPartChunk / 32);     // 64 ballot words per chunk; word w covers rows c*2048 + w*32 ..
       if (threadIdx.x < 64) {
         const int i0 = c * kPartChunk + threadIdx.x * 32;
@@ -1430,7 +1443,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (threadIdx.x == 0) { ctrl->part_ticket = 0u; ctrl->part_barrier = 0u; }
+    if (threadIdx.x == 0) { ctrl->part_ticket = 0u; ctrl->part_barrier = 0u; ctrl->part_next[0] = 0u; ctrl->part_next[1] = 0u; }
     if (n > 0) for (int c = threadIdx.x; c < (n + kPartChunk - 1) / kPartChunk; c += blockDim.x) chunk_left[c] = 0;      // phase 1 of the next launch accumulates into zeros
     d_round_ctl(ctrl, leaves, tree, flags, meta, p, last, s_copy);
   }

@@ -209,7 +209,8 @@ def test_numerical_max_bin_above_255(built, max_bin):
     for _ in range(8):
         assert b.update_one_iter() == ob.update()
     m = parse_model(b.save_model_to_string())
-    compare_models(m, parse_model(ob.model_string()))
+    # feature 1's NaN rows are separated early, so deeper nodes on it sit in NaN-free leaves where the scan direction is a rounding tie
+    compare_models(m, parse_model(ob.model_string()), allow_nan_direction_ties=True)
     used = np.concatenate([t["split_feature"] for t in m["trees"] if t["num_leaves"] > 1])
     assert {0, 1, 2} <= set(used.tolist()), "wide numerical features must actually be split on"
     np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=1e-9, atol=1e-9)

@@ -16,9 +16,10 @@ except Exception as e: print('$name failed', e)
 PY
 }
 run nccl B200GBM_FUSED_REDUCE=0
+run p2p B200GBM_FUSED_REDUCE=2
 run fused B200GBM_FUSED_REDUCE=1
 STEPS=3 run nccl_split_timing B200GBM_FUSED_REDUCE=0 B200GBM_SPLIT_TIMING=1
 grep -h "split timing" gpurun_out/r2s8_nccl_split_timing.err | head -2 | cut -c1-500
-STEPS=3 run fused_split_timing B200GBM_FUSED_REDUCE=1 B200GBM_SPLIT_TIMING=1
-grep -h "split timing" gpurun_out/r2s8_fused_split_timing.err | head -2 | cut -c1-500
+STEPS=3 run p2p_split_timing B200GBM_FUSED_REDUCE=2 B200GBM_SPLIT_TIMING=1
+grep -h "split timing" gpurun_out/r2s8_p2p_split_timing.err | head -2 | cut -c1-500
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -rs -k "4" > gpurun_out/r2s8_pytest_4rank.log 2>&1; tail -4 gpurun_out/r2s8_pytest_4rank.log
