@@ -497,6 +497,7 @@ def main():
     else:
         wall_ms, ingest_ms_max, hist_ms, hist_rows_all = wall * 1000.0, ingest_ms, tm["hist_ms"], float(tm["hist_rows"])
         hashes = [mhash]
+    split_timing = os.environ.get("B200GBM_SPLIT_TIMING") is not None
     if rank != 0:
         if world > 1:
             capi.network_free()
@@ -551,6 +552,8 @@ def main():
             "dataset_build_s": build_s}
     line.update(checks)
     print(json.dumps(line))
+    if split_timing:
+        bst.free()          # the per-operation breakdown of the TIMED booster (rank 0) goes to stderr when it is freed
     if world > 1:
         capi.network_free()
 

@@ -895,7 +895,7 @@ static size_t LambdarankSmem(int max_q, int truncation) {
   return static_cast<size_t>(max_q) * (8 + 8 + 4 + 4 + 4 + 4) + 8 + static_cast<size_t>(truncation) * (lr_tile(truncation) + 1) * 8;
 }
 static size_t Align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
-constexpr int kScanSmem = 8 * (768 + 64) * 8;     // k_scan: per-warp scratch of the categorical split search
+constexpr int kScanSmem = (768 + 64) * 8;         // k_scan: scratch of the categorical split search (one warp per block runs it)
 
 Booster::Booster(const std::string& model_text) {
   std::unique_ptr<HostModel> m = HostModel::FromString(model_text);
@@ -1620,7 +1620,7 @@ void Booster::TrainOneTree(int k, HostTree* out) {
   nvtxRangePop();
   timing.launches += 4;
   const int pgrid = std::max(1, std::min(n / kPartChunk + 1, part_max_blocks_));
-  const dim3 sgrid(std::max(1, (d.nfn + 7) / 8), 2);      // tile features; the pick step in its last block also sees the wide features' candidates
+  const dim3 sgrid(std::max(1, d.nfn), 2);      // one block per (leaf, tile feature); the pick step in the last block also sees the wide features' candidates
   std::vector<cudaEvent_t> evs;
   // B200GBM_SPLIT_TIMING=1 (debug): an event after every operation of a split; per-operation averages go to stderr when the booster is freed
   static const bool split_timing = getenv("B200GBM_SPLIT_TIMING") != nullptr;

@@ -946,72 +946,6 @@ k_pick(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, con
   d_pick_block(ctrl, leaves, meta, cands, p);
 }
 
-__device__ __forceinline__ void
-d_scan_one(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const long long* __restrict__ H, long long* __restrict__ pool,
-           size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* cands, const SplitParams& p, int which, int leaf, int u, int lane, int warp);
-
-__global__ void __launch_bounds__(256)
-k_scan(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta,
-       const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
-       SplitCand* cands, SplitParams p) {
-  const int which = blockIdx.y;
-  const int leaf = which ? ctrl->larger : ctrl->smaller;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int u = blockIdx.x * 8 + warp;
-  if (ctrl->go && leaf >= 0 && u < p.nfn) d_scan_one(ctrl, leaves, meta, H, pool, slot_elems, flags, cands, p, which, leaf, u, lane, warp);
-  // the block that finishes last picks the best candidate per leaf and the next leaf to split (was a separate kernel)
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned t = atomicAdd(&ctrl->scan_ticket, 1u);
-    s_last = (t == gridDim.x * gridDim.y - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    d_pick_block(ctrl, leaves, meta, cands, p);
-    if (threadIdx.x == 0) ctrl->scan_ticket = 0u;
-  }
-}
-
-__device__ __forceinline__ void
-d_scan_one(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const long long* __restrict__ H, long long* __restrict__ pool,
-           size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* cands, const SplitParams& p, int which, int leaf, int u, int lane, int warp) {
-  SplitCand out;
-  out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
-  out.l2_extra = 0; out.is_cat = 0; out.cat_list_len = 0;
-  for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
-  uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
-  if (!*flag) { if (lane == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); } return; }
-
-  const LeafState& L = leaves[leaf];
-  long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
-  const long long* src = H + static_cast<size_t>(u) * 512;
-  long long qg[8], qh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int b = lane * 8 + j;
-    longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
-    if (which) {
-      longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2);
-      s.x = pr.x - s.x; s.y = pr.y - s.y;
-    }
-    *reinterpret_cast<longlong2*>(dst + b * 2) = s;
-    qg[j] = s.x; qh[j] = s.y;
-  }
-  if (meta[u].is_categorical) {
-    extern __shared__ double scan_ws[];      // 8 warps x (3*256 doubles + 2*256 bytes)
-    d_scan_feature_cat(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out, scan_ws + warp * (768 + 64));
-  } else {
-    d_scan_feature(qg, qh, lane, meta[u], L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
-  }
-  if (lane == 0) {
-    cands[which * p.nf_pad + u] = out;
-    __threadfence();       // visible to the block that runs the pick step
-  }
-}
-
 // ---------------------------------------------------------------- fused data-parallel reduce + scan (C2 + K5 + C3)
 // Replaces  K4 -> ncclAllReduce(histogram) -> K5  by LightGBM's reduce-scatter scheme executed over NVLink peer
 // memory inside the scan kernel: rank r owns a contiguous slice of feature tiles; after a flag barrier ("all local
@@ -1814,6 +1748,66 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
   }
   cands[which * p.nf_pad + u] = out;
   __threadfence();
+}
+
+// ---------------------------------------------------------------- K5/K6 for the tile features: one BLOCK per (smaller|larger, feature)
+// Thread t = bin t.  The block reduces the feature into the leaf's pool slot (larger child: parent - smaller, exact int64), then runs the
+// same block-wide two-pass scan as the wide numerical features (d_scan_wide_numeric with one bin per thread: exclusive block scans of
+// (g, h, count), one candidate per thread and direction, block argmax with the sequential tie-breaks) — the dependent chain of software
+// fp64 divisions per thread is 2 long instead of 16 as in the round-1 warp-per-feature scan, and the code is shared and small (the old
+// kernel was instruction-fetch bound).  Categorical tile features keep the warp-level search (d_scan_feature_cat) on warp 0.  The block that
+// finishes last picks the best candidate per leaf and the next leaf to split.
+__global__ void __launch_bounds__(256, 4)
+k_scan(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta,
+       const long long* __restrict__ H, long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags,
+       SplitCand* cands, SplitParams p) {
+  const int which = blockIdx.y;
+  const int leaf = which ? ctrl->larger : ctrl->smaller;
+  const int u = blockIdx.x;
+  if (ctrl->go && leaf >= 0 && u < p.nfn) {
+    SplitCand out;
+    out.gain = kNegInf; out.left_g = 0; out.left_h = 0; out.threshold = 0; out.left_count = 0; out.default_left = 1; out.feature = u;
+    out.l2_extra = 0; out.is_cat = 0; out.cat_list_len = 0;
+    for (int wd = 0; wd < 8; ++wd) out.cat_bits[wd] = 0u;
+    uint8_t* flag = &flags[static_cast<size_t>(leaf) * p.nf_pad + u];
+    if (*flag) {
+      const LeafState& L = leaves[leaf];
+      const FeatMeta fm = meta[u];
+      long long* dst = pool + static_cast<size_t>(L.hist_slot) * slot_elems + static_cast<size_t>(u) * 512;
+      const long long* src = H + static_cast<size_t>(u) * 512;
+      {
+        const int b = threadIdx.x;
+        longlong2 sv = *reinterpret_cast<const longlong2*>(src + b * 2);
+        if (which) { const longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2); sv.x = pr.x - sv.x; sv.y = pr.y - sv.y; }
+        *reinterpret_cast<longlong2*>(dst + b * 2) = sv;
+      }
+      __syncthreads();      // the scan reads bins other threads of this block reduced
+      if (!fm.is_categorical) {
+        const WideMeta wm{fm.num_bin, 0, 0, 0, fm.default_bin, fm.missing_type, fm.real_index, 0, fm.offset, 0, 0, 0};
+        d_scan_wide_numeric(dst, wm, L, ctrl->inv_g, ctrl->inv_h, p, flag, &out);
+      } else if (threadIdx.x < 32) {
+        extern __shared__ double scan_ws[];      // (3*256 doubles + 2*256 bytes) of scratch for the categorical search
+        long long qg[8], qh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int b = threadIdx.x * 8 + j; qg[j] = dst[b * 2]; qh[j] = dst[b * 2 + 1]; }
+        d_scan_feature_cat(qg, qh, threadIdx.x, fm, L, ctrl->inv_g, ctrl->inv_h, p, flag, &out, scan_ws);
+      }
+    }
+    if (threadIdx.x == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); }      // visible to the block that runs the pick step
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctrl->scan_ticket, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    d_pick_block(ctrl, leaves, meta, cands, p);
+    if (threadIdx.x == 0) ctrl->scan_ticket = 0u;
+  }
 }
 
 // ---------------------------------------------------------------- K8/K9 leaf values -> scores

@@ -25,6 +25,15 @@ def dataset(seed, n, F):
     return X, s
 
 
+def variant(X, name):
+    """per-case feature matrix: cases named *widecat* get a high-cardinality categorical column 9 (hundreds of bins: the uint16 path)"""
+    if "widecat" not in name:
+        return X
+    X2 = X.copy()
+    X2[:, 9] = np.floor(np.abs(X[:, 9]) * 173.0) % 450.0
+    return X2
+
+
 def main():
     out = {}
     out["lcg_sample"] = {"%d_%d_%d" % (s, n, k): O.random_sample(s, n, k).tolist() for s, n, k in [(1, 20, 5), (1, 100, 80), (7, 1000, 10), (1, 50, 50)]}
@@ -50,11 +59,17 @@ def main():
         ("regression_quantile", "objective=quantile alpha=0.7 num_leaves=7 min_data_in_leaf=20 verbosity=-1 learning_rate=0.3", s.astype(np.float32)),
         ("regression_categorical|categorical_feature=4", "objective=regression num_leaves=7 min_data_in_leaf=20 verbosity=-1 min_data_per_group=50 cat_smooth=5",
          s.astype(np.float32)),
+        # round 2: one-vs-all multiclass, cross-entropy on {0,1} labels, a categorical feature with more than 256 bins
+        ("multiclass_ova", "objective=multiclassova num_class=3 num_leaves=5 learning_rate=0.1 min_data_in_leaf=20 verbosity=-1 sigmoid=1.0",
+         np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)),
+        ("binary_xentropy", "objective=cross_entropy num_leaves=7 learning_rate=0.1 min_data_in_leaf=20 verbosity=-1", (s > 0).astype(np.float32)),
+        ("regression_widecat|categorical_feature=9", "objective=regression num_leaves=7 min_data_in_leaf=20 verbosity=-1 min_data_per_group=20 cat_smooth=2 min_data_in_bin=1",
+         s.astype(np.float32)),
     ]:
-        d = O.OracleDataset(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", y)
+        d = O.OracleDataset(variant(X, name), DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", y)
         b = O.OracleBooster(d, params)
         b.train(5)
-        models[name] = {"params": params, "model": b.model_string(), "raw_pred_first8": b.predict_raw(X[:8]).tolist()}
+        models[name] = {"params": params, "model": b.model_string(), "raw_pred_first8": b.predict_raw(variant(X, name)[:8]).tolist()}
     out["models"] = models
     # one hand-checkable split: 4 bins, constant hessian
     hist = np.zeros((256, 2)); hist[0] = [-30, 30]; hist[1] = [-10, 30]; hist[2] = [10, 30]; hist[3] = [40, 30]

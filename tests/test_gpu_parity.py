@@ -556,13 +556,14 @@ def test_cuda_path_reproduces_committed_golden_models(built):
     labels = {"regression": s.astype(np.float32), "binary": (s > 0).astype(np.float32), "multiclass": np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)}
     assert len(golden) >= 7
     for name, g in golden.items():
-        ds = capi.Dataset.from_mat(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else ""))
+        Xc = mg.variant(X, name)
+        ds = capi.Dataset.from_mat(Xc, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else ""))
         ds.set_field("label", labels[name.split("_")[0].split("|")[0]])
         b = capi.Booster(ds, g["params"])
         for _ in range(5):
             b.update_one_iter()
         compare_models(parse_model(b.save_model_to_string()), parse_model(g["model"]))
-        raw = b.predict_for_mat(X[:8], predict_type=1).reshape(8, -1)
+        raw = b.predict_for_mat(Xc[:8], predict_type=1).reshape(8, -1)
         np.testing.assert_allclose(raw, np.array(g["raw_pred_first8"]).reshape(8, -1), rtol=1e-5, atol=1e-7)
 
 

@@ -211,11 +211,12 @@ def test_golden_models(O):
     labels = {"regression": s.astype(np.float32), "binary": (s > 0).astype(np.float32), "multiclass": np.clip(np.floor(s + 1.5), 0, 2).astype(np.float32)}
     from mmlspark_b200.modeltext import parse_model, compare_models
     for name, g in GOLDEN["models"].items():
-        d = O.OracleDataset(X, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", labels[name.split("_")[0].split("|")[0]])
+        Xc = mg.variant(X, name)
+        d = O.OracleDataset(Xc, DS_PARAMS + (" " + name.split("|")[1] if "|" in name else "")).set_field("label", labels[name.split("_")[0].split("|")[0]])
         b = O.OracleBooster(d, g["params"])
         b.train(5)
         compare_models(parse_model(b.model_string()), parse_model(g["model"]), value_tol=1e-12, gain_tol=1e-6)
-        np.testing.assert_allclose(b.predict_raw(X[:8]), np.array(g["raw_pred_first8"]), rtol=1e-12)
+        np.testing.assert_allclose(b.predict_raw(Xc[:8]), np.array(g["raw_pred_first8"]), rtol=1e-12)
 
 
 def test_training_scores_equal_model_predictions_and_loss_decreases(O):
