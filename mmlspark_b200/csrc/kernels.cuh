@@ -885,58 +885,56 @@ __device__ __forceinline__ SplitCand d_load_cand(const SplitCand* c) {
   for (int i = 0; i < static_cast<int>(sizeof(SplitCand) / 8); ++i) dst[i] = __ldcg(src + i);
   return out;
 }
-// best candidate per leaf (argmax over features, ties -> smaller real feature index), then the leaf to split; one 256-thread block
+// best candidate per leaf (argmax over features, ties -> smaller real feature index), then the leaf to split; one 256-thread block.
+// The two leaves of the round are handled side by side (threads 0..127: smaller, 128..255: larger) with warp-shuffle argmaxes — the
+// first version looped over the two leaves with an 8-step shared-memory tree each (18 block barriers) and ncu showed this serial tail
+// taking longer than the scan itself.  The order (gain desc, real feature index asc) is total, so any reduction shape picks the same winner.
 __device__ __noinline__ void
 d_pick_block(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, const SplitCand* cands, const SplitParams& p) {
-  __shared__ double s_gain[256];
-  __shared__ int s_feat[256], s_idx[256];
-  if (ctrl->go) {
-    for (int which = 0; which < 2; ++which) {
-      const int leaf = which ? ctrl->larger : ctrl->smaller;
-      if (leaf < 0) continue;
-      double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
-      for (int u = threadIdx.x; u < p.nf; u += blockDim.x) {
-        const double cg = __ldcg(&cands[which * p.nf_pad + u].gain);
-        const int rf = meta[u].real_index;
-        if (cg > bg || (cg == bg && rf < bf)) { bg = cg; bf = rf; bi = u; }
-      }
-      s_gain[threadIdx.x] = bg; s_feat[threadIdx.x] = bf; s_idx[threadIdx.x] = bi;
-      __syncthreads();
-      for (int s = 128; s; s >>= 1) {
-        if (threadIdx.x < s) {
-          double og = s_gain[threadIdx.x + s]; int of = s_feat[threadIdx.x + s];
-          if (og > s_gain[threadIdx.x] || (og == s_gain[threadIdx.x] && of < s_feat[threadIdx.x])) {
-            s_gain[threadIdx.x] = og; s_feat[threadIdx.x] = of; s_idx[threadIdx.x] = s_idx[threadIdx.x + s];
-          }
-        }
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        LeafState& L = leaves[leaf];
-        LeafBest b;
-        b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
-        b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0; b.cat_list_len = 0; b.pad = 0;
-        for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
-        if (s_idx[0] >= 0 && s_gain[0] > kNegInf) {
-          const SplitCand c = d_load_cand(&cands[which * p.nf_pad + s_idx[0]]);
-          b.cat_list_len = c.cat_list_len;
-          for (int k = 0; k < c.cat_list_len && k < kCatListMax; ++k) b.cat_list[k] = c.cat_list[k];
-          const double sum_h = L.sum_h + 2 * kEpsD;
-          b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
-          b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
-          b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
-          b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
-          SplitParams pc = p;
-          pc.l2 += c.l2_extra;
-          b.left_out = d_calc_output(c.left_g, c.left_h, pc);
-          b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, pc);
-          b.is_cat = c.is_cat;
-          for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = c.cat_bits[wd];
-        }
-        L.best = b;
-      }
-      __syncthreads();
+  __shared__ double s_gain[8];
+  __shared__ int s_feat[8], s_idx[8];
+  const int which = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int leaf = ctrl->go ? (which ? ctrl->larger : ctrl->smaller) : -1;
+  double bg = kNegInf; int bf = 0x7fffffff, bi = -1;
+  if (leaf >= 0) {
+    for (int u = t; u < p.nf; u += 128) {
+      const double cg = __ldcg(&cands[which * p.nf_pad + u].gain);
+      const int rf = meta[u].real_index;
+      if (cg > bg || (cg == bg && rf < bf)) { bg = cg; bf = rf; bi = u; }
     }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, bg, o);
+    const int of = __shfl_xor_sync(0xffffffffu, bf, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (og > bg || (og == bg && of < bf)) { bg = og; bf = of; bi = oi; }
+  }
+  if (lane == 0) { s_gain[warp] = bg; s_feat[warp] = bf; s_idx[warp] = bi; }
+  __syncthreads();
+  if (t == 0 && leaf >= 0) {
+    for (int w = which * 4; w < which * 4 + 4; ++w)
+      if (s_gain[w] > bg || (s_gain[w] == bg && s_feat[w] < bf)) { bg = s_gain[w]; bf = s_feat[w]; bi = s_idx[w]; }
+    LeafState& L = leaves[leaf];
+    LeafBest b;
+    b.gain = kNegInf; b.feature = -1; b.threshold = 0; b.default_left = 1; b.left_count = 0; b.right_count = 0;
+    b.left_g = b.left_h = b.right_g = b.right_h = b.left_out = b.right_out = 0; b.is_cat = 0; b.cat_list_len = 0; b.pad = 0;
+    for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = 0u;
+    if (bi >= 0 && bg > kNegInf) {
+      const SplitCand c = d_load_cand(&cands[which * p.nf_pad + bi]);
+      b.cat_list_len = c.cat_list_len;
+      for (int k = 0; k < c.cat_list_len && k < kCatListMax; ++k) b.cat_list[k] = c.cat_list[k];
+      const double sum_h = L.sum_h + 2 * kEpsD;
+      b.gain = c.gain; b.feature = c.feature; b.threshold = c.threshold; b.default_left = c.default_left;
+      b.left_count = c.left_count; b.right_count = L.global_count - c.left_count;
+      b.left_g = c.left_g; b.left_h = c.left_h - kEpsD;
+      b.right_g = L.sum_g - c.left_g; b.right_h = sum_h - c.left_h - kEpsD;
+      SplitParams pc = p;
+      pc.l2 += c.l2_extra;
+      b.left_out = d_calc_output(c.left_g, c.left_h, pc);
+      b.right_out = d_calc_output(L.sum_g - c.left_g, sum_h - c.left_h, pc);
+      b.is_cat = c.is_cat;
+      for (int wd = 0; wd < 8; ++wd) b.cat_bits[wd] = c.cat_bits[wd];
+    }
+    L.best = b;
   }
   __syncthreads();
   if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
