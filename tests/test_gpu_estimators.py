@@ -282,6 +282,33 @@ def test_classifier_all_boosting_types(built):
     assert "average_output" in _with_boosting(LightGBMClassifier(numIterations=3, numTasks=1), "rf").fit(df).getNativeModel()
 
 
+def test_multiclassova_classifier_and_high_cardinality_categorical_slots(built):
+    """objective=multiclassova (LightGBMParams.scala:296-300): one sigmoid per class from the native output transform (probabilities do
+    NOT sum to 1); categoricalSlotIndexes with a high-cardinality column (LightGBMBase.scala:168-199) takes the > 256-bin path, and a saved
+    model reloaded through loadNativeModelFromString predicts the same."""
+    from mmlspark_b200.lightgbm import Frame, LightGBMClassifier, LightGBMClassificationModel
+    rng = np.random.default_rng(17)
+    n, K = 40000, 3
+    cat = np.floor(2000.0 ** rng.random(n)) - 1                      # ~1000 distinct categories, log-uniform
+    eff = rng.standard_normal(2000)
+    X = np.column_stack([rng.standard_normal((n, 5)), cat])
+    s = X[:, 0] + 0.8 * eff[cat.astype(int)] + 0.3 * rng.standard_normal(n)
+    y = np.digitize(s, [-0.7, 0.7]).astype(np.float64)
+    df = Frame({"features": X, "label": y})
+    m = LightGBMClassifier(objective="multiclassova", numIterations=25, numLeaves=15, numTasks=1, categoricalSlotIndexes=[5]).fit(df)
+    out = m.transform(df)
+    p = out["probability"]
+    assert p.shape == (n, K) and (p > 0).all() and (p < 1).all()
+    assert np.abs(p.sum(axis=1) - 1.0).max() > 1e-3                  # independent sigmoids, not a softmax
+    np.testing.assert_allclose(p, 1.0 / (1.0 + np.exp(-out["rawPrediction"])), rtol=1e-9, atol=1e-12)
+    assert (out["prediction"] == y).mean() > 0.75
+    text = m.getNativeModel()
+    assert "objective=multiclassova num_class:3 sigmoid:1" in text
+    assert any(int(l.split("=")[1]) > 0 for l in text.split("\n") if l.startswith("num_cat=")), "expected splits on the categorical slot"
+    m2 = LightGBMClassificationModel.loadNativeModelFromString(text)
+    np.testing.assert_allclose(m2.transform(df)["probability"], p, rtol=1e-12)
+
+
 def test_multiclass_and_regressor_all_boosting_types(built):
     """VerifyLightGBMClassifier.scala:676-705 (multiclass sweep) and VerifyLightGBMRegressor.scala:188-207 (regression sweep)."""
     from mmlspark_b200.lightgbm import Frame, LightGBMClassifier, LightGBMRegressor
