@@ -1630,15 +1630,14 @@ __device__ __noinline__ void d_scan_wide_numeric(const long long* __restrict__ h
 }
 
 // Split search of a WIDE categorical feature (FeatureHistogram::FindBestThresholdCategoricalInner, many-vs-many branch): one block per
-// (smaller|larger, feature).  The histogram is reduced into the leaf's pool slot (parent - smaller for the larger child), the bins that
-// hold >= cat_smooth rows are sorted by g / (h + cat_smooth) with a block-wide bitonic sort over (ctr, bin) keys — the stable order of
-// the reference — and thread 0 accumulates from both ends exactly like the sequential code (at most max_cat_threshold bins each).
+// (smaller|larger, feature).  The histogram is reduced into the leaf's pool slot (parent - smaller for the larger child), the
+// max_cat_threshold smallest and largest ctr = g / (h + cat_smooth) among the bins that hold >= cat_smooth rows are selected in the
+// (ctr, bin) order of the reference's stable sort, and thread 0 accumulates from both ends exactly like the sequential code.
 __global__ void __launch_bounds__(256)
 k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ leaves, const WideMeta* __restrict__ wm, const long long* __restrict__ H,
             long long* __restrict__ pool, size_t slot_elems, uint8_t* __restrict__ flags, SplitCand* __restrict__ cands, SplitParams p) {
   extern __shared__ __align__(16) unsigned char sw_smem[];
-  double* s_key = reinterpret_cast<double*>(sw_smem);                          // [P]
-  unsigned short* s_id = reinterpret_cast<unsigned short*>(s_key + kWideMaxBins);   // [P]
+  double* s_key = reinterpret_cast<double*>(sw_smem);                          // [num_bin] ctr keys of the used bins, +inf otherwise
   __shared__ int s_used;
   const int which = blockIdx.y, w = blockIdx.x, u = p.nfn + w;
   const int leaf = which ? ctrl->larger : ctrl->smaller;
@@ -1668,60 +1667,107 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
     if (threadIdx.x == 0) { cands[which * p.nf_pad + u] = out; __threadfence(); }
     return;
   }
-  int P = 1;
-  while (P < m.num_bin) P <<= 1;
+  // ---- reduce into the pool slot and build the ctr keys (loads of 4 bins in flight per thread before the dependent stores)
   if (threadIdx.x == 0) s_used = 0;
   __syncthreads();
   int my_used = 0;
-  for (int b = threadIdx.x; b < P; b += blockDim.x) {
-    double key = __longlong_as_double(0x7ff0000000000000LL);      // +inf: unused bins and padding sort last
-    if (b < m.num_bin) {
-      longlong2 s = *reinterpret_cast<const longlong2*>(src + b * 2);
-      if (which) { const longlong2 pr = *reinterpret_cast<const longlong2*>(dst + b * 2); s.x = pr.x - s.x; s.y = pr.y - s.y; }
-      *reinterpret_cast<longlong2*>(dst + b * 2) = s;
-      const double g = static_cast<double>(s.x) * inv_g, h = static_cast<double>(s.y) * inv_h;
-      const int cnt = static_cast<int>(h * cnt_factor + 0.5);
-      if (b >= 1 && cnt >= p.cat_smooth) { key = g / (h + p.cat_smooth); ++my_used; }
+  const double kPosInf = __longlong_as_double(0x7ff0000000000000LL);      // unused bins: never selected
+  for (int b0 = threadIdx.x; b0 < m.num_bin; b0 += 4 * blockDim.x) {
+    longlong2 sv[4], pr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = b0 + q * blockDim.x;
+      if (b < m.num_bin) {
+        sv[q] = *reinterpret_cast<const longlong2*>(src + b * 2);
+        if (which) pr[q] = *reinterpret_cast<const longlong2*>(dst + b * 2);
+      }
     }
-    s_key[b] = key; s_id[b] = static_cast<unsigned short>(b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = b0 + q * blockDim.x;
+      if (b >= m.num_bin) continue;
+      longlong2 v = sv[q];
+      if (which) { v.x = pr[q].x - v.x; v.y = pr[q].y - v.y; }
+      *reinterpret_cast<longlong2*>(dst + b * 2) = v;
+      const double g = static_cast<double>(v.x) * inv_g, h = static_cast<double>(v.y) * inv_h;
+      const int cnt = static_cast<int>(h * cnt_factor + 0.5);
+      double key = kPosInf;
+      if (b >= 1 && cnt >= p.cat_smooth) { key = g / (h + p.cat_smooth); ++my_used; }
+      s_key[b] = key;
+    }
   }
   if (my_used) atomicAdd(&s_used, my_used);
   __syncthreads();
-  // bitonic sort ascending by (key, bin)
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const double a = s_key[i], c = s_key[ixj];
-          const unsigned short ia = s_id[i], ic = s_id[ixj];
-          const bool a_gt_c = (a > c) || (a == c && ia > ic);
-          const bool up = (i & k) == 0;
-          if (up ? a_gt_c : !a_gt_c) { s_key[i] = c; s_key[ixj] = a; s_id[i] = ic; s_id[ixj] = ia; }
+  const int used_bin = s_used;
+  const int max_num_cat = min(min(p.max_cat_threshold, kCatListMax), (used_bin + 1) / 2);
+  // ---- the reference sorts the used bins by (ctr, bin) and walks max_num_cat bins from either end; only those 2 * max_num_cat order
+  // statistics are needed, so instead of sorting thousands of keys (the first version's block-wide bitonic sort took ~600 us per launch)
+  // the block selects them one by one: round r = the smallest (largest) key beyond the previous round's, a strided scan of the keys in
+  // shared memory + a warp-shuffle / 8-entry reduction.  The (key, bin) order is total, so the selection equals the stable sort.
+  __shared__ unsigned short s_sel[2][kCatListMax];
+  __shared__ double s_selg[2][kCatListMax], s_selh[2][kCatListMax];
+  __shared__ double s_rk[8];
+  __shared__ int s_ri[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int side = 0; side < 2; ++side) {
+    double pk = side == 0 ? kNegInf : kPosInf;
+    int pi = side == 0 ? -1 : 0x7fffffff;
+    for (int r = 0; r < max_num_cat; ++r) {
+      double bk = side == 0 ? kPosInf : kNegInf;
+      int bi = side == 0 ? 0x7fffffff : -1;
+      for (int b = threadIdx.x; b < m.num_bin; b += blockDim.x) {
+        const double k = s_key[b];
+        if (!(k < kPosInf)) continue;
+        if (side == 0) {
+          if ((k > pk || (k == pk && b > pi)) && (k < bk || (k == bk && b < bi))) { bk = k; bi = b; }
+        } else {
+          if ((k < pk || (k == pk && b < pi)) && (k > bk || (k == bk && b > bi))) { bk = k; bi = b; }
         }
       }
+      for (int o = 16; o; o >>= 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool take = side == 0 ? (oi != 0x7fffffff && (bi == 0x7fffffff || ok < bk || (ok == bk && oi < bi)))
+                                    : (oi != -1 && (bi == -1 || ok > bk || (ok == bk && oi > bi)));
+        if (take) { bk = ok; bi = oi; }
+      }
+      if (lane == 0) { s_rk[warp] = bk; s_ri[warp] = bi; }
       __syncthreads();
+      bk = s_rk[0]; bi = s_ri[0];
+      for (int w2 = 1; w2 < 8; ++w2) {
+        const double ok = s_rk[w2];
+        const int oi = s_ri[w2];
+        const bool take = side == 0 ? (oi != 0x7fffffff && (bi == 0x7fffffff || ok < bk || (ok == bk && oi < bi)))
+                                    : (oi != -1 && (bi == -1 || ok > bk || (ok == bk && oi > bi)));
+        if (take) { bk = ok; bi = oi; }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_sel[side][r] = static_cast<unsigned short>(bi);      // exists: r < max_num_cat <= used_bin
+      pk = bk; pi = bi;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * max_num_cat) {
+    const int side = threadIdx.x / max_num_cat, i = threadIdx.x - side * max_num_cat;
+    const int t = s_sel[side][i];
+    s_selg[side][i] = static_cast<double>(dst[t * 2]) * inv_g;
+    s_selh[side][i] = static_cast<double>(dst[t * 2 + 1]) * inv_h;
+  }
+  __syncthreads();
   if (threadIdx.x != 0) return;
-  const int used_bin = s_used;
   SplitParams pshift = p;
   if (!(p.max_delta_step > 0)) pshift.max_delta_step = 0;
   const double min_gain_shift = d_leaf_gain(sum_g, sum_h, pshift) + p.min_gain_to_split;
   SplitParams pc = p;
   pc.l2 += p.cat_l2;
-  const int max_num_cat = min(p.max_cat_threshold, (used_bin + 1) / 2);
   bool any_valid = false;
   double best_gain = kNegInf, best_lg = 0, best_lh = 0;
   int best_i = -1, best_dir = 1, best_lc = 0;
   for (int d = 0; d < 2; ++d) {
-    const int dir = d == 0 ? 1 : -1;
-    int pos = d == 0 ? 0 : used_bin - 1;
     int cnt_cur_group = 0, left_count = 0;
     double slg = 0.0, slh = kEpsD;
     for (int i = 0; i < used_bin && i < max_num_cat; ++i) {
-      const int t = s_id[pos];
-      pos += dir;
-      const double g = static_cast<double>(dst[t * 2]) * inv_g, h = static_cast<double>(dst[t * 2 + 1]) * inv_h;
+      const double g = s_selg[d][i], h = s_selh[d][i];
       const int cnt = static_cast<int>(h * cnt_factor + 0.5);
       slg += g; slh += h; left_count += cnt; cnt_cur_group += cnt;
       if (left_count < p.min_data_in_leaf || slh < p.min_sum_hessian) continue;
@@ -1734,7 +1780,7 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
       const double gain = d_leaf_gain(slg, slh, pc) + d_leaf_gain(sum_g - slg, srh, pc);
       if (gain <= min_gain_shift) continue;
       any_valid = true;
-      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_lc = left_count; best_i = i; best_dir = dir; }
+      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_lc = left_count; best_i = i; best_dir = d == 0 ? 1 : -1; }
     }
   }
   *flag = any_valid ? 1 : 0;
@@ -1742,7 +1788,7 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
     out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = 0; out.left_count = best_lc;
     out.default_left = 0; out.is_cat = 1; out.l2_extra = p.cat_l2;
     out.cat_list_len = best_i + 1;
-    for (int i = 0; i <= best_i && i < kCatListMax; ++i) out.cat_list[i] = best_dir == 1 ? s_id[i] : s_id[used_bin - 1 - i];
+    for (int i = 0; i <= best_i && i < kCatListMax; ++i) out.cat_list[i] = s_sel[best_dir == 1 ? 0 : 1][i];
   }
   cands[which * p.nf_pad + u] = out;
   __threadfence();

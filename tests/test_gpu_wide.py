@@ -215,3 +215,27 @@ def test_numerical_max_bin_above_255(built, max_bin):
     assert {0, 1, 2} <= set(used.tolist()), "wide numerical features must actually be split on"
     np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(b.predict_device(X[:300], predict_type=capi.PREDICT_RAW_SCORE)[:, 0], ob.predict_raw(X[:300])[:, 0], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("boosting", ["dart", "goss"])
+def test_wide_categorical_with_dart_and_goss(built, boosting):
+    """DART re-applies stored device trees (incl. their bin-list categorical nodes) to the binned rows; GOSS re-weights gradients"""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    n = 60_000
+    X, s = _data(7, n)
+    y = (s > 0).astype(np.float32)
+    params = _params("binary", "is_unbalance=false").replace("boosting_type=gbdt", "boosting_type=" + boosting)
+    if boosting == "dart":
+        params += " drop_rate=0.5 skip_drop=0.0"
+    else:
+        params = params.replace("learning_rate=0.1", "learning_rate=0.5")
+    ds = capi.Dataset.from_mat(X, DS).set_field("label", y)
+    ods = O.OracleDataset(X, DS).set_field("label", y)
+    b = capi.Booster(ds, params)
+    ob = O.OracleBooster(ods, params)
+    for _ in range(8):
+        assert b.update_one_iter() == ob.update()
+    compare_models(parse_model(b.save_model_to_string()), parse_model(ob.model_string()))
+    np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=1e-8, atol=1e-8)
