@@ -1709,41 +1709,41 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
   __shared__ double s_rk[8];
   __shared__ int s_ri[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // tournament: every thread keeps the best remaining key of ITS bins (b = tid + 256 j); a round reduces the 256 cached candidates and only
+  // the winner's owner rescans its own bins — the first selection version had every thread rescan all of its bins every round and ran
+  // instruction-bound on one SM per feature (~5 us per round)
   for (int side = 0; side < 2; ++side) {
-    double pk = side == 0 ? kNegInf : kPosInf;
-    int pi = side == 0 ? -1 : 0x7fffffff;
-    for (int r = 0; r < max_num_cat; ++r) {
-      double bk = side == 0 ? kPosInf : kNegInf;
-      int bi = side == 0 ? 0x7fffffff : -1;
+    auto better = [&](double k, int b, double rk, int rb) -> bool {      // (k, b) precedes (rk, rb) on this side; rb sentinel = nothing yet
+      if (side == 0) return rb == 0x7fffffff || k < rk || (k == rk && b < rb);
+      return rb == -1 || k > rk || (k == rk && b > rb);
+    };
+    auto own_next = [&](double pk, int pi, double* ok, int* oi) {         // best own key strictly beyond (pk, pi)
+      double bk = 0.0; int bi = side == 0 ? 0x7fffffff : -1;
       for (int b = threadIdx.x; b < m.num_bin; b += blockDim.x) {
         const double k = s_key[b];
         if (!(k < kPosInf)) continue;
-        if (side == 0) {
-          if ((k > pk || (k == pk && b > pi)) && (k < bk || (k == bk && b < bi))) { bk = k; bi = b; }
-        } else {
-          if ((k < pk || (k == pk && b < pi)) && (k > bk || (k == bk && b > bi))) { bk = k; bi = b; }
-        }
+        const bool beyond = side == 0 ? (k > pk || (k == pk && b > pi)) : (k < pk || (k == pk && b < pi));
+        if (beyond && better(k, b, bk, bi)) { bk = k; bi = b; }
       }
+      *ok = bk; *oi = bi;
+    };
+    const int none = side == 0 ? 0x7fffffff : -1;
+    double ck; int ci;
+    own_next(side == 0 ? kNegInf : kPosInf, side == 0 ? -1 : 0x7fffffff, &ck, &ci);
+    for (int r = 0; r < max_num_cat; ++r) {
+      double bk = ck; int bi = ci;
       for (int o = 16; o; o >>= 1) {
         const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const bool take = side == 0 ? (oi != 0x7fffffff && (bi == 0x7fffffff || ok < bk || (ok == bk && oi < bi)))
-                                    : (oi != -1 && (bi == -1 || ok > bk || (ok == bk && oi > bi)));
-        if (take) { bk = ok; bi = oi; }
+        if (oi != none && better(ok, oi, bk, bi)) { bk = ok; bi = oi; }
       }
       if (lane == 0) { s_rk[warp] = bk; s_ri[warp] = bi; }
       __syncthreads();
       bk = s_rk[0]; bi = s_ri[0];
-      for (int w2 = 1; w2 < 8; ++w2) {
-        const double ok = s_rk[w2];
-        const int oi = s_ri[w2];
-        const bool take = side == 0 ? (oi != 0x7fffffff && (bi == 0x7fffffff || ok < bk || (ok == bk && oi < bi)))
-                                    : (oi != -1 && (bi == -1 || ok > bk || (ok == bk && oi > bi)));
-        if (take) { bk = ok; bi = oi; }
-      }
+      for (int w2 = 1; w2 < 8; ++w2) if (s_ri[w2] != none && better(s_rk[w2], s_ri[w2], bk, bi)) { bk = s_rk[w2]; bi = s_ri[w2]; }
       __syncthreads();
       if (threadIdx.x == 0) s_sel[side][r] = static_cast<unsigned short>(bi);      // exists: r < max_num_cat <= used_bin
-      pk = bk; pi = bi;
+      if (bi != none && (bi & 255) == static_cast<int>(threadIdx.x)) own_next(bk, bi, &ck, &ci);      // only the owner of the winner moves on
     }
   }
   __syncthreads();
