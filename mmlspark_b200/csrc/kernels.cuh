@@ -1629,6 +1629,34 @@ __device__ __noinline__ void d_scan_wide_numeric(const long long* __restrict__ h
   }
 }
 
+// order of the wide categorical selection: side 0 ascending (key, bin), side 1 descending
+__device__ __forceinline__ bool d_sel_prec(int side, double k, int b, double rk, int rb) {
+  return side == 0 ? (k < rk || (k == rk && b < rb)) : (k > rk || (k == rk && b > rb));
+}
+constexpr int kSelList = 512;
+// bitonic sort by 256 threads of TWO (key, id) arrays of n (power of two <= stride) entries: array 0 ascending, array 1 descending in
+// (key, id); ends with a barrier
+__device__ __noinline__ void d_block_bitonic2(double* k, int* id, int stride, int n) {
+  for (int k2 = 2; k2 <= n; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int x = i ^ j;
+        if (x <= i) continue;
+        const bool up = (i & k2) == 0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          double* kk = k + side * stride; int* ii = id + side * stride;
+          const double ka = kk[i], kb = kk[x];
+          const int ia = ii[i], ib = ii[x];
+          const bool sw = up ? d_sel_prec(side, kb, ib, ka, ia) : d_sel_prec(side, ka, ia, kb, ib);
+          if (sw) { kk[i] = kb; kk[x] = ka; ii[i] = ib; ii[x] = ia; }
+        }
+      }
+    }
+  __syncthreads();
+}
+
 // Split search of a WIDE categorical feature (FeatureHistogram::FindBestThresholdCategoricalInner, many-vs-many branch): one block per
 // (smaller|larger, feature).  The histogram is reduced into the leaf's pool slot (parent - smaller for the larger child), the
 // max_cat_threshold smallest and largest ctr = g / (h + cat_smooth) among the bins that hold >= cat_smooth rows are selected in the
@@ -1701,17 +1729,60 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
   const int used_bin = s_used;
   const int max_num_cat = min(min(p.max_cat_threshold, kCatListMax), (used_bin + 1) / 2);
   // ---- the reference sorts the used bins by (ctr, bin) and walks max_num_cat bins from either end; only those 2 * max_num_cat order
-  // statistics are needed, so instead of sorting thousands of keys (the first version's block-wide bitonic sort took ~600 us per launch)
-  // the block selects them one by one: round r = the smallest (largest) key beyond the previous round's, a strided scan of the keys in
-  // shared memory + a warp-shuffle / 8-entry reduction.  The (key, bin) order is total, so the selection equals the stable sort.
+  // statistics are needed.  Sorting thousands of keys (first version: block-wide bitonic sort, ~600 us per launch) and selecting them
+  // one per round (second version: 64 dependent rounds of a strided rescan, ~300 us — the rescan's latency is the same whether one
+  // thread or all of them run it) both serialise on one SM.  Instead: (A) every thread takes the min and max of its own bins,
+  // (B) the 256 per-thread minima (maxima) are sorted and the max_num_cat-th of them is a threshold that at least max_num_cat keys
+  // reach, (C) the keys within the threshold are appended to a short list (typically max_num_cat + a few), (D) the list is sorted.
+  // Three passes over the keys instead of 2 * max_num_cat.  The (key, bin) order is total, so the result equals the stable sort.
   __shared__ unsigned short s_sel[2][kCatListMax];
   __shared__ double s_selg[2][kCatListMax], s_selh[2][kCatListMax];
   __shared__ double s_rk[8];
   __shared__ int s_ri[8];
+  __shared__ double s_tk[2][256], s_lk[2][kSelList];
+  __shared__ int s_ti[2][256], s_li[2][kSelList];
+  __shared__ int s_cnt[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // tournament: every thread keeps the best remaining key of ITS bins (b = tid + 256 j); a round reduces the 256 cached candidates and only
-  // the winner's owner rescans its own bins — the first selection version had every thread rescan all of its bins every round and ran
-  // instruction-bound on one SM per feature (~5 us per round)
+  bool overflow = false;
+  if (max_num_cat > 0) {
+    double ak = kPosInf, zk = kNegInf; int ai = 0x7fffffff, zi = -1;
+    for (int b = threadIdx.x; b < m.num_bin; b += blockDim.x) {
+      const double k = s_key[b];
+      if (!(k < kPosInf)) continue;
+      if (k < ak) { ak = k; ai = b; }
+      if (k >= zk) { zk = k; zi = b; }
+    }
+    s_tk[0][threadIdx.x] = ak; s_ti[0][threadIdx.x] = ai; s_tk[1][threadIdx.x] = zk; s_ti[1][threadIdx.x] = zi;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    d_block_bitonic2(&s_tk[0][0], &s_ti[0][0], 256, 256);
+    const double t0k = s_tk[0][max_num_cat - 1], t1k = s_tk[1][max_num_cat - 1];
+    const int t0i = s_ti[0][max_num_cat - 1], t1i = s_ti[1][max_num_cat - 1];
+    for (int b = threadIdx.x; b < m.num_bin; b += blockDim.x) {
+      const double k = s_key[b];
+      if (!(k < kPosInf)) continue;
+      if (!d_sel_prec(0, t0k, t0i, k, b)) { const int pos = atomicAdd(&s_cnt[0], 1); if (pos < kSelList) { s_lk[0][pos] = k; s_li[0][pos] = b; } }
+      if (!d_sel_prec(1, t1k, t1i, k, b)) { const int pos = atomicAdd(&s_cnt[1], 1); if (pos < kSelList) { s_lk[1][pos] = k; s_li[1][pos] = b; } }
+    }
+    __syncthreads();
+    const int n0 = s_cnt[0], n1 = s_cnt[1];
+    overflow = n0 > kSelList || n1 > kSelList;      // e.g. all small keys on bins congruent mod 256: fall back to the round-based selection
+    if (!overflow) {
+      int n2 = 2;
+      while (n2 < n0 || n2 < n1) n2 <<= 1;
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        if (i >= n0) { s_lk[0][i] = kPosInf; s_li[0][i] = 0x7fffffff; }
+        if (i >= n1) { s_lk[1][i] = kNegInf; s_li[1][i] = -1; }
+      }
+      d_block_bitonic2(&s_lk[0][0], &s_li[0][0], kSelList, n2);
+      if (threadIdx.x < 2 * max_num_cat) {
+        const int side = threadIdx.x / max_num_cat, i = threadIdx.x - side * max_num_cat;
+        s_sel[side][i] = static_cast<unsigned short>(s_li[side][i]);
+      }
+    }
+  }
+  // fallback (list overflow): tournament — every thread keeps the best remaining key of ITS bins (b = tid + 256 j); a round reduces the
+  // 256 cached candidates and only the winner's owner rescans its own bins
+  if (overflow)
   for (int side = 0; side < 2; ++side) {
     auto better = [&](double k, int b, double rk, int rb) -> bool {      // (k, b) precedes (rk, rb) on this side; rb sentinel = nothing yet
       if (side == 0) return rb == 0x7fffffff || k < rk || (k == rk && b < rb);
@@ -1754,16 +1825,15 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
     s_selh[side][i] = static_cast<double>(dst[t * 2 + 1]) * inv_h;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  SplitParams pshift = p;
-  if (!(p.max_delta_step > 0)) pshift.max_delta_step = 0;
-  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, pshift) + p.min_gain_to_split;
-  SplitParams pc = p;
-  pc.l2 += p.cat_l2;
-  bool any_valid = false;
-  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
-  int best_i = -1, best_dir = 1, best_lc = 0;
-  for (int d = 0; d < 2; ++d) {
+  // the walk from either end is sequential only in its cheap state (running sums, the min_data_per_group counter, continue / break); lane 0
+  // of warps 0 and 1 run it for one direction each and mark the prefixes the reference evaluates, the gains (fp64 divisions) are then
+  // computed one prefix per thread, and thread 0 takes the first maximum in the reference's (direction, i) order
+  __shared__ double s_plg[2][kCatListMax], s_plh[2][kCatListMax], s_pgain[2][kCatListMax];
+  __shared__ int s_plc[2][kCatListMax];
+  if (threadIdx.x < 2 * kCatListMax) s_pgain[threadIdx.x / kCatListMax][threadIdx.x % kCatListMax] = kNegInf;
+  __syncthreads();
+  if (lane == 0 && warp < 2) {
+    const int d = warp;
     int cnt_cur_group = 0, left_count = 0;
     double slg = 0.0, slh = kEpsD;
     for (int i = 0; i < used_bin && i < max_num_cat; ++i) {
@@ -1777,12 +1847,34 @@ k_scan_wide(const TreeCtrl* __restrict__ ctrl, const LeafState* __restrict__ lea
       if (srh < p.min_sum_hessian) break;
       if (cnt_cur_group < p.min_data_per_group) continue;
       cnt_cur_group = 0;
-      const double gain = d_leaf_gain(slg, slh, pc) + d_leaf_gain(sum_g - slg, srh, pc);
-      if (gain <= min_gain_shift) continue;
-      any_valid = true;
-      if (gain > best_gain) { best_gain = gain; best_lg = slg; best_lh = slh; best_lc = left_count; best_i = i; best_dir = d == 0 ? 1 : -1; }
+      s_plg[d][i] = slg; s_plh[d][i] = slh; s_plc[d][i] = left_count; s_pgain[d][i] = 0.0;      // 0.0 = "evaluate me"
     }
   }
+  __syncthreads();
+  SplitParams pshift = p;
+  if (!(p.max_delta_step > 0)) pshift.max_delta_step = 0;
+  const double min_gain_shift = d_leaf_gain(sum_g, sum_h, pshift) + p.min_gain_to_split;
+  if (threadIdx.x < 2 * kCatListMax) {
+    const int d = threadIdx.x / kCatListMax, i = threadIdx.x % kCatListMax;
+    if (s_pgain[d][i] == 0.0) {
+      SplitParams pc = p;
+      pc.l2 += p.cat_l2;
+      const double slg = s_plg[d][i], slh = s_plh[d][i];
+      s_pgain[d][i] = d_leaf_gain(slg, slh, pc) + d_leaf_gain(sum_g - slg, sum_h - slh, pc);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  bool any_valid = false;
+  double best_gain = kNegInf, best_lg = 0, best_lh = 0;
+  int best_i = -1, best_dir = 1, best_lc = 0;
+  for (int d = 0; d < 2; ++d)
+    for (int i = 0; i < max_num_cat; ++i) {
+      const double gain = s_pgain[d][i];
+      if (!(gain > min_gain_shift)) continue;      // also skips the -inf of the prefixes the walk did not evaluate
+      any_valid = true;
+      if (gain > best_gain) { best_gain = gain; best_lg = s_plg[d][i]; best_lh = s_plh[d][i]; best_lc = s_plc[d][i]; best_i = i; best_dir = d == 0 ? 1 : -1; }
+    }
   *flag = any_valid ? 1 : 0;
   if (any_valid) {
     out.gain = best_gain - min_gain_shift; out.left_g = best_lg; out.left_h = best_lh; out.threshold = 0; out.left_count = best_lc;
