@@ -1437,7 +1437,8 @@ void Booster::ResetFeaturesByTree() {
   int cnt = std::max(static_cast<int>(total * cfg.feature_fraction + 0.5), std::min(2, total));
   std::fill(feature_used_host_.begin(), feature_used_host_.end(), 0);
   for (int i : col_rand_.Sample(total, cnt)) feature_used_host_[train->sample_order[i]] = 1;      // the draw indexes the used features in real-index order
-  B200_CUDA(cudaStreamSynchronize(stream_));      // the previous tree must not still be reading the mask
+  // no host sync: the copy is ordered after the previous tree's kernels on the same stream, and a copy from pageable memory is staged
+  // by the driver before the call returns, so the host vector may be rewritten for the next tree
   feature_used_.Upload(feature_used_host_.data(), train->nf_pad, stream_);
 }
 
