@@ -100,14 +100,64 @@ def shard(cfg, rank, world, n_total):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe's clocks line).  Sampled in-process through NVML every
+    20 ms (an `nvidia-smi -lms` child needs ~0.5 s to produce its first line, longer than the timed region of a multi-GPU run); the device
+    is addressed by the UUID of this rank's CUDA device.  Falls back to `nvidia-smi -lms 200` when NVML cannot be loaded."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, reason bitmask)
+        self.nvml = None
+        self.handle = None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = None
+            if handle is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                phys = int(ids[index]) if ids and ids[index].strip().isdigit() else index
+                handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((sm, self.max_mhz, mask))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._sample_nvml()
+            self._stop.wait(0.02)
 
     def start(self):
+        if self.nvml is not None:
+            self._sample_nvml()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -122,12 +172,23 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._sample_nvml()          # one more while the last kernels of the region have just finished
+            self._stop.set()
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(nm for nm, bit in bits.items() if any(x[2] & bit for x in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz if sm else None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 20 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
@@ -136,10 +197,11 @@ class ClockSampler:
                 sm.append(float(p[0])); mx.append(float(p[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[3:7]):
+            for nm, v in zip(self.NAMES, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 200"}
 
 
 def measured_peak():

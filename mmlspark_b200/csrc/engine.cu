@@ -1647,8 +1647,9 @@ void Booster::TrainOneTree(int k, HostTree* out) {
     if (d.nw > 0) {      // the features with more than 256 bins: own sub-histogram layout (k4_hist_wide)
       int max_nb = 0;
       for (const WideMeta& wm : d.wide_host) max_nb = std::max(max_nb, wm.num_bin);
-      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 2 * num_sms_ / d.nw))), static_cast<unsigned>(d.nw),
-                       static_cast<unsigned>((max_nb + kWideHistSeg - 1) / kWideHistSeg));      // z: 8192-bin segments of the largest feature
+      const int segs = (max_nb + kWideHistSeg - 1) / kWideHistSeg;      // z: 8192-bin segments of the largest feature
+      // x: row parts, chosen so that the grid is about four waves of one CTA per SM (128 KB of shared memory each)
+      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 4 * num_sms_ / (d.nw * segs)))), static_cast<unsigned>(d.nw), static_cast<unsigned>(segs));
       if (const_hessian_)
         k4_hist_wide<3><<<wgrid, kWideThreads, 4 * kWideHistSeg * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                          reinterpret_cast<unsigned long long*>(H_.p));

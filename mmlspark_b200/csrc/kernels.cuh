@@ -1447,16 +1447,28 @@ k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const Wide
   __syncthreads();
   for (int c0 = p0; c0 < p1; c0 += kFlushRows) {
     const int c1 = min(c0 + kFlushRows, p1);
-    for (int p = c0 + threadIdx.x; p < c1; p += kWideThreads) {
-      int4 q; unsigned b;
-      if (w.use_idx) { const int r = idx[w.begin + p]; b = col[r]; q = qord[w.begin + p]; }
-      else { const size_t r = static_cast<size_t>(w.begin + p); b = col[r]; q = qgh[r]; }
-      b -= lo;
-      if (b >= static_cast<unsigned>(nb)) continue;           // another segment's bin
-      atomicAdd(&pl0[b], static_cast<unsigned>(q.x));
-      atomicAdd(&pl1[b], static_cast<unsigned>(q.y));
-      atomicAdd(&pl2[b], static_cast<unsigned>(q.z));
-      if (NATOM == 4) atomicAdd(&pl3[b], static_cast<unsigned>(q.w));
+    // four rows per thread in flight (index -> bin is a dependent pair of DRAM/L2 accesses; with one CTA per SM the loop is latency-bound)
+    for (int p = c0 + threadIdx.x; p < c1; p += 4 * kWideThreads) {
+      int4 q[4]; unsigned b[4]; size_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = p + j * kWideThreads;
+        r[j] = 0;
+        if (pj < c1) {
+          if (w.use_idx) { r[j] = static_cast<size_t>(idx[w.begin + pj]); q[j] = qord[w.begin + pj]; }
+          else { r[j] = static_cast<size_t>(w.begin + pj); q[j] = qgh[r[j]]; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = (p + j * kWideThreads < c1) ? static_cast<unsigned>(col[r[j]]) - lo : 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (b[j] >= static_cast<unsigned>(nb)) continue;           // another segment's bin (or past the end)
+        atomicAdd(&pl0[b[j]], static_cast<unsigned>(q[j].x));
+        atomicAdd(&pl1[b[j]], static_cast<unsigned>(q[j].y));
+        atomicAdd(&pl2[b[j]], static_cast<unsigned>(q[j].z));
+        if (NATOM == 4) atomicAdd(&pl3[b[j]], static_cast<unsigned>(q[j].w));
+      }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < nb; e += kWideThreads) {
