@@ -1648,8 +1648,11 @@ void Booster::TrainOneTree(int k, HostTree* out) {
       int max_nb = 0;
       for (const WideMeta& wm : d.wide_host) max_nb = std::max(max_nb, wm.num_bin);
       const int segs = (max_nb + kWideHistSeg - 1) / kWideHistSeg;      // z: 8192-bin segments of the largest feature
-      // x: row parts, chosen so that the grid is about four waves of one CTA per SM (128 KB of shared memory each)
-      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 4 * num_sms_ / (d.nw * segs)))), static_cast<unsigned>(d.nw), static_cast<unsigned>(segs));
+      // x: row parts, chosen so that the CTAs that have work (a (feature, segment) pair past the feature's last bin exits at once) make
+      // about four waves of one CTA per SM (128 KB of shared memory each)
+      int units = 0;
+      for (const WideMeta& wm : d.wide_host) units += (wm.num_bin + kWideHistSeg - 1) / kWideHistSeg;
+      const dim3 wgrid(static_cast<unsigned>(std::max(1, std::min(64, 4 * num_sms_ / std::max(1, units)))), static_cast<unsigned>(d.nw), static_cast<unsigned>(segs));
       if (const_hessian_)
         k4_hist_wide<3><<<wgrid, kWideThreads, 4 * kWideHistSeg * 4, s>>>(d.bins16.p, d.rows_stride, d.wide_meta.p, qgh_.p, qord_.p, idx0_.p, idx1_.p, &ctrl->hist_work,
                                                                          reinterpret_cast<unsigned long long*>(H_.p));

@@ -1423,7 +1423,7 @@ __global__ void k_bin_wide(const T* __restrict__ X, long long nrow, int row_majo
 // with the same fixed-point fields as the tile kernel; lanes read consecutive rows of the uint16 column (or gather through the leaf's
 // index list), so the atomics of a warp fall on data-dependent banks — these features are a few percent of a wide table's columns and
 // run at a fraction of the tile kernel's rate, which is acceptable.  Flush every 2^14 rows (field headroom) into the int64 histogram.
-constexpr int kWideThreads = 512;
+constexpr int kWideThreads = 1024;     // one CTA per SM (128 KB of planes): the loop is latency-bound, so as many rows in flight as the SM allows
 template <int NATOM>
 __global__ void __launch_bounds__(kWideThreads, 1)
 k4_hist_wide(const uint16_t* __restrict__ bins16, size_t rows_stride, const WideMeta* __restrict__ wm, const int4* __restrict__ qgh,
