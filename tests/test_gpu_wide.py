@@ -239,3 +239,42 @@ def test_wide_categorical_with_dart_and_goss(built, boosting):
         assert b.update_one_iter() == ob.update()
     compare_models(parse_model(b.save_model_to_string()), parse_model(ob.model_string()))
     np.testing.assert_allclose(b.get_scores(0), ob.scores(), rtol=1e-8, atol=1e-8)
+
+
+def test_wide_categorical_selection_list_overflow_falls_back(built):
+    """k_scan_wide selects the max_cat_threshold smallest / largest ctr keys through a threshold taken from the per-thread minima (maxima)
+    and a <= 512-entry candidate list.  Adversarial layout: ~600 bins owned by only 31 of the 256 threads (bin % 256 < 31) carry the small
+    keys, so the 32nd smallest per-thread minimum is a large key and the list overflows; the kernel must fall back to the round-based
+    selection and still agree with the oracle's stable sort."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    ncat, per = 8000, 40
+    n = ncat * per
+    cat = np.repeat(np.arange(ncat), per).astype(np.float64)
+    rng.shuffle(cat)
+    X = np.stack([cat, rng.standard_normal(n)], axis=1)
+    dsp = "max_bin=255 is_pre_partition=True bin_construct_sample_cnt=400000 num_threads=0 categorical_feature=0"
+    ds = capi.Dataset.from_mat(X, dsp)
+    bins = ds.get_bins16()[:, 0].astype(np.int64)
+    assert bins.max() > 7000
+    low = ((bins % 256) < 31) & ((bins // 256) < 20) & (bins > 0)
+    assert len(np.unique(bins[low])) > 512
+    catnoise = rng.standard_normal(int(bins.max()) + 1) * 0.05            # distinct ctr per category, no exact ties among the candidates
+    y = (np.where(low, -5.0, 5.0) + catnoise[bins] + 0.01 * rng.standard_normal(n)).astype(np.float32)
+    ds.set_field("label", y)
+    params = _params("regression", "min_data_per_group=10 cat_smooth=10 min_data_in_leaf=5")
+    b = capi.Booster(ds, params)
+    for _ in range(3):
+        assert not b.update_one_iter()
+    ods = O.OracleDataset(X, dsp)
+    assert np.array_equal(ods.bins16()[:, 0], bins)
+    ods.set_field("label", y)
+    ob = O.OracleBooster(ods, params)
+    ob.train(3)
+    ma, mb = parse_model(b.save_model_to_string()), parse_model(ob.model_string())
+    compare_models(ma, mb)
+    assert any((np.asarray(t["decision_type"]).astype(np.int64) & 1).any() for t in ma["trees"]), "no categorical split was made"
+    np.testing.assert_allclose(b.get_scores(), ob.scores(), rtol=1e-9, atol=1e-9)
+    b.free(); ds.free()
