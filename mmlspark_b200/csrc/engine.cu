@@ -1591,7 +1591,9 @@ void Booster::LaunchPartition(int grid, int last) {
   long long* H = H_.p;
   size_t h_elems = slot_elems_;
   const uint16_t* bins16 = d.bins16.p;
-  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16};
+  static const int tickets = [] { const char* e = std::getenv("B200GBM_PART_TICKETS"); return e ? std::atoi(e) : 8; }();      // 0: one chunk per ticket
+  int tickets_per_block = tickets;
+  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16, &tickets_per_block};
   B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_partition), dim3(grid), dim3(256), args, 0, stream_));
 }
 

@@ -1215,7 +1215,7 @@ __global__ void __launch_bounds__(256)
 k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p, int last,
             const uint8_t* __restrict__ bins, size_t rows_stride, int* __restrict__ idx0, int* __restrict__ idx1, unsigned* __restrict__ bits,
             int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems,
-            const uint16_t* __restrict__ bins16) {
+            const uint16_t* __restrict__ bins16, int tickets_per_block) {
   __shared__ int s_pref[kPartLocalScan + 1];
   __shared__ unsigned short s_list[kCatListMax];
   __shared__ int s_wl[64];
@@ -1248,12 +1248,16 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     // ---- phase 1 (no block-wide barrier: every warp adds the left count of its 256 rows to the chunk's counter, which the tail of
     // the previous partition kernel left at zero)
     // chunks are handed out dynamically (one atomic per chunk): the rows' DRAM latency varies, and the grid barrier waits for the slowest block
+    // a ticket grants `grp` consecutive chunks: a 100M-row leaf has 48K chunks, and one same-address atomic per chunk and phase is a
+    // serial ~100 us; with ~tickets_per_block tickets per block the hand-out stays dynamic and the atomics are negligible
+    const int grp = tickets_per_block > 0 ? max(1, chunks / (static_cast<int>(gridDim.x) * tickets_per_block)) : 1;
     for (;;) {
       __syncthreads();
       if (threadIdx.x == 0) s_chunk = static_cast<int>(atomicAdd(&ctrl->part_next[0], 1u));
       __syncthreads();
-      const int c = s_chunk;
-      if (c >= chunks) break;
+      const int cbase = s_chunk * grp;
+      if (cbase >= chunks) break;
+      for (int c = cbase; c < min(cbase + grp, chunks); ++c) {
       int local = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -1269,6 +1273,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
         if (lane == 0) { bits[(c * kPartChunk + k * 256 + threadIdx.x) >> 5] = bal; local += __popc(bal); }
       }
       if (lane == 0 && local) atomicAdd(&chunk_left[c], local);
+      }
     }
     d_grid_barrier(&ctrl->part_barrier, gridDim.x);
     // ---- phase 2: exclusive prefix of the chunk counts + total
@@ -1326,8 +1331,9 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
       __syncthreads();
       if (threadIdx.x == 0) s_chunk = static_cast<int>(atomicAdd(&ctrl->part_next[1], 1u));
       __syncthreads();
-      const int c = s_chunk;
-      if (c >= chunks) break;
+      const int cbase = s_chunk * grp;
+      if (cbase >= chunks) break;
+      for (int c = cbase; c < min(cbase + grp, chunks); ++c) {
       const int wbase = c * (kPartChunk / 32);     // 64 ballot words per chunk; word w covers rows c*2048 + w*32 ..
       if (threadIdx.x < 64) {
         const int i0 = c * kPartChunk + threadIdx.x * 32;
@@ -1361,7 +1367,8 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
           if (left == q_left) qord[pos] = qgh[r];      // replaces a separate gather pass before K4 (k_gather_q)
         }
       }
-      __syncthreads();
+      __syncthreads();      // s_wl is rewritten for the next chunk
+      }
     }
     if (local_scan && blockIdx.x == 0 && threadIdx.x == 0) ctrl->part_left_total = total_left;
   }
