@@ -578,6 +578,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (tm["hist_ms"] / 1000.0) / 1e9 if tm["hist_ms"] > 0 else None
     binfo = bst.get_info()
+    minfo = bst.get_memory_info()
     traffic, traffic_src = k4_traffic(N, F, world)
     roofline = {"bound": "hbm", "kernel": "k4_hist_build_ws<%d>" % (3 if binfo["constant_hessian"] else 4), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
@@ -611,7 +612,8 @@ def main():
                                  {0: "ncclAllReduce int64", 1: "fused reduce-scatter+scan over NVLink peer memory (k_scan_dp)",
                                   2: "two-shot all-reduce kernel over NVLink peer memory (k_allreduce_p2p)"}[binfo["reduce_mode"]]),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"], "clocks": clocks,
-            "dataset_build_s": build_s}
+            "dataset_build_s": build_s,
+            "partition_column_copy_gb": round(minfo["partition_column_copy_bytes"] / 1e9, 2), "device_free_gb": round(minfo["device_free_bytes"] / 1e9, 1)}
     line.update(checks)
     print(json.dumps(line))
     if split_timing:

@@ -198,6 +198,9 @@ int B200GBM_BoosterPredictForMatDevice(BoosterHandle handle, const void* data, i
 /* out = {num_machines, rank, histogram reduce mode (0 = ncclAllReduce, 1 = reduce-scatter + scan of the owned feature slice over NVLink
  * peer memory, 2 = two-shot all-reduce kernel over peer memory + replicated scan), constant_hessian} */
 int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4);
+/* out = {bytes of the optional column-major copy of the training bins kept for the partition kernel (0 = not kept: it is built before the
+ * first tree only if it leaves a reserve of device memory, B200GBM_COLUMN_COPY=0 disables it), free device memory in bytes} */
+int B200GBM_BoosterGetMemoryInfo(BoosterHandle handle, int64_t* out2);
 
 #ifdef __cplusplus
 }

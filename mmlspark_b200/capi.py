@@ -426,6 +426,11 @@ class Booster:
         check(load().B200GBM_BoosterGetInfo(self.handle, _ptr(out)))
         return dict(num_machines=int(out[0]), rank=int(out[1]), fused_peer_reduce=int(out[2]) == 1, reduce_mode=int(out[2]), constant_hessian=bool(out[3]))
 
+    def get_memory_info(self):
+        out = np.zeros(2, dtype=np.int64)
+        check(load().B200GBM_BoosterGetMemoryInfo(self.handle, _ptr(out)))
+        return dict(partition_column_copy_bytes=int(out[0]), device_free_bytes=int(out[1]))
+
     def get_scores(self, data_idx=0):
         n = C.c_int64(0)
         check(load().LGBM_BoosterGetNumPredict(self.handle, C.c_int(data_idx), C.byref(n)))

@@ -597,6 +597,11 @@ int B200GBM_BoosterGetInfo(BoosterHandle handle, int* out4) {
   BS(handle)->GetInfo(out4);
   API_END();
 }
+int B200GBM_BoosterGetMemoryInfo(BoosterHandle handle, int64_t* out2) {
+  API_BEGIN();
+  BS(handle)->GetMemoryInfo(out2);
+  API_END();
+}
 int B200GBM_BoosterGetScores(BoosterHandle handle, int data_idx, double* out) {
   API_BEGIN();
   BS(handle)->GetRawScores(data_idx, out);

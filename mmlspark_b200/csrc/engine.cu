@@ -1573,6 +1573,39 @@ void Booster::RenewTreeOutput(int k, double rf_pred) {
 }
 
 // k_partition is launched cooperatively: its software grid barriers need every block resident
+// Column-major copy of the training tiles for k_partition (kernels.cuh: k_tiles_to_columns).  Built once, before the first tree, after every
+// other buffer of the booster exists, and only if it leaves a reserve of device memory (validation scores, metric and prediction scratch
+// come later); B200GBM_COLUMN_COPY=0 disables it.  Without it the partition reads one 32-byte sector per row — same results.
+void Booster::EnsureColumnCopy() {
+  if (cols_tried_) return;
+  cols_tried_ = true;
+  const Dataset& d = *train;
+  const char* env = std::getenv("B200GBM_COLUMN_COPY");
+  if ((env && std::atoi(env) == 0) || d.nfn == 0 || d.num_data == 0) return;
+  const size_t stride = (static_cast<size_t>(d.num_data) + 255) & ~static_cast<size_t>(255);
+  const size_t need = static_cast<size_t>(d.num_tiles) * 32 * stride;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return; }
+  const size_t reserve = std::max<size_t>(static_cast<size_t>(8) << 30, total_b / 10);
+  if (free_b < need + reserve) return;
+  uint8_t* p = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&p), need) != cudaSuccess) { cudaGetLastError(); return; }
+  bins_cols_.p = p; bins_cols_.n = need;
+  cols_stride_ = stride;
+  const long long work = ((static_cast<long long>(d.num_data) + 255) / 256) * d.num_tiles;
+  k_tiles_to_columns<<<static_cast<unsigned>(std::min<long long>(work, static_cast<long long>(num_sms_) * 16)), 256, 0, stream_>>>(
+      d.bins.p, d.rows_stride, d.num_tiles, d.num_data, bins_cols_.p, stride);
+  B200_CUDA(cudaGetLastError());
+}
+
+void Booster::GetMemoryInfo(int64_t* out2) {
+  if (train) B200_CUDA(cudaSetDevice(device_));
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+  out2[0] = static_cast<int64_t>(bins_cols_.n);
+  out2[1] = static_cast<int64_t>(free_b);
+}
+
 void Booster::LaunchPartition(int grid, int last) {
   const Dataset& d = *train;
   TreeCtrl* ctrl = ctrl_.p;
@@ -1593,7 +1626,10 @@ void Booster::LaunchPartition(int grid, int last) {
   const uint16_t* bins16 = d.bins16.p;
   static const int tickets = [] { const char* e = std::getenv("B200GBM_PART_TICKETS"); return e ? std::atoi(e) : 8; }();      // 0: one chunk per ticket
   int tickets_per_block = tickets;
-  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16, &tickets_per_block};
+  const uint8_t* cols = bins_cols_.p;
+  size_t cols_stride = cols_stride_;
+  void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16, &tickets_per_block,
+                  &cols, &cols_stride};
   B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_partition), dim3(grid), dim3(256), args, 0, stream_));
 }
 
@@ -1601,6 +1637,7 @@ void Booster::LaunchPartition(int grid, int last) {
 // selection, partition sizes all live in TreeCtrl / LeafState on the device.
 void Booster::TrainOneTree(int k, HostTree* out) {
   NvtxRange nvtx_tree("b200gbm:tree");
+  EnsureColumnCopy();
   const Dataset& d = *train;
   const int n = d.num_data;
   const int L = cfg.num_leaves;

@@ -261,6 +261,13 @@ class Booster {
   unsigned char* tree_host_ = nullptr;   // pinned mirror of tree_blob_
   TreeCtrl* ctrl_host_ = nullptr;        // pinned
   LeafState* leaves_host_ = nullptr;     // pinned
+  DevBuf<uint8_t> bins_cols_;      // optional [feature][row] copy of the uint8 tiles for the partition kernel
+  size_t cols_stride_ = 0;
+  bool cols_tried_ = false;
+  void EnsureColumnCopy();
+ public:
+  void GetMemoryInfo(int64_t* out2);
+ private:
   DevBuf<unsigned> part_bits_;
   DevBuf<int> part_chunks_;
   // lambdarank

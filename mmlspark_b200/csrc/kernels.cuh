@@ -1180,6 +1180,38 @@ k_pick_dp(TreeCtrl* ctrl, LeafState* leaves, const FeatMeta* __restrict__ meta, 
   if (threadIdx.x < 32 && !ctrl->finished) d_choose_leaf(ctrl, leaves, meta, p, threadIdx.x);
 }
 
+// ---------------------------------------------------------------- column-major copy of the uint8 tiles (for the partition kernel)
+// The tile layout [tile][row][32 features] is what K4 streams, but the partition kernel needs ONE feature of every row of a leaf and pays
+// a 32-byte sector for each byte (62 % of its DRAM bytes at 100M rows).  When device memory allows, the booster keeps a second copy
+// [feature][row] (cols_stride = rows rounded up to 256), built once by this kernel.
+__global__ void __launch_bounds__(256)
+k_tiles_to_columns(const uint8_t* __restrict__ bins, size_t rows_stride, int num_tiles, long long nrow, uint8_t* __restrict__ cols, size_t cols_stride) {
+  __shared__ uint4 s_t[256 * 2 + 16];                      // 256 rows x 32 bytes
+  const long long per_tile = (nrow + 255) / 256;
+  for (long long w = blockIdx.x; w < per_tile * num_tiles; w += gridDim.x) {
+    const int tile = static_cast<int>(w / per_tile);
+    const long long r0 = (w % per_tile) * 256;
+    const int rows = static_cast<int>(min(256LL, nrow - r0));
+    const uint4* src = reinterpret_cast<const uint4*>(bins + (static_cast<size_t>(tile) * rows_stride + static_cast<size_t>(r0)) * 32);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * 2; i += 256) s_t[i] = src[i];
+    __syncthreads();
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_t);
+    const int f = threadIdx.x >> 3, g = threadIdx.x & 7;   // feature of the tile, group of 32 rows
+    unsigned wv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned v = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int r = g * 32 + k * 4 + j; v |= (r < rows ? static_cast<unsigned>(sb[r * 32 + f]) : 0u) << (8 * j); }
+      wv[k] = v;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(cols + (static_cast<size_t>(tile) * 32 + f) * cols_stride + static_cast<size_t>(r0) + g * 32);
+    dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);       // cols_stride is a multiple of 256: padding rows exist and are never read
+    dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+  }
+}
+
 // ---------------------------------------------------------------- K7 row partition (stable), one cooperative kernel per split
 // Replaces [UPSTREAM] DataPartition::Split.  Round 1 ran three kernels (decision bits + per-chunk left counts, single-block scan of the
 // chunk counts, scatter) plus a memset of the scratch histogram and the next round's controller: five launches on the per-split
@@ -1215,7 +1247,7 @@ __global__ void __launch_bounds__(256)
 k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p, int last,
             const uint8_t* __restrict__ bins, size_t rows_stride, int* __restrict__ idx0, int* __restrict__ idx1, unsigned* __restrict__ bits,
             int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems,
-            const uint16_t* __restrict__ bins16, int tickets_per_block) {
+            const uint16_t* __restrict__ bins16, int tickets_per_block, const uint8_t* __restrict__ cols, size_t cols_stride) {
   __shared__ int s_pref[kPartLocalScan + 1];
   __shared__ unsigned short s_list[kCatListMax];
   __shared__ int s_wl[64];
@@ -1240,6 +1272,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
     const int wide = ctrl->split_wide;
     const uint8_t* col = bins + (static_cast<size_t>((wide >= 0 ? 0 : f) >> 5) * rows_stride) * 32 + ((wide >= 0 ? 0 : f) & 31);
     const uint16_t* wcol = wide >= 0 ? bins16 + static_cast<size_t>(wide) * rows_stride : nullptr;
+    const uint8_t* ccol = (cols != nullptr && wide < 0) ? cols + static_cast<size_t>(f) * cols_stride : nullptr;      // column-major copy, if kept
     const bool wide_cat = wide >= 0 && ctrl->split_is_cat;
     const int list_len = wide_cat ? ctrl->split_cat_list_len : 0;
     if (threadIdx.x < list_len) s_list[threadIdx.x] = ctrl->split_cat_list[threadIdx.x];
@@ -1265,7 +1298,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
         bool left = false;
         if (i < n) {
           const int r = identity ? (begin + i) : src[begin + i];
-          const unsigned bin = wide >= 0 ? static_cast<unsigned>(wcol[r]) : static_cast<unsigned>(col[static_cast<size_t>(r) * 32]);
+          const unsigned bin = wide >= 0 ? static_cast<unsigned>(wcol[r]) : (ccol ? static_cast<unsigned>(ccol[r]) : static_cast<unsigned>(col[static_cast<size_t>(r) * 32]));
           if (wide_cat) { for (int kk = 0; kk < list_len; ++kk) left |= (bin == s_list[kk]); }
           else left = d_goes_left(bin, ctrl);
         }

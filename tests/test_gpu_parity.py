@@ -770,3 +770,38 @@ def test_batched_gpu_treeshap_matches_host_predictor(built, objective):
     dev32 = b.predict_device(Xs.astype(np.float32), predict_type=capi.PREDICT_CONTRIB, start_iteration=2, num_iteration=5)
     raw32 = b.predict_device(Xs.astype(np.float32), predict_type=capi.PREDICT_RAW_SCORE, start_iteration=2, num_iteration=5).reshape(700, K)
     np.testing.assert_allclose(dev32.reshape(700, K, F + 1).sum(axis=2), raw32, rtol=0, atol=1e-9)
+
+
+def test_partition_column_copy_is_transparent(built, monkeypatch):
+    """The booster keeps an optional [feature][row] copy of the training tiles so that k_partition reads one byte per row instead of a
+    32-byte sector.  With and without it (B200GBM_COLUMN_COPY=0) the models must be identical byte for byte, on a row count that is not a
+    multiple of the 256-row transposition block, with categorical + NaN features, and both must match the oracle."""
+    from mmlspark_b200 import capi
+    from mmlspark_b200.modeltext import parse_model, compare_models
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    n, F = 70_001, 37                                   # two tiles, the second one partly filled
+    X = rng.standard_normal((n, F))
+    X[:, 3] = rng.integers(0, 30, n)
+    X[rng.random(n) < 0.05, 5] = np.nan
+    y = (X[:, 0] + np.sin(2 * X[:, 1]) + (X[:, 3] % 3) + X[:, 36] * 0.5 + 0.3 * rng.standard_normal(n) > 0.8).astype(np.float32)
+    dsp = DS_PARAMS + " categorical_feature=3"
+    params = _classifier_params("binary", "is_unbalance=false")
+    texts, copies = [], []
+    for env in ("1", "0"):
+        monkeypatch.setenv("B200GBM_COLUMN_COPY", env)
+        ds = capi.Dataset.from_mat(X, dsp)
+        ds.set_field("label", y)
+        b = capi.Booster(ds, params)
+        for _ in range(8):
+            assert not b.update_one_iter()
+        texts.append(b.save_model_to_string())
+        copies.append(b.get_memory_info()["partition_column_copy_bytes"])
+        b.free(); ds.free()
+    assert copies[0] == 2 * 32 * 70_144 and copies[1] == 0
+    assert texts[0] == texts[1]
+    ods = O.OracleDataset(X, dsp)
+    ods.set_field("label", y)
+    ob = O.OracleBooster(ods, params)
+    ob.train(8)
+    compare_models(parse_model(texts[0]), parse_model(ob.model_string()))
