@@ -1,6 +1,6 @@
 """Small end-to-end runs for compute-sanitizer (memcheck / racecheck / synccheck): every hand-synchronised kernel of the engine at shapes a
 sanitizer finishes in minutes — K4 with TMA bulk copies (root) and cp.async gathers (leaves), the ticket-elected pick step of k_scan, the
-software grid barriers of k_partition, the bitonic sort of k_scan_wide, k4_hist_wide, bagging, lambdarank and the device metrics."""
+software grid barriers of k_partition, the threshold selection + short bitonic sorts of k_scan_wide, the column-major copy (k_tiles_to_columns), k4_hist_wide, bagging, lambdarank and the device metrics."""
 import sys
 
 import numpy as np
