@@ -1042,7 +1042,7 @@ void Booster::InitTraining() {
   cands_.Alloc(2 * static_cast<size_t>(train->nf_pad));
   leaves_.Alloc(L); ctrl_.Alloc(1); ctrl_.Zero(stream_);
   const int chunks = n / kPartChunk + 2;
-  part_bits_.Alloc(static_cast<size_t>(chunks) * (kPartChunk / 32)); part_chunks_.Alloc(chunks); part_chunks_.Zero(stream_);
+  part_bits_.Alloc(static_cast<size_t>(chunks) * (kPartChunk / 32)); part_chunks_.Alloc(static_cast<size_t>(chunks) + chunks / kPartLocalScan + 8); part_chunks_.Zero(stream_);      // + the super-chunk totals of the two-level scan
   // SoA tree blob
   {
     size_t off = 0;
@@ -1628,8 +1628,9 @@ void Booster::LaunchPartition(int grid, int last) {
   int tickets_per_block = tickets;
   const uint8_t* cols = bins_cols_.p;
   size_t cols_stride = cols_stride_;
+  int* super_tot = part_chunks_.p + (train->num_data / kPartChunk + 2);
   void* args[] = {&ctrl, &leaves, &tree, &flags, &meta, &sp, &last, &bins, &rows_stride, &i0, &i1, &bits, &chunks, &qgh, &qord, &H, &h_elems, &bins16, &tickets_per_block,
-                  &cols, &cols_stride};
+                  &cols, &cols_stride, &super_tot};
   B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_partition), dim3(grid), dim3(256), args, 0, stream_));
 }
 

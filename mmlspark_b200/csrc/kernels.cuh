@@ -1221,7 +1221,7 @@ k_tiles_to_columns(const uint8_t* __restrict__ bins, size_t rows_stride, int num
 //   phase 1  decision bit per row (ballot words) and the left count of every 2048-row chunk
 //   ---- grid barrier
 //   phase 2  chunk prefix: leaves of <= 2048 chunks (4M rows) are scanned redundantly by every block in shared memory (no second
-//            barrier); larger ones by block 0 in place, followed by a second barrier
+//            barrier); larger ones in two levels (one block per 2048 counts, second barrier, every block scans the totals)
 //   phase 3  stable scatter into the other index buffer (lefts first, then rights, original order kept); the (g,h) words of the
 //            child K4 scans next go into partition order (qord)
 //   tail     the block that finishes last applies the split to the tree and prepares the next round (d_round_ctl)
@@ -1247,7 +1247,7 @@ __global__ void __launch_bounds__(256, 3)
 k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, const FeatMeta* __restrict__ meta, SplitParams p, int last,
             const uint8_t* __restrict__ bins, size_t rows_stride, int* __restrict__ idx0, int* __restrict__ idx1, unsigned* __restrict__ bits,
             int* __restrict__ chunk_left, const int4* __restrict__ qgh, int4* __restrict__ qord, long long* __restrict__ H, size_t h_elems,
-            const uint16_t* __restrict__ bins16, int tickets_per_block, const uint8_t* __restrict__ cols, size_t cols_stride) {
+            const uint16_t* __restrict__ bins16, int tickets_per_block, const uint8_t* __restrict__ cols, size_t cols_stride, int* __restrict__ super_tot) {
   __shared__ int s_pref[kPartLocalScan + 1];
   __shared__ unsigned short s_list[kCatListMax];
   __shared__ int s_wl[64];
@@ -1342,29 +1342,45 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
       __syncthreads();
       total_left = s_pref[kPartLocalScan];
     } else {
-      if (blockIdx.x == 0) {
-        __shared__ int s_carry;
-        if (threadIdx.x == 0) s_carry = 0;
+      // two levels: block s scans the 2048 counts of "super-chunk" s in place (prefix relative to the super-chunk) and publishes its total;
+      // after the second barrier every block scans the totals.  (The first version had block 0 scan all counts alone: ~190 us for the 48K
+      // chunks of a 100M-row root while every other block waited at the barrier.)
+      const int supers = (chunks + kPartLocalScan - 1) / kPartLocalScan;
+      for (int sp = blockIdx.x; sp < supers; sp += gridDim.x) {
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = sp * kPartLocalScan + threadIdx.x * 8 + k; v[k] = i < chunks ? __ldcg(chunk_left + i) : 0; sum += v[k]; }
+        int inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         __syncthreads();
-        for (int base = 0; base < chunks; base += 256) {
-          const int i = base + threadIdx.x;
-          const int v = i < chunks ? __ldcg(chunk_left + i) : 0;
-          int inc = v;
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-          if (lane == 31) s_cnt[warp] = inc;
-          __syncthreads();
-          int woff = 0;
-          for (int w = 0; w < warp; ++w) woff += s_cnt[w];
-          const int excl = s_carry + woff + inc - v;
-          if (i < chunks) chunk_left[i] = excl;
-          __syncthreads();
-          if (threadIdx.x == 255) s_carry = excl + v;
-          __syncthreads();
-        }
-        if (threadIdx.x == 0) ctrl->part_left_total = s_carry;
+        if (lane == 31) s_cnt[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+        int run = woff + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = sp * kPartLocalScan + threadIdx.x * 8 + k; if (i < chunks) chunk_left[i] = run; run += v[k]; }
+        if (threadIdx.x == 255) super_tot[sp] = run;
       }
       d_grid_barrier(&ctrl->part_barrier, 2 * gridDim.x);
-      total_left = *reinterpret_cast<volatile int*>(&ctrl->part_left_total);
+      {   // exclusive scan of the super-chunk totals (at most 2048 of them: 8.6G rows) into s_pref
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = threadIdx.x * 8 + k; v[k] = i < supers ? __ldcg(super_tot + i) : 0; sum += v[k]; }
+        int inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
+        if (lane == 31) s_cnt[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+        int run = woff + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_pref[threadIdx.x * 8 + k] = run; run += v[k]; }
+        if (threadIdx.x == 255) s_pref[kPartLocalScan] = run;
+        __syncthreads();
+        total_left = s_pref[kPartLocalScan];
+      }
     }
     // the child K4 scans next is the one with fewer rows by the rule of d_round_ctl (global counts of the split in data-parallel
     // mode, true counts otherwise; ties -> right): its (g,h) words are written in partition order (qord)
@@ -1394,7 +1410,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
         s_wl[lane * 2] = ex; s_wl[lane * 2 + 1] = ex + a;
       }
       __syncthreads();
-      const int left_base = local_scan ? s_pref[c] : __ldcg(chunk_left + c);
+      const int left_base = local_scan ? s_pref[c] : s_pref[c / kPartLocalScan] + __ldcg(chunk_left + c);
       const int right_base = c * kPartChunk - left_base;
       // same batching as phase 1: the 8 index loads, then the (g,h) words of the rows that go to the child K4 scans next, then the stores
       int rr[8], pp[8]; bool qq[8]; int4 qv[8];
@@ -1423,7 +1439,7 @@ k_partition(TreeCtrl* ctrl, LeafState* leaves, TreeDev tree, uint8_t* flags, con
       __syncthreads();      // s_wl is rewritten for the next chunk
       }
     }
-    if (local_scan && blockIdx.x == 0 && threadIdx.x == 0) ctrl->part_left_total = total_left;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->part_left_total = total_left;
   }
   // ---- tail: the last block to finish runs the controller of the next round
   __syncthreads();
