@@ -1599,7 +1599,7 @@ void Booster::EnsureColumnCopy() {
 }
 
 void Booster::GetMemoryInfo(int64_t* out2) {
-  if (train) B200_CUDA(cudaSetDevice(device_));
+  EnsureDevice();
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
   out2[0] = static_cast<int64_t>(bins_cols_.n);
