@@ -94,6 +94,31 @@ def test_poisson_matches_sklearn_hgb(O):
     np.testing.assert_allclose(got, h._raw_predict(X).ravel(), rtol=0, atol=1e-10)
 
 
+def test_gamma_matches_sklearn_hgb(O):
+    """log-link Gamma deviance: gradient 1 - y exp(-s), hessian y exp(-s), init score log(mean y) in both implementations.
+    The hessians vary by orders of magnitude here, which exposes a LightGBM rule sklearn does not have: the row count of a histogram bin
+    is RECONSTRUCTED from its hessian mass (cnt = round(h * num_data / sum_hessian), SURVEY.md "Count-from-hessian"), so `min_data_in_leaf` acts on
+    hessian-weighted counts.  With the count constraint off (min_data_in_leaf = 0 / min_samples_leaf = 1) the two implementations agree
+    to 1e-13; with it on, they differ exactly because of that rule (sklearn splits off a 24-row leaf of low-hessian rows that LightGBM's
+    estimate counts as 8)."""
+    rng, X, _ = _data(10)
+    mu = np.exp(0.02 * X[:, 0] - 0.001 * X[:, 1] ** 2 + 0.02 * (X[:, 2] > 3) * X[:, 3])
+    y = rng.gamma(shape=2.0, scale=mu / 2.0).astype(np.float32) + np.float32(1e-3)
+
+    def both(min_leaf, iters):
+        h = sk.HistGradientBoostingRegressor(loss="gamma", learning_rate=0.1, max_iter=iters, max_leaf_nodes=31, min_samples_leaf=max(min_leaf, 1),
+                                             max_bins=255, early_stopping=False).fit(X, y.astype(np.float64))
+        ds = O.OracleDataset(X, "max_bin=255 min_data_in_leaf=%d" % min_leaf).set_field("label", y)
+        b = O.OracleBooster(ds, "num_leaves=31 learning_rate=0.1 min_data_in_leaf=%d min_sum_hessian_in_leaf=0.001 verbosity=-1 objective=gamma" % min_leaf)
+        b.train(iters)
+        return b.predict_raw(X)[:, 0], h._raw_predict(X).ravel()
+
+    got, ref = both(0, 8)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10)
+    got, ref = both(20, 1)
+    assert np.abs(got - ref).max() > 1e-2
+
+
 @pytest.mark.parametrize("loss,params,kw,atol", [
     ("absolute_error", "objective=regression_l1", {}, 1e-6),              # the init score is a label_t (float32) percentile in LightGBM
     ("quantile", "objective=quantile alpha=0.8", {"quantile": 0.8}, 1e-5),        # LightGBM keeps alpha as float32
