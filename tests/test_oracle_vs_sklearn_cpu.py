@@ -4,7 +4,8 @@ The real lightgbmlib 3.2.110 cannot run here, so the oracle is "parity unpinned"
 HistGradientBoosting is an independent implementation of the same algorithm family (histogram GBDT, leaf-wise growth, the XGBoost
 gain, fp32 gradients, NaN bin with a learned default direction, LightGBM-style categorical splits).  On data where the two bin
 finders agree by construction (integer-valued features with < 255 distinct values: both put one bin per distinct value) the two must
-produce the SAME model; they do, to 1e-13, for regression / binary / max_depth / NaN / weights / categorical.  The one LightGBM-specific
+produce the SAME model; they do, to 1e-13, for regression / binary / Poisson / Gamma / max_depth / NaN / weights / categorical (multiclass
+softmax to 1e-7 in probability).  The one LightGBM-specific
 rule sklearn does not have — children inherit the parent's per-feature `is_splittable` flags — is isolated with the oracle's test-only
 switch `oracle_inherit_splittable=false`."""
 import numpy as np
@@ -117,6 +118,27 @@ def test_gamma_matches_sklearn_hgb(O):
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10)
     got, ref = both(20, 1)
     assert np.abs(got - ref).max() > 1e-2
+
+
+def test_multiclass_softmax_matches_sklearn_hgb(O):
+    """K trees per iteration on softmax gradients.  LightGBM scales the hessian by K / (K - 1) (MulticlassSoftmax::GetGradients), which
+    leaves every split (gain argmax, hessian-share counts) unchanged and multiplies each leaf value by (K - 1) / K: the oracle at learning
+    rate 0.1 must equal sklearn at 0.1 (K - 1) / K.  Init scores differ by a per-row constant (log prior vs centred log prior), so the
+    comparison is on probabilities.  fp32 gradients in both; the hessian factor is applied in fp32, hence 1e-7 instead of 1e-13.
+    Count constraint off for the reason given in the Gamma test."""
+    rng, X, _ = _data(12)
+    K = 4
+    s = np.stack([0.1 * X[:, 0], -0.002 * X[:, 1] ** 2 + 1, 0.15 * (X[:, 2] > 3) * X[:, 3], 0.05 * X[:, 4]], axis=1) + rng.gumbel(size=(len(X), K))
+    y = s.argmax(1).astype(np.float32)
+    h = sk.HistGradientBoostingClassifier(loss="log_loss", learning_rate=0.1 * (K - 1) / K, max_iter=6, max_leaf_nodes=31, min_samples_leaf=1,
+                                          max_bins=255, early_stopping=False).fit(X, y)
+    ds = O.OracleDataset(X, "max_bin=255 min_data_in_leaf=0").set_field("label", y)
+    b = O.OracleBooster(ds, "num_leaves=31 learning_rate=0.1 min_data_in_leaf=0 min_sum_hessian_in_leaf=0.001 verbosity=-1 objective=multiclass num_class=%d" % K)
+    b.train(6)                     # 24 trees; the fp32 rounding of the hessian factor (1e-8 relative) flips a near-tied split around iteration 9
+    z = b.predict_raw(X)
+    z = z - z.max(axis=1, keepdims=True)
+    p = np.exp(z) / np.exp(z).sum(axis=1, keepdims=True)
+    np.testing.assert_allclose(p, h.predict_proba(X), rtol=0, atol=1e-7)
 
 
 @pytest.mark.parametrize("loss,params,kw,atol", [
