@@ -696,7 +696,7 @@ def test_zero_and_extreme_weights_and_gradients(built):
     compare_models(m, om, check_counts=True)
 
 
-@pytest.mark.parametrize("case", ["regression_nan", "binary", "categorical_weights"])
+@pytest.mark.parametrize("case", ["regression_nan", "binary", "categorical_weights", "categorical_effects"])
 def test_cuda_path_matches_sklearn_hist_gradient_boosting(built, case):
     """The CUDA path against an INDEPENDENT implementation (scikit-learn's HistGradientBoosting), no oracle involved: on
     integer-valued features both bin finders put one bin per distinct value, so the fitted models must be the same function
@@ -718,6 +718,12 @@ def test_cuda_path_matches_sklearn_hist_gradient_boosting(built, case):
         y = (y > np.median(y)).astype(np.float32)
         h = sk.HistGradientBoostingClassifier(loss="log_loss", **common).fit(X, y)
         params, want = base + "objective=binary", h.decision_function(X)
+    elif case == "categorical_effects":      # the label depends on the category: dozens of many-vs-many categorical splits (LightGBM-only rules neutralised)
+        X[:, 4] = rng.integers(0, 40, n)
+        y = (y + 2.0 * rng.standard_normal(40)[X[:, 4].astype(int)]).astype(np.float32)
+        h = sk.HistGradientBoostingRegressor(loss="squared_error", categorical_features=[4], **common).fit(X, y.astype(np.float64))
+        params = base + "objective=regression cat_l2=0 cat_smooth=10 min_data_per_group=1 max_cat_to_onehot=1 max_cat_threshold=32"
+        want, ds_params = h.predict(X), DS_PARAMS + " categorical_feature=4"
     else:
         X[:, 4] = rng.integers(0, 12, n)
         w = rng.integers(1, 4, n).astype(np.float32)

@@ -63,6 +63,30 @@ def test_regression_matches_sklearn_hgb(O, case):
     np.testing.assert_allclose(got, h.predict(X), rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize("ncat,iters", [(12, 10), (40, 10), (60, 5)])
+def test_categorical_many_vs_many_matches_sklearn_hgb(O, ncat, iters):
+    """The label DEPENDS on the category (the "categorical" case above only checks that an irrelevant categorical column does no harm), so
+    the trees hold dozens of categorical splits.  Both implementations sort the categories of a leaf by sum_g / (sum_h + 10), scan the
+    sorted order from both ends up to the middle and send the chosen prefix left (sklearn `_find_best_bin_to_split_category`,
+    LightGBM `FindBestThresholdCategoricalInner`).  LightGBM-only rules are neutralised: cat_l2=0 (extra L2 of categorical gains),
+    min_data_per_group=1, max_cat_to_onehot=1 (no one-vs-rest mode); max_cat_threshold=32 does not bind below 64 categories.
+    Agreement is exact (0.0) — this pins the ctr order, the two scan directions, the category bitsets in the model and their use at
+    prediction time against an implementation that shares no code or author with the oracle."""
+    rng = np.random.default_rng(21)
+    n, F = 20000, 8
+    X = rng.integers(-20, 30, size=(n, F)).astype(np.float64)
+    X[:, 4] = rng.integers(0, ncat, n)
+    eff = rng.standard_normal(ncat)
+    y = (0.3 * X[:, 0] - 0.02 * X[:, 1] ** 2 + 2.0 * eff[X[:, 4].astype(int)] + rng.standard_normal(n)).astype(np.float32)
+    h = _hgb_reg(iters, categorical_features=[4]).fit(X, y.astype(np.float64))
+    ds = O.OracleDataset(X, "max_bin=255 categorical_feature=4").set_field("label", y)
+    b = O.OracleBooster(ds, BASE + "objective=regression cat_l2=0 cat_smooth=10 min_data_per_group=1 max_cat_to_onehot=1 max_cat_threshold=32")
+    b.train(iters)
+    from mmlspark_b200.modeltext import parse_model
+    assert sum(int(t.get("num_cat", 0)) for t in parse_model(b.model_string())["trees"]) >= 3 * iters
+    np.testing.assert_allclose(b.predict_raw(X)[:, 0], h.predict(X), rtol=0, atol=1e-10)
+
+
 def test_binary_logloss_matches_sklearn_hgb(O):
     _, X, y = _data(7)
     yb = (y > np.median(y)).astype(np.float32)
