@@ -87,13 +87,15 @@ def test_categorical_many_vs_many_matches_sklearn_hgb(O, ncat, iters):
     np.testing.assert_allclose(b.predict_raw(X)[:, 0], h.predict(X), rtol=0, atol=1e-10)
 
 
-def test_binary_logloss_matches_sklearn_hgb(O):
-    _, X, y = _data(7)
+@pytest.mark.parametrize("weighted", [False, True])
+def test_binary_logloss_matches_sklearn_hgb(O, weighted):
+    rng, X, y = _data(7)
     yb = (y > np.median(y)).astype(np.float32)
+    w = rng.integers(1, 5, len(yb)).astype(np.float64) if weighted else None
     h = sk.HistGradientBoostingClassifier(loss="log_loss", learning_rate=0.1, max_iter=20, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255,
-                                          early_stopping=False).fit(X, yb)
-    got = _oracle_pred(O, X, yb, "objective=binary", 20)
-    np.testing.assert_allclose(got, h.decision_function(X), rtol=0, atol=1e-10)      # incl. the log-odds init score
+                                          early_stopping=False).fit(X, yb, sample_weight=w)
+    got = _oracle_pred(O, X, yb, "objective=binary", 20, weight=w)
+    np.testing.assert_allclose(got, h.decision_function(X), rtol=0, atol=1e-10)      # incl. the (weighted) log-odds init score
 
 
 def test_splittable_inheritance_is_the_only_structural_difference(O):
