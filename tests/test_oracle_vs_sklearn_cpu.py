@@ -71,7 +71,10 @@ def test_categorical_many_vs_many_matches_sklearn_hgb(O, ncat, iters):
     LightGBM `FindBestThresholdCategoricalInner`).  LightGBM-only rules are neutralised: cat_l2=0 (extra L2 of categorical gains),
     min_data_per_group=1, max_cat_to_onehot=1 (no one-vs-rest mode); max_cat_threshold=32 does not bind below 64 categories.
     Agreement is exact (0.0) — this pins the ctr order, the two scan directions, the category bitsets in the model and their use at
-    prediction time against an implementation that shares no code or author with the oracle."""
+    prediction time against an implementation that shares no code or author with the oracle.
+    (60 categories are run for 5 iterations only: sklearn scans (n_used + 1) // 2 - 1 prefixes in the backward direction where LightGBM
+    scans (n_used + 1) / 2 in both, and at iteration 10 a leaf with 57 used categories has its best split at exactly the 29th backward
+    prefix — gain 966.53 vs sklearn's 963.71, re-derived by hand.)"""
     rng = np.random.default_rng(21)
     n, F = 20000, 8
     X = rng.integers(-20, 30, size=(n, F)).astype(np.float64)
